@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the sprs product path on B200.
+
+Metric (BASELINE.json): CSR SpMV f64 GFLOP/s and achieved fraction of the HBM roofline
+(2*nnz flops over 12*nnz + 8*n bytes), at 1/2/4/8 B200, beside the sprs CPU path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A "step" is one `y = A x` over the whole matrix (all ranks together).  The default
+workload is BASELINE config 5 -- the configuration the metric is quoted on: 10M x 10M
+R-MAT, ~100 nnz/row (~1e9 nnz, 12 GB, fits one GPU) -- at every N (strong scaling:
+contiguous nnz-balanced row blocks per rank, x replicated, all-gather of y).
+Other workloads: spmv_rand_1m (config 2), spmm_rand_1m_k64 (config 3),
+spgemm_rmat_500k (config 4).  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (kind, n, nnz_per_row, generator)
+    "spmv_rmat_10m": ("spmv", 10_000_000, 100, "rmat"),
+    "spmv_rand_1m": ("spmv", 1_000_000, 32, "rand"),
+    "spmm_rand_1m_k64": ("spmm", 1_000_000, 32, "rand"),
+    "spgemm_rmat_500k": ("spgemm", 500_000, 16, "rmat"),
+    # small variants for quick checks
+    "spmv_rmat_1m": ("spmv", 1_000_000, 100, "rmat"),
+}
+SEEDS = {"spmv_rmat_10m": 0x5EED0005, "spmv_rand_1m": 0x5EED0002, "spmm_rand_1m_k64": 0x5EED0002,
+         "spgemm_rmat_500k": 0x5EED0004, "spmv_rmat_1m": 0x5EED0005}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "50", "-i", str(self.device)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            if not (t0 - 0.05 <= ts <= t1 + 0.1):
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def nnz_balanced_bounds(indptr_t, nparts):
+    """Row boundaries so every part holds ~nnz/nparts non-zeros (binary search in indptr;
+    slice_outer-style contiguous blocks)."""
+    import torch
+    nnz = int(indptr_t[-1].item())
+    rows = indptr_t.numel() - 1
+    targets = torch.tensor([(nnz * g) // nparts for g in range(1, nparts)],
+                           device=indptr_t.device, dtype=indptr_t.dtype)
+    cuts = torch.searchsorted(indptr_t, targets).tolist() if nparts > 1 else []
+    return [0] + [min(max(int(c), 0), rows) for c in cuts] + [rows]
+
+
+def sample_rows_to_host(a, target_nnz, nblocks=8):
+    """A bounded sample of the SAME matrix for the CPU baseline: `nblocks` contiguous row
+    blocks spread over the matrix, ~target_nnz non-zeros in total, as one host CSR."""
+    import torch
+    ip = a.indptr.to(torch.int64)
+    n = a.rows
+    per = max(1, target_nnz // nblocks)
+    parts_ip, parts_ind, parts_dat, total, rows = [np.zeros(1, np.int64)], [], [], 0, 0
+    for b in range(nblocks):
+        r0 = (n * b) // nblocks
+        s = int(ip[r0])
+        r1 = int(torch.searchsorted(ip, torch.tensor([s + per], device=ip.device))[0])
+        r1 = max(r0 + 1, min(r1, (n * (b + 1)) // nblocks))
+        e = int(ip[r1])
+        parts_ip.append((ip[r0 + 1:r1 + 1] - s + total).cpu().numpy())
+        parts_ind.append(a.indices[s:e].cpu().numpy().view(np.uint32))
+        parts_dat.append(a.data[s:e].cpu().numpy())
+        total += e - s
+        rows += r1 - r0
+    return (np.concatenate(parts_ip).astype(np.uint32), np.concatenate(parts_ind),
+            np.concatenate(parts_dat), rows)
+
+
+def cpu_spmv_baseline(a, x_t, budget_nnz):
+    """Faithful CPU restatement (oracle port), 1 thread -- sprs SpMV is single-threaded
+     -- on a bounded sample of the same matrix; plus the all-cores row-chunked
+    extension, labelled as not in the reference."""
+    from oracle import oracle as O
+    hip, hind, hdat, rows = sample_rows_to_host(a, budget_nnz)
+    hx = x_t.cpu().numpy()
+    nnz = int(hip[-1])
+    y = np.zeros(rows)
+    O.mul_acc_mat_vec_csr(hip, hind, hdat, hx, y)  # warm-up (page-in)
+    ts = []
+    for _ in range(3):
+        y[:] = 0
+        t = time.perf_counter()
+        O.mul_acc_mat_vec_csr(hip, hind, hdat, hx, y)
+        ts.append(time.perf_counter() - t)
+    t1 = statistics.median(ts)
+    cores = O.num_procs()
+    ts = []
+    for _ in range(3):
+        y[:] = 0
+        t = time.perf_counter()
+        O.ext_spmv_csr_omp(hip, hind, hdat, hx, y, cores)
+        ts.append(time.perf_counter() - t)
+    tn = statistics.median(ts)
+    return {"value": 2.0 * nnz / t1 / 1e9, "unit": "GFLOP/s", "cores": 1, "kind": "port",
+            "sample": "%d rows / %d nnz of the same matrix (8 row blocks), 1 thread as in sprs "
+                      "(SpMV is single-threaded there), median of 3" % (rows, nnz),
+            "ext_all_cores": {"value": 2.0 * nnz / tn / 1e9, "cores": cores,
+                              "note": "OpenMP row-chunked extension -- NOT in the reference"},
+            "host_cores": cores}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the
+    Rust reference cannot be built here), on the box's host cores, same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kind, n, npr, gen = WORKLOADS[args.workload]
+    from oracle import oracle as O
+    # inputs: same generator as the GPU arm when a GPU is present, else a numpy stand-in
+    sample_nnz = 1 << 26
+    try:
+        import torch
+        import sprs_b200 as sp
+        from sprs_b200 import generate as G
+        ctx = sp.Context.default(0)
+        torch.cuda.set_device(0)
+        a = (G.rmat_csr if gen == "rmat" else G.rand_csr)(ctx, n, npr, seed=SEEDS[args.workload])
+        x = G.normal_vector(ctx, n)
+        hip, hind, hdat, rows = sample_rows_to_host(a, sample_nnz)
+        hx = x.cpu().numpy()
+        src = "device-generated matrix, 8 row blocks"
+        del a, x
+        torch.cuda.empty_cache()
+    except Exception as e:  # no GPU: uniform random sample of the same shape
+        rng = np.random.default_rng(SEEDS[args.workload])
+        rows = sample_nnz // npr
+        hind = rng.integers(0, n, size=rows * npr, dtype=np.uint32).reshape(rows, npr)
+        hind.sort(axis=1)
+        hind = hind.reshape(-1)
+        hip = (np.arange(rows + 1, dtype=np.uint64) * npr).astype(np.uint32)
+        hdat = rng.standard_normal(rows * npr)
+        hx = rng.standard_normal(n)
+        src = "numpy uniform stand-in (no GPU for the generator: %s)" % type(e).__name__
+    nnz = int(hip[-1])
+    y = np.zeros(rows)
+    for _ in range(args.warmup):
+        O.mul_acc_mat_vec_csr(hip, hind, hdat, hx, y)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.mul_acc_mat_vec_csr(hip, hind, hdat, hx, y)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = 2.0 * nnz / dt / 1e9
+    line = {"impl": "reference", "metric": "csr_spmv_f64_gflops", "value": val,
+            "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "n": n, "nnz_per_row": npr,
+                       "sample_nnz": nnz, "sample_rows": rows, "source": src},
+            "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": 1, "kind": "port",
+                             "sample": "%d nnz per step; sprs SpMV/SpMM are single-threaded "
+                                       "(SURVEY F6), so 1 thread IS all the threads the "
+                                       "reference path can use; host has %d cores" %
+                                       (nnz, O.num_procs())},
+            "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="spmv_rmat_10m", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import sprs_b200 as sp
+    from sprs_b200 import generate as G
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = sp.Context.default(local)
+    kind, n, npr, gen = WORKLOADS[args.workload]
+    if kind != "spmv":
+        from sprs_b200 import bench_other
+        return bench_other.run(args, ctx, kind, n, npr, gen, SEEDS[args.workload])
+    peaks, peak_src = measured_peaks()
+    hbm_peak = float(peaks["hbm_gbs"])
+
+    # ---- inputs, generated in HBM (every rank builds the same matrix, keeps its block)
+    t_gen = time.time()
+    full = (G.rmat_csr if gen == "rmat" else G.rand_csr)(ctx, n, npr, seed=SEEDS[args.workload])
+    nnz = full.nnz
+    x = G.normal_vector(ctx, n)
+    bounds = nnz_balanced_bounds(full.indptr, world)
+    r0, r1 = bounds[rank], bounds[rank + 1]
+    if world > 1:
+        a = full.slice_rows(r0, r1)
+    else:
+        a = full
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu_base = cpu_spmv_baseline(full, x, 1 << 27)
+    if world > 1:
+        del full
+        torch.cuda.empty_cache()
+    t_gen = time.time() - t_gen
+    y = torch.zeros(n, device=dev, dtype=torch.float64)
+    y_views = [y[bounds[g]:bounds[g + 1]] for g in range(world)]
+
+    def step():
+        G.spmv(ctx, a, x, y_views[rank])
+        if world > 1:
+            dist.all_gather(y_views, y_views[rank])
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    # ---- timed region: K steps, CUDA events on the launching stream, max over ranks
+    launches0 = ctx.launches
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+            torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    tw0 = time.time()
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    for i in range(args.steps):
+        evs[i][0].record()
+        G.spmv(ctx, a, x, y_views[rank])
+        evs[i][1].record()
+        if world > 1:
+            dist.all_gather(y_views, y_views[rank])
+        evs[i][2].record()
+    e_stop.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    tw1 = time.time()
+    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
+    launches = ctx.launches - launches0
+    total_ms = e_start.elapsed_time(e_stop)
+    kern_ms = [evs[i][0].elapsed_time(evs[i][1]) for i in range(args.steps)]
+    coll_ms = [evs[i][1].elapsed_time(evs[i][2]) for i in range(args.steps)]
+    t = torch.tensor([total_ms, statistics.mean(kern_ms), statistics.mean(coll_ms)],
+                     device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms_avg, coll_ms_avg = t.tolist()
+    ms_per_step = total_ms / args.steps
+
+    # ---- e2e: the reference-facing call with HOST buffers: `&A * &x` through the C ABI,
+    # x H2D from pinned memory and y D2H inside the timed region, every step.
+    import ctypes as C
+    rows_local = r1 - r0
+    hx = torch.empty(n, dtype=torch.float64).pin_memory()
+    hx.copy_(x)
+    hy = torch.empty(max(rows_local, 1), dtype=torch.float64).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step():
+        ctx.check(ctx.lib.sprs_b200_mul_mat_vec(ctx.h, a.mirror.h, C.c_void_p(hx.data_ptr()), n,
+                                                C.c_void_p(hy.data_ptr()), rows_local))
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    te = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+    # parity spot-check of the e2e result against the device-resident result
+    ok = bool(torch.equal(hy[:rows_local].to(dev), y_views[rank]))
+
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_extra and args.workload == "spmv_rmat_10m":
+        del a, full
+        torch.cuda.empty_cache()
+        extra = bench_small_spmv(ctx, G, hbm_peak, dev)
+
+    if rank == 0:
+        flops = 2.0 * nnz
+        alg_bytes = 12.0 * nnz + 8.0 * n
+        gflops = flops / (ms_per_step * 1e-3) / 1e9
+        # roofline of the dominant kernel (spmv_tile_kernel; the carry fix-up kernel rides in
+        # the same event pair and is < 0.5 % of it): algorithmic bytes this rank's launch
+        # moves / its mean duration.  Rank 0's block; blocks are nnz-balanced.
+        local_bytes = 12.0 * a_nnz_of(bounds, nnz, world) + 8.0 * (n / world)
+        achieved = local_bytes / (kern_ms_avg * 1e-3) / 1e9
+        line = {
+            "metric": "csr_spmv_f64_gflops", "value": gflops, "unit": "GFLOP/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "n": n, "nnz": nnz, "nnz_per_row": npr,
+                       "generator": gen, "index_bytes": 4, "partition": "nnz-balanced row blocks",
+                       "collective": "all_gather(y) NCCL" if world > 1 else "none",
+                       "l2_policy": "inputs (%.1f GB) exceed L2 (126 MB); no flush needed" %
+                                    (alg_bytes / 1e9),
+                       "gen_seconds": round(t_gen, 1)},
+            "achieved_hbm_frac": (alg_bytes / (ms_per_step * 1e-3) / 1e9) / (hbm_peak * world),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None,
+                         "kernel": "spmv_tile_kernel (+ spmv_fixup_kernel)",
+                         "kernel_ms": kern_ms_avg, "peak_source": peak_src,
+                         "algorithmic_bytes": "12*nnz + 8*rows per launch"},
+            "collective_ms": coll_ms_avg,
+            "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s",
+                    "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * n * world,
+                    "d2h_bytes_per_step": 8 * n, "api": "sprs_b200_mul_mat_vec (host x, y; "
+                    "A resident as a device mirror)", "matches_device_result": ok},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if cpu_base:
+            line["cpu_baseline"] = cpu_base
+        if extra:
+            line["extra"] = extra
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def a_nnz_of(bounds, nnz, world):
+    return nnz / world
+
+
+def bench_small_spmv(ctx, G, hbm_peak, dev):
+    """BASELINE config 2 (1M x 1M sprs-rand, 32 nnz/row), reported as an extra line item.
+    392 MB of inputs > L2, so no flush is needed between iterations."""
+    import torch
+    n = 1_000_000
+    a = G.rand_csr(ctx, n, n, 32, seed=0x5EED0002)
+    x = G.normal_vector(ctx, n)
+    y = torch.empty(n, device=dev, dtype=torch.float64)
+    for _ in range(5):
+        G.spmv(ctx, a, x, y)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = 50
+    e0.record()
+    for _ in range(k):
+        G.spmv(ctx, a, x, y)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / k
+    by = 12.0 * a.nnz + 8.0 * n
+    return {"spmv_rand_1m": {"nnz": a.nnz, "ms": ms, "gflops": 2.0 * a.nnz / ms / 1e6,
+                             "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / hbm_peak}}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,195 @@
+/* sprs_b200.h -- C ABI of the B200-native sprs product path.
+ *
+ * This is the drop-in boundary: exactly what a Rust `sprs-b200-sys` crate would
+ * bind (INTEGRATION.md shows the extern "C" block and the safe wrapper).  It
+ * follows the reference's own FFI conventions:
+ *   - raw-pointer CSR, plain scalars, explicit sizes, zero-based ("proper")
+ *     indptr expected from callers that slice -- the in-tree precedent is
+ *     `prod_nnz(a_rows,a_cols,b_cols,a_indptr*,a_indices*,a_data*,...)`
+ *     sprs-benches/src/eigen.cpp:5-29, declared sprs-benches/src/main.rs:27-42,
+ *     called with proper_indptr()/as_ptr() at main.rs:55-80;
+ *   - caller-owned host buffers borrowed for the call (sprs_suitesparse_camd/
+ *     src/lib.rs:39-51), library-owned opaque handles released by an explicit
+ *     *_free called from Rust `Drop` (the UMFPACK pattern,
+ *     suitesparse_umfpack_sys/src/umfpack_free_numeric.rs:3-6);
+ *   - `int` status returns, 0 = ok; the Rust side maps non-zero to
+ *     LinalgError::ThirdPartyError(code, msg) (sprs/src/errors.rs:70) and keeps
+ *     the reference's panics ("Dimension mismatch", "Storage mismatch") for
+ *     contract violations (prod.rs:114-118, 198-201, 283-286; smmp.rs:207).
+ *
+ * Scalars are f64 (BASELINE).  Host index arrays may be 4 or 8 bytes wide
+ * (u32/i32 or u64/usize/i64/isize -- signed types are valid because sprs
+ * structure checks guarantee non-negative values, sparse.rs:326-332); the
+ * device mirror always stores u32 indices and u32 (or u64 when nnz >= 2^32)
+ * indptr.  No call routes through a CPU implementation: if the device or the
+ * kernels are unavailable every entry point fails with SPRS_B200_ERR_CUDA.
+ */
+#ifndef SPRS_B200_H
+#define SPRS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sprs_b200_ctx sprs_b200_ctx;       /* one device + stream + scratch          */
+typedef struct sprs_b200_csmat sprs_b200_csmat;   /* device mirror of a CsMatBase           */
+typedef struct sprs_b200_spgemm sprs_b200_spgemm; /* state between symbolic and numeric     */
+
+/* sprs::CompressedStorage (sprs/src/sparse.rs:31-38) */
+enum { SPRS_B200_CSR = 0, SPRS_B200_CSC = 1 };
+
+/* status codes */
+enum {
+    SPRS_B200_OK = 0,
+    SPRS_B200_ERR_DIMENSION = 1,   /* "Dimension mismatch"  (prod.rs:114-116)            */
+    SPRS_B200_ERR_STORAGE = 2,     /* "Storage mismatch"    (prod.rs:118)                */
+    SPRS_B200_ERR_CUDA = 3,        /* CUDA runtime / launch failure; see last_error      */
+    SPRS_B200_ERR_NCCL = 4,
+    SPRS_B200_ERR_INDEX_RANGE = 5, /* "Index type is not large enough" (csmat.rs:1794)   */
+    SPRS_B200_ERR_ARGUMENT = 6,    /* null pointer, bad width, bad handle                */
+    SPRS_B200_ERR_STRUCTURE = 7,   /* indptr not monotone / index out of bounds          */
+    SPRS_B200_ERR_UNSUPPORTED = 8
+};
+
+int sprs_b200_version(void);
+
+/* ---- context -------------------------------------------------------------- */
+int sprs_b200_ctx_create(int device, sprs_b200_ctx** out);
+int sprs_b200_ctx_destroy(sprs_b200_ctx* ctx);
+/* message of the last failing call on this ctx (or of a failed ctx_create when ctx==NULL) */
+const char* sprs_b200_last_error(const sprs_b200_ctx* ctx);
+int sprs_b200_ctx_device(const sprs_b200_ctx* ctx);
+int sprs_b200_ctx_sm_count(const sprs_b200_ctx* ctx);
+int sprs_b200_ctx_synchronize(sprs_b200_ctx* ctx);
+
+/* ---- device mirror of CsMatBase{storage, nrows, ncols, indptr, indices, data}
+ *      (sprs/src/sparse.rs:94-109).  `indptr` has outer+1 entries and may be
+ *      non-zero-based (row-sliced view, indptr.rs:122-124): it is rebased on
+ *      upload, as proper_indptr() does (csmat.rs:919-921).  Widths in bytes.   */
+int sprs_b200_csmat_upload(sprs_b200_ctx* ctx, int storage, uint64_t rows, uint64_t cols,
+                           const void* indptr, int indptr_bytes, const void* indices,
+                           int index_bytes, const double* data, sprs_b200_csmat** out);
+/* Adopt device-resident arrays (u32, zero-based, 16-byte aligned) without copying; the
+ * caller keeps ownership and must keep them alive.  Used by generators / benchmarks. */
+int sprs_b200_csmat_from_device(sprs_b200_ctx* ctx, int storage, uint64_t rows, uint64_t cols,
+                                uint64_t nnz, const uint32_t* d_indptr,
+                                const uint32_t* d_indices, const double* d_data,
+                                sprs_b200_csmat** out);
+int sprs_b200_csmat_free(sprs_b200_csmat* m);
+int sprs_b200_csmat_storage(const sprs_b200_csmat* m);
+uint64_t sprs_b200_csmat_rows(const sprs_b200_csmat* m);
+uint64_t sprs_b200_csmat_cols(const sprs_b200_csmat* m);
+uint64_t sprs_b200_csmat_nnz(const sprs_b200_csmat* m);
+/* copy the mirror back to caller-allocated host arrays (outer+1, nnz, nnz entries) */
+int sprs_b200_csmat_download(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, void* indptr,
+                             int indptr_bytes, void* indices, int index_bytes, double* data);
+/* raw device pointers of the mirror (u32 indices; indptr u32 unless nnz >= 2^32) */
+int sprs_b200_csmat_device_arrays(const sprs_b200_csmat* m, const void** d_indptr,
+                                  int* indptr_bytes, const uint32_t** d_indices,
+                                  const double** d_data);
+/* CsMatBase::to_other_storage / raw::convert_mat_storage (csmat.rs:1405-1426,1782-1829):
+ * a new mirror with the other storage order, indices ascending per outer dim. */
+int sprs_b200_csmat_to_other_storage(sprs_b200_ctx* ctx, const sprs_b200_csmat* m,
+                                     sprs_b200_csmat** out);
+
+/* ---- sparse x dense vector, HOST buffers (copies are part of the call) --------
+ * prod::mul_acc_mat_vec_csr(mat, in_vec, res_vec)  prod.rs:103-127 : y += A x
+ * prod::mul_acc_mat_vec_csc                        prod.rs:74-99
+ * Errors: DIMENSION if x_len != cols or y_len != rows, STORAGE if wrong storage. */
+int sprs_b200_mul_acc_mat_vec_csr(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
+                                  const double* in_vec, uint64_t in_len, double* res_vec,
+                                  uint64_t res_len);
+int sprs_b200_mul_acc_mat_vec_csc(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
+                                  const double* in_vec, uint64_t in_len, double* res_vec,
+                                  uint64_t res_len);
+/* `&A * &x` (csmat.rs:2119-2160): y = A x into a caller-allocated zero-initialised-
+ * or-not buffer (y is overwritten; saves uploading the zeros the operator allocates). */
+int sprs_b200_mul_mat_vec(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, const double* x,
+                          uint64_t x_len, double* y, uint64_t y_len);
+
+/* ---- sparse x dense matrix, HOST buffers; rhs/out are ndarray views, strides in
+ * ELEMENTS (may be negative/any, like ArrayView).  out += lhs * rhs.
+ * prod::csr_mulacc_dense_rowmaj prod.rs:189-214 ; csr_mulacc_dense_colmaj :274-298
+ * prod::csc_mulacc_dense_rowmaj prod.rs:219-241 ; csc_mulacc_dense_colmaj :246-269  */
+int sprs_b200_csr_mulacc_dense_rowmaj(sprs_b200_ctx* ctx, const sprs_b200_csmat* lhs,
+                                      const double* rhs, uint64_t rhs_rows, uint64_t rhs_cols,
+                                      int64_t rhs_rs, int64_t rhs_cs, double* out,
+                                      uint64_t out_rows, uint64_t out_cols, int64_t out_rs,
+                                      int64_t out_cs);
+int sprs_b200_csr_mulacc_dense_colmaj(sprs_b200_ctx* ctx, const sprs_b200_csmat* lhs,
+                                      const double* rhs, uint64_t rhs_rows, uint64_t rhs_cols,
+                                      int64_t rhs_rs, int64_t rhs_cs, double* out,
+                                      uint64_t out_rows, uint64_t out_cols, int64_t out_rs,
+                                      int64_t out_cs);
+int sprs_b200_csc_mulacc_dense_rowmaj(sprs_b200_ctx* ctx, const sprs_b200_csmat* lhs,
+                                      const double* rhs, uint64_t rhs_rows, uint64_t rhs_cols,
+                                      int64_t rhs_rs, int64_t rhs_cs, double* out,
+                                      uint64_t out_rows, uint64_t out_cols, int64_t out_rs,
+                                      int64_t out_cs);
+int sprs_b200_csc_mulacc_dense_colmaj(sprs_b200_ctx* ctx, const sprs_b200_csmat* lhs,
+                                      const double* rhs, uint64_t rhs_rows, uint64_t rhs_cols,
+                                      int64_t rhs_rs, int64_t rhs_cs, double* out,
+                                      uint64_t out_rows, uint64_t out_cols, int64_t out_rs,
+                                      int64_t out_cs);
+
+/* ---- device-resident entry points (x, y, B, C already in HBM; `stream` is a
+ * cudaStream_t passed as void*, NULL = the ctx stream).  Asynchronous: they return
+ * after enqueueing.  accumulate != 0 : y += A x ; == 0 : y = A x.
+ * The matrix must be CSR (convert a CSC mirror with csmat_to_other_storage).     */
+int sprs_b200_spmv_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, const double* d_x,
+                       double* d_y, int accumulate, void* stream);
+/* C(rows x k) (+)= A * B(cols x k); B, C row-major with leading dimensions ldb, ldc
+ * (csr_mulacc_dense_rowmaj on contiguous C-order operands, csmat.rs:2010-2018).  */
+int sprs_b200_spmm_rowmaj_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, const double* d_b,
+                              uint64_t ldb, uint64_t k, double* d_c, uint64_t ldc,
+                              int accumulate, void* stream);
+/* number of kernel launches the library has issued on this ctx (all entry points) */
+uint64_t sprs_b200_launch_count(const sprs_b200_ctx* ctx);
+
+/* ---- sparse x sparse: smmp::mul_csr_csr (smmp.rs:196-237), two calls so the
+ * CALLER allocates the output Vecs, like symbolic -> numeric (smmp.rs:81,151).
+ * symbolic: pattern of C = A*B; returns a plan and nnz(C).
+ * numeric : fills caller arrays: indptr (A.rows+1), indices (nnzC, ascending per
+ *           row, structural zeros kept -- smmp.rs:109-129), data (nnzC).
+ * Both operands must be CSR with A.cols == B.rows (else DIMENSION / STORAGE).     */
+int sprs_b200_spgemm_symbolic(sprs_b200_ctx* ctx, const sprs_b200_csmat* a,
+                              const sprs_b200_csmat* b, sprs_b200_spgemm** plan,
+                              uint64_t* nnz_c);
+int sprs_b200_spgemm_numeric(sprs_b200_ctx* ctx, sprs_b200_spgemm* plan, void* c_indptr,
+                             int indptr_bytes, void* c_indices, int index_bytes,
+                             double* c_data);
+/* same, leaving C on the device as a new mirror (plan may then be freed) */
+int sprs_b200_spgemm_numeric_dev(sprs_b200_ctx* ctx, sprs_b200_spgemm* plan,
+                                 sprs_b200_csmat** c);
+/* work counters of a plan: n_prod = sum_i sum_{k in A_i} nnz(B_k) */
+uint64_t sprs_b200_spgemm_nprod(const sprs_b200_spgemm* plan);
+int sprs_b200_spgemm_free(sprs_b200_spgemm* plan);
+
+/* ---- synthetic inputs, generated in HBM (sprs-rand/src/lib.rs:24-81
+ * gives the uniform distribution; R-MAT is this repo's definition).  Each writes
+ * `count` 64-bit keys (row<<32 | col) for candidate edges [first, first+count);
+ * rejected candidates (index >= n) get key UINT64_MAX.  Sorting/dedup is the
+ * caller's job (bench plumbing).                                                  */
+int sprs_b200_gen_rmat_keys(sprs_b200_ctx* ctx, uint64_t seed, int scale, uint64_t n_rows,
+                            uint64_t n_cols, double a, double b, double c, uint64_t first,
+                            uint64_t count, uint64_t* d_keys, void* stream);
+int sprs_b200_gen_uniform_keys(sprs_b200_ctx* ctx, uint64_t seed, uint64_t n_rows,
+                               uint64_t n_cols, uint64_t first, uint64_t count,
+                               uint64_t* d_keys, void* stream);
+/* N(0,1) value per key (hash of key and seed): partition independent */
+int sprs_b200_gen_normal_from_keys(sprs_b200_ctx* ctx, uint64_t seed, const uint64_t* d_keys,
+                                   uint64_t count, double* d_out, void* stream);
+/* split sorted unique keys into u32 row / col arrays (row optional) */
+int sprs_b200_gen_split_keys(sprs_b200_ctx* ctx, const uint64_t* d_keys, uint64_t count,
+                             uint32_t* d_rows, uint32_t* d_cols, void* stream);
+/* 64-bit mix of each key (for thinning to an exact nnz) */
+int sprs_b200_gen_hash_keys(sprs_b200_ctx* ctx, uint64_t seed, const uint64_t* d_keys,
+                            uint64_t count, uint64_t* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPRS_B200_H */

@@ -1,0 +1,80 @@
+"""ctypes binding of libsprs_b200.so -- the same C ABI (include/sprs_b200.h) a Rust
+`sprs-b200-sys` crate binds.  Loading fails loudly when the library is missing:
+there is no CPU fallback anywhere in this package."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsprs_b200.so")
+
+OK, ERR_DIMENSION, ERR_STORAGE, ERR_CUDA, ERR_NCCL, ERR_INDEX_RANGE, ERR_ARGUMENT, \
+    ERR_STRUCTURE, ERR_UNSUPPORTED = range(9)
+CSR, CSC = 0, 1
+
+_vp, _u64, _i64, _int, _dp = C.c_void_p, C.c_uint64, C.c_int64, C.c_int, C.c_void_p
+_dense_sig = [_vp, _vp, _dp, _u64, _u64, _i64, _i64, _dp, _u64, _u64, _i64, _i64]
+
+# name -> (restype, argtypes); one entry per symbol declared in include/sprs_b200.h
+PROTOTYPES = {
+    "sprs_b200_version": (_int, []),
+    "sprs_b200_ctx_create": (_int, [_int, C.POINTER(_vp)]),
+    "sprs_b200_ctx_destroy": (_int, [_vp]),
+    "sprs_b200_last_error": (C.c_char_p, [_vp]),
+    "sprs_b200_ctx_device": (_int, [_vp]),
+    "sprs_b200_ctx_sm_count": (_int, [_vp]),
+    "sprs_b200_ctx_synchronize": (_int, [_vp]),
+    "sprs_b200_csmat_upload": (_int, [_vp, _int, _u64, _u64, _vp, _int, _vp, _int, _dp,
+                                      C.POINTER(_vp)]),
+    "sprs_b200_csmat_from_device": (_int, [_vp, _int, _u64, _u64, _u64, _vp, _vp, _vp,
+                                           C.POINTER(_vp)]),
+    "sprs_b200_csmat_free": (_int, [_vp]),
+    "sprs_b200_csmat_storage": (_int, [_vp]),
+    "sprs_b200_csmat_rows": (_u64, [_vp]),
+    "sprs_b200_csmat_cols": (_u64, [_vp]),
+    "sprs_b200_csmat_nnz": (_u64, [_vp]),
+    "sprs_b200_csmat_download": (_int, [_vp, _vp, _vp, _int, _vp, _int, _dp]),
+    "sprs_b200_csmat_device_arrays": (_int, [_vp, C.POINTER(_vp), C.POINTER(_int),
+                                             C.POINTER(_vp), C.POINTER(_vp)]),
+    "sprs_b200_csmat_to_other_storage": (_int, [_vp, _vp, C.POINTER(_vp)]),
+    "sprs_b200_mul_acc_mat_vec_csr": (_int, [_vp, _vp, _dp, _u64, _dp, _u64]),
+    "sprs_b200_mul_acc_mat_vec_csc": (_int, [_vp, _vp, _dp, _u64, _dp, _u64]),
+    "sprs_b200_mul_mat_vec": (_int, [_vp, _vp, _dp, _u64, _dp, _u64]),
+    "sprs_b200_csr_mulacc_dense_rowmaj": (_int, _dense_sig),
+    "sprs_b200_csr_mulacc_dense_colmaj": (_int, _dense_sig),
+    "sprs_b200_csc_mulacc_dense_rowmaj": (_int, _dense_sig),
+    "sprs_b200_csc_mulacc_dense_colmaj": (_int, _dense_sig),
+    "sprs_b200_spmv_dev": (_int, [_vp, _vp, _dp, _dp, _int, _vp]),
+    "sprs_b200_spmm_rowmaj_dev": (_int, [_vp, _vp, _dp, _u64, _u64, _dp, _u64, _int, _vp]),
+    "sprs_b200_launch_count": (_u64, [_vp]),
+    "sprs_b200_spgemm_symbolic": (_int, [_vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_u64)]),
+    "sprs_b200_spgemm_numeric": (_int, [_vp, _vp, _vp, _int, _vp, _int, _dp]),
+    "sprs_b200_spgemm_numeric_dev": (_int, [_vp, _vp, C.POINTER(_vp)]),
+    "sprs_b200_spgemm_nprod": (_u64, [_vp]),
+    "sprs_b200_spgemm_free": (_int, [_vp]),
+    "sprs_b200_gen_rmat_keys": (_int, [_vp, _u64, _int, _u64, _u64, C.c_double, C.c_double,
+                                       C.c_double, _u64, _u64, _vp, _vp]),
+    "sprs_b200_gen_uniform_keys": (_int, [_vp, _u64, _u64, _u64, _u64, _u64, _vp, _vp]),
+    "sprs_b200_gen_normal_from_keys": (_int, [_vp, _u64, _vp, _u64, _vp, _vp]),
+    "sprs_b200_gen_split_keys": (_int, [_vp, _vp, _u64, _vp, _vp, _vp]),
+    "sprs_b200_gen_hash_keys": (_int, [_vp, _u64, _vp, _u64, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libsprs_b200.so and attach prototypes.  Raises (never falls back)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libsprs_b200.so is not built (%s): run `python -c 'import __graft_entry__ as g; "
+            "g.build()'` or `make -C sprs_b200/csrc`.  sprs_b200 has no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

@@ -1,0 +1,99 @@
+// common.cuh -- internal types shared by the sm_100a kernels and the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/sprs_b200.h"
+
+// ---- error plumbing: C functions return int, never throw/abort ----
+struct sprs_b200_ctx {
+    int device = 0;
+    int sm_count = 148;
+    size_t l2_bytes = 0;
+    cudaStream_t stream = nullptr;  // used when the caller passes stream == NULL
+    std::string last_error;
+    uint64_t launches = 0;
+    // pinned host staging + device scratch for the host-buffer entry points
+    void* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    void* d_scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t d_scratch_bytes[4] = {0, 0, 0, 0};
+};
+
+struct sprs_b200_csmat {
+    sprs_b200_ctx* ctx = nullptr;
+    int storage = SPRS_B200_CSR;
+    uint64_t rows = 0, cols = 0, nnz = 0;
+    uint64_t outer = 0, inner = 0;
+    int indptr_bytes = 4;          // 4 unless nnz >= 2^32
+    void* d_indptr = nullptr;      // outer+1 entries
+    uint32_t* d_indices = nullptr; // nnz entries
+    double* d_data = nullptr;      // nnz entries
+    bool owns = true;              // false for from_device adoption
+    // SpMV partition (built lazily, see spmv.cu): tile_row[t] = first outer index whose
+    // end lies beyond nnz position t*TILE; n_tiles+1 entries.  carry: n_tiles doubles.
+    uint32_t* d_tile_row = nullptr;
+    double* d_carry = nullptr;
+    uint64_t n_tiles = 0;
+};
+
+#define SPRS_FAIL(ctx, code, ...)                                  \
+    do {                                                           \
+        char _buf[512];                                            \
+        snprintf(_buf, sizeof(_buf), __VA_ARGS__);                 \
+        sprs_b200_set_error((ctx), _buf);                          \
+        return (code);                                             \
+    } while (0)
+
+#define SPRS_CUDA(ctx, expr)                                                              \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess)                                                            \
+            SPRS_FAIL((ctx), SPRS_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,          \
+                      cudaGetErrorString(_e), __FILE__, __LINE__);                        \
+    } while (0)
+
+#define SPRS_TRY(expr)                      \
+    do {                                    \
+        int _s = (expr);                    \
+        if (_s != SPRS_B200_OK) return _s;  \
+    } while (0)
+
+void sprs_b200_set_error(const sprs_b200_ctx* ctx, const char* msg);
+
+static inline cudaStream_t pick_stream(sprs_b200_ctx* ctx, void* stream) {
+    return stream ? (cudaStream_t)stream : ctx->stream;
+}
+
+// scratch slot `i` of at least `bytes` (grown geometrically, contents undefined)
+int ctx_scratch(sprs_b200_ctx* ctx, int i, size_t bytes, void** out);
+int ctx_stage(sprs_b200_ctx* ctx, size_t bytes, void** out);
+
+// ---- kernels' launch wrappers (defined in the .cu files) -----------------------
+int spmv_prepare(sprs_b200_ctx* ctx, sprs_b200_csmat* m, cudaStream_t s);
+int spmv_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x, double* d_y,
+                int accumulate, cudaStream_t s);
+int spmm_rowmaj_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_b,
+                       uint64_t ldb, uint64_t k, double* d_c, uint64_t ldc, int accumulate,
+                       cudaStream_t s);
+int transpose_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, sprs_b200_csmat* out,
+                     cudaStream_t s);
+int exclusive_scan_u32_to_u64(sprs_b200_ctx* ctx, const uint32_t* d_in, uint64_t n,
+                              uint64_t* d_out /* n+1 */, cudaStream_t s);
+
+// ---- small device helpers -----------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {  // splitmix64 finaliser
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+#endif
