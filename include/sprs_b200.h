@@ -136,8 +136,8 @@ int sprs_b200_csc_mulacc_dense_colmaj(sprs_b200_ctx* ctx, const sprs_b200_csmat*
                                       int64_t out_cs);
 
 /* ---- device-resident entry points (x, y, B, C already in HBM; `stream` is a
- * cudaStream_t passed as void*, NULL = the ctx stream).  Asynchronous: they return
- * after enqueueing.  accumulate != 0 : y += A x ; == 0 : y = A x.
+ * cudaStream_t passed as void*; NULL is CUDA's legacy default stream, as usual).
+ * Asynchronous: they return after enqueueing.  accumulate != 0 : y += A x ; == 0 : y = A x.
  * The matrix must be CSR (convert a CSC mirror with csmat_to_other_storage).     */
 int sprs_b200_spmv_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, const double* d_x,
                        double* d_y, int accumulate, void* stream);

@@ -14,7 +14,7 @@ struct sprs_b200_ctx {
     int device = 0;
     int sm_count = 148;
     size_t l2_bytes = 0;
-    cudaStream_t stream = nullptr;  // used when the caller passes stream == NULL
+    cudaStream_t stream = nullptr;  // private stream of the host-buffer entry points
     std::string last_error;
     uint64_t launches = 0;
     // pinned host staging + device scratch for the host-buffer entry points
@@ -65,8 +65,10 @@ struct sprs_b200_csmat {
 
 void sprs_b200_set_error(const sprs_b200_ctx* ctx, const char* msg);
 
-static inline cudaStream_t pick_stream(sprs_b200_ctx* ctx, void* stream) {
-    return stream ? (cudaStream_t)stream : ctx->stream;
+// Device-resident entry points run on exactly the stream they are given; NULL is the
+// CUDA legacy default stream (that is what torch's default stream is), NOT ctx->stream.
+static inline cudaStream_t pick_stream(sprs_b200_ctx*, void* stream) {
+    return (cudaStream_t)stream;
 }
 
 // scratch slot `i` of at least `bytes` (grown geometrically, contents undefined)
