@@ -90,6 +90,10 @@ int sprs_b200_csmat_download(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, void*
 int sprs_b200_csmat_device_arrays(const sprs_b200_csmat* m, const void** d_indptr,
                                   int* indptr_bytes, const uint32_t** d_indices,
                                   const double** d_data);
+/* check_compressed_structure (sprs/src/sparse.rs:300-369) on the device: counts outer
+ * dims with a decreasing indptr, an out-of-range index or non-ascending indices. */
+int sprs_b200_csmat_check_structure(sprs_b200_ctx* ctx, const sprs_b200_csmat* m,
+                                    uint64_t* n_violations);
 /* CsMatBase::to_other_storage / raw::convert_mat_storage (csmat.rs:1405-1426,1782-1829):
  * a new mirror with the other storage order, indices ascending per outer dim. */
 int sprs_b200_csmat_to_other_storage(sprs_b200_ctx* ctx, const sprs_b200_csmat* m,

@@ -23,6 +23,25 @@ __global__ void convert_rebase_kernel(const Src* __restrict__ in, Dst* __restric
 
 inline unsigned grid_for(uint64_t n) { return (unsigned)((n + 255) / 256); }
 
+template <typename P>
+__global__ void check_structure_kernel(const P* __restrict__ indptr,
+                                       const uint32_t* __restrict__ indices, uint64_t outer,
+                                       uint64_t inner, unsigned long long* __restrict__ bad) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t w0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = w0; r < outer; r += nw) {  // one warp per outer dimension
+        const uint64_t s = indptr[r], e = indptr[r + 1];
+        bool viol = e < s;
+        if (!viol)
+            for (uint64_t k = s + lane; k < e; k += 32) {
+                const uint32_t c = indices[k];
+                if (c >= inner || (k > s && indices[k - 1] >= c)) viol = true;
+            }
+        if (__any_sync(0xffffffffu, viol) && lane == 0) atomicAdd(bad, 1ull);
+    }
+}
+
 int upload_indexlike(sprs_b200_ctx* ctx, const void* host, int host_bytes, uint64_t n,
                      uint64_t base, void* d_out, int dev_bytes, cudaStream_t s) {
     if (n == 0) return SPRS_B200_OK;
@@ -341,6 +360,32 @@ int sprs_b200_csmat_device_arrays(const sprs_b200_csmat* m, const void** d_indpt
     if (indptr_bytes) *indptr_bytes = m->indptr_bytes;
     if (d_indices) *d_indices = m->d_indices;
     if (d_data) *d_data = m->d_data;
+    return SPRS_B200_OK;
+}
+
+int sprs_b200_csmat_check_structure(sprs_b200_ctx* ctx, const sprs_b200_csmat* m,
+                                    uint64_t* n_violations) {
+    if (!ctx || !m || !n_violations) return SPRS_B200_ERR_ARGUMENT;
+    SPRS_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    void* d_bad = nullptr;
+    SPRS_TRY(ctx_scratch(ctx, 0, 8, &d_bad));
+    SPRS_CUDA(ctx, cudaMemsetAsync(d_bad, 0, 8, s));
+    if (m->outer) {
+        const unsigned g = (unsigned)std::min<uint64_t>((m->outer + 7) / 8,
+                                                        (uint64_t)ctx->sm_count * 32);
+        if (m->indptr_bytes == 4)
+            check_structure_kernel<uint32_t><<<g, 256, 0, s>>>(
+                (const uint32_t*)m->d_indptr, m->d_indices, m->outer, m->inner,
+                (unsigned long long*)d_bad);
+        else
+            check_structure_kernel<uint64_t><<<g, 256, 0, s>>>(
+                (const uint64_t*)m->d_indptr, m->d_indices, m->outer, m->inner,
+                (unsigned long long*)d_bad);
+        ctx->launches += 1;
+    }
+    SPRS_CUDA(ctx, cudaMemcpyAsync(n_violations, d_bad, 8, cudaMemcpyDeviceToHost, s));
+    SPRS_CUDA(ctx, cudaStreamSynchronize(s));
     return SPRS_B200_OK;
 }
 

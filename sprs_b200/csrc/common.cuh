@@ -84,8 +84,6 @@ int spmm_rowmaj_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const doubl
                        cudaStream_t s);
 int transpose_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, sprs_b200_csmat* out,
                      cudaStream_t s);
-int exclusive_scan_u32_to_u64(sprs_b200_ctx* ctx, const uint32_t* d_in, uint64_t n,
-                              uint64_t* d_out /* n+1 */, cudaStream_t s);
 
 // ---- small device helpers -----------------------------------------------------
 #ifdef __CUDACC__

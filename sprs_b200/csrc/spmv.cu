@@ -4,43 +4,51 @@
 // one-column case of prod::csr_mulacc_dense_colmaj (prod.rs:274-298), which is what
 // `&A * &x` runs (sprs/src/sparse/csmat.rs:2142-2148).
 //
-// Design (DESIGN.md "SpMV"): the nnz stream is cut into fixed tiles of SPMV_TILE
-// non-zeros (not rows), so every CTA streams the same number of bytes whatever the
-// row-length distribution (R-MAT rows are heavily skewed).  Per tile:
-//   1. one elected thread issues two 1-D TMA bulk copies (cp.async.bulk ->
-//      SASS UBLKCP) that land the tile's `data` (16 KB) and `indices` (8 KB) in
-//      shared memory, completion on an mbarrier; L2 policy evict_first because the
-//      matrix is streamed exactly once;
-//   2. phase A: every thread gathers x[col] for 8 non-zeros (L2 policy evict_last:
-//      x is the only re-used operand), multiplies (unfused, like MulAcc::mul_acc,
-//      mul_acc.rs:28-30) and writes the products back to shared memory.  The
-//      L1TEX/LSU pipe carries only the gathers -- the matrix stream bypasses it;
-//   3. phase B: the rows that END in this tile are reduced from shared memory by
-//      lane groups of G = 1..32 lanes (G picked per tile from its mean row length,
-//      very long rows go through a per-tile warp queue), and y is written once.
-//      The row that continues into the next tile leaves its partial in carry[t].
+// Design (DESIGN.md "SpMV"): the nnz stream is cut into fixed tiles of WT non-zeros
+// (not rows), so every tile streams the same number of bytes whatever the row-length
+// distribution (R-MAT rows are heavily skewed).  A tile belongs to ONE WARP; warps are
+// persistent and autonomous (no CTA-wide barrier anywhere), each running a private
+// STAGES-deep TMA pipeline:
+//   1. lane 0 issues two 1-D TMA bulk copies per tile (cp.async.bulk -> SASS UBLKCP)
+//      that land the tile's `data` and `indices` in the warp's shared-memory stage,
+//      completion on a per-stage mbarrier; L2 policy evict_first (the matrix is
+//      streamed exactly once), issued STAGES tiles ahead;
+//   2. phase A: every lane gathers x[col] for WT/32 non-zeros (all loads in flight
+//      before the first use; L2 policy evict_last: x is the only re-used operand),
+//      multiplies (unfused, like MulAcc::mul_acc, mul_acc.rs:28-30) and writes the
+//      products back to the stage;
+//   3. phase B: the rows that END in this tile are reduced from shared memory by lane
+//      groups of G = 1..32 lanes (G picked per tile from its mean row length; row
+//      boundaries are prefetched into registers before the TMA wait), and y is written
+//      once.  The row that continues into the next tile leaves its partial in carry[t];
 //   4. a second tiny kernel adds the carries in tile order (deterministic, no atomics).
-// Rows of <= 6 nnz-per-row tiles are summed by one thread in storage order, i.e.
-// bit-identical to the reference's sequential sum; longer rows use a tree and agree
-// to rounding (parity gate: |d| <= 1e-6 * sum|terms|).
+// Because the warps drift apart, gathers (L1TEX-bound), shared-memory reductions and
+// TMA waits of different warps overlap instead of alternating in CTA-wide phases
+// (profiles/r1_spmv_notes.md: the first CTA-tile version sat at 44 % L1TEX utilisation
+// with barrier + MIO-throttle stalls).
+// Rows inside tiles whose mean row length is <= 6 are summed by one lane in storage
+// order, i.e. bit-identical to the reference's sequential sum; longer rows use a tree
+// and agree to rounding (parity gate: |d| <= 1e-6 * sum|terms|).
 //
 // Algorithmic bytes per nnz: 12 (8 data + 4 index) + 8 per row (y) -- the
 // BASELINE roofline 12*nnz + 8*n; indptr (4 B/row) and x gathers are overhead.
 
 #include "common.cuh"
 
-namespace {
+#include <cstdlib>
 
-constexpr int SPMV_TILE = 2048;  // nnz per tile: 24 KB of shared memory
-constexpr int SPMV_NT = 256;     // threads per CTA: 8 gathers in flight per thread
-constexpr int SPMV_EPT = SPMV_TILE / SPMV_NT;
-constexpr int SPMV_QCAP = SPMV_TILE / 32 + 1;
+namespace {
 
 // ---- PTX wrappers: mbarrier + 1-D TMA bulk copy + L2 cache policies -------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)
                  : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
@@ -84,10 +92,10 @@ __device__ __forceinline__ double ldg_f64_hint(const double* p, uint64_t policy)
     return v;
 }
 
-// ---- partition: tile_row[t] = first row whose end lies beyond nnz position t*TILE
+// ---- partition: tile_row[t] = first row whose end lies beyond nnz position t*wt
 template <typename P>
 __global__ void tile_row_kernel(const P* __restrict__ indptr, uint32_t rows, uint64_t n_tiles,
-                                uint32_t* __restrict__ tile_row) {
+                                uint32_t wt, uint32_t* __restrict__ tile_row) {
     const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (t > n_tiles) return;
     if (t == 0) {
@@ -98,7 +106,7 @@ __global__ void tile_row_kernel(const P* __restrict__ indptr, uint32_t rows, uin
         tile_row[t] = rows;  // trailing empty rows belong to the last tile
         return;
     }
-    const uint64_t k0 = t * (uint64_t)SPMV_TILE;
+    const uint64_t k0 = t * (uint64_t)wt;
     uint32_t lo = 0, hi = rows;  // first r with indptr[r+1] > k0
     while (lo < hi) {
         const uint32_t mid = lo + (hi - lo) / 2;
@@ -126,138 +134,163 @@ __device__ __forceinline__ void emit_row(const TileCtx& tc, uint64_t r, double s
     }
 }
 
+// Reduce rows [r0, r_last] of one warp tile with groups of G lanes per row.  Row
+// boundaries come 31 rows at a time: lane L holds indptr[rbase + L].
 template <typename P, int G>
-__device__ __forceinline__ void reduce_rows(const TileCtx& tc, const P* __restrict__ indptr,
-                                            const double* sprod, uint32_t r0, uint64_t r_last,
-                                            int* qcount, uint32_t* qrow, int* qs, int* qe) {
-    constexpr int NG = SPMV_NT / G;
-    const int gid = threadIdx.x / G, gl = threadIdx.x % G;
-    for (uint64_t base = r0; base <= r_last; base += NG) {
-        const uint64_t r = base + gid;
-        const bool valid = r <= r_last;
-        int ls = 0, le = 0;
-        if (valid) {
-            uint64_t s = (uint64_t)indptr[r], e = (uint64_t)indptr[r + 1];
+__device__ __forceinline__ void reduce_rows_warp(const TileCtx& tc, const P* __restrict__ indptr,
+                                                 const double* sprod, uint32_t r0,
+                                                 uint64_t r_last, uint64_t b_first, int lane) {
+    constexpr int NG = 32 / G;
+    const int gid = lane / G, gl = lane % G;
+    uint64_t b = b_first;  // boundaries of the first chunk were prefetched by the caller
+    for (uint64_t rbase = r0; rbase <= r_last; rbase += 31) {
+        if (rbase != r0) {
+            const uint64_t rr = rbase + lane;
+            b = rr <= r_last + 1 ? (uint64_t)indptr[rr] : 0;
+        }
+        const int nrows = (r_last - rbase + 1) < 31 ? (int)(r_last - rbase + 1) : 31;
+        for (int j0 = 0; j0 < nrows; j0 += NG) {
+            const int j = j0 + gid;
+            const bool valid = j < nrows;
+            const int js = valid ? j : 0;
+            uint64_t s = __shfl_sync(0xffffffffu, b, js);
+            uint64_t e = __shfl_sync(0xffffffffu, b, js + 1);
+            int ls = 0, le = 0;
             s = s > tc.k0 ? s : tc.k0;
             e = e < tc.k1 ? e : tc.k1;
-            if (e > s) {
+            if (valid && e > s) {
                 ls = (int)(s - tc.k0);
                 le = (int)(e - tc.k0);
             }
-        }
-        const bool is_long = (le - ls) > 32 * G;
-        double acc = 0.0;
-        if (!is_long) {
-            for (int j = ls + gl; j < le; j += G) acc = __dadd_rn(acc, sprod[j]);
-        }
+            const bool is_long = (G < 32) && (le - ls) > 16 * G;
+            double acc = 0.0;
+            if (!is_long)
+                for (int q = ls + gl; q < le; q += G) acc = __dadd_rn(acc, sprod[q]);
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1)
-            acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-        if (gl == 0 && valid) {
-            if (is_long) {
-                const int q = atomicAdd(qcount, 1);
-                qrow[q] = (uint32_t)r;
-                qs[q] = ls;
-                qe[q] = le;
-            } else {
-                emit_row(tc, r, acc);
+            for (int o = G / 2; o > 0; o >>= 1)
+                acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+            if (gl == 0 && valid && !is_long) emit_row(tc, rbase + j, acc);
+            if (G < 32) {  // rows too long for their group: the whole warp takes them
+                unsigned pending = __ballot_sync(0xffffffffu, gl == 0 && valid && is_long);
+                while (pending) {
+                    const int src = __ffs(pending) - 1;
+                    pending &= pending - 1;
+                    const int qs = __shfl_sync(0xffffffffu, ls, src);
+                    const int qe = __shfl_sync(0xffffffffu, le, src);
+                    const int jj = __shfl_sync(0xffffffffu, j, src);
+                    double a2 = 0.0;
+                    for (int q = qs + lane; q < qe; q += 32) a2 = __dadd_rn(a2, sprod[q]);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+                        a2 = __dadd_rn(a2, __shfl_xor_sync(0xffffffffu, a2, o));
+                    if (lane == 0) emit_row(tc, rbase + jj, a2);
+                }
             }
         }
     }
 }
 
-template <typename P>
-__global__ void __launch_bounds__(SPMV_NT)
-    spmv_tile_kernel(const P* __restrict__ indptr, const uint32_t* __restrict__ indices,
+template <typename P, int WT, int STAGES, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32)
+    spmv_warp_kernel(const P* __restrict__ indptr, const uint32_t* __restrict__ indices,
                      const double* __restrict__ data, const uint32_t* __restrict__ tile_row,
                      const double* __restrict__ x, double* __restrict__ y,
-                     double* __restrict__ carry, uint64_t nnz, uint32_t rows, int accumulate) {
-    __shared__ __align__(128) double sprod[SPMV_TILE];
-    __shared__ __align__(128) uint32_t sidx[SPMV_TILE];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ int qcount;
-    __shared__ uint32_t qrow[SPMV_QCAP];
-    __shared__ int qs[SPMV_QCAP], qe[SPMV_QCAP];
-
-    const int tid = threadIdx.x;
-    const uint64_t t = blockIdx.x;
-    const uint64_t k0 = t * (uint64_t)SPMV_TILE;
-    const uint64_t k1 = (k0 + SPMV_TILE < nnz) ? k0 + SPMV_TILE : nnz;
-    const int cnt = (int)(k1 - k0);
-    const bool full = cnt == SPMV_TILE;
-
-    if (tid == 0) {
-        qcount = 0;
-        if (full) mbar_init(&bar, 1);
-    }
-    __syncthreads();
-    if (full) {
-        if (tid == 0) {
-            const uint64_t pol = policy_evict_first();
-            mbar_expect_tx(&bar, SPMV_TILE * 12);
-            bulk_g2s(sprod, data + k0, SPMV_TILE * 8, &bar, pol);
-            bulk_g2s(sidx, indices + k0, SPMV_TILE * 4, &bar, pol);
-        }
-    } else {  // ragged last tile: guarded loads (no out-of-bounds bulk copy)
-        for (int e = tid; e < cnt; e += SPMV_NT) {
-            sprod[e] = data[k0 + e];
-            sidx[e] = indices[k0 + e];
-        }
-    }
-    const uint32_t r0 = tile_row[t], r1 = tile_row[t + 1];  // overlaps the TMA flight
+                     double* __restrict__ carry, uint64_t nnz, uint32_t rows, uint64_t n_tiles,
+                     int accumulate) {
+    constexpr int EPL = WT / 32;               // non-zeros per lane per tile
+    constexpr int STAGE_BYTES = WT * 12;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bars[NWARPS][STAGES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wsm = smem_raw + (size_t)warp * STAGES * STAGE_BYTES;
+    const uint64_t gw = (uint64_t)blockIdx.x * NWARPS + warp;
+    const uint64_t GW = (uint64_t)gridDim.x * NWARPS;
+    const uint64_t pol_stream = policy_evict_first();
     const uint64_t polx = policy_evict_last();
-    if (full) {
-        mbar_wait(&bar, 0);
-        // ---- phase A: gather, multiply, products back to shared memory
-        uint32_t c[SPMV_EPT];
-        double xv[SPMV_EPT];
-#pragma unroll
-        for (int i = 0; i < SPMV_EPT; ++i) c[i] = sidx[tid + i * SPMV_NT];
-#pragma unroll
-        for (int i = 0; i < SPMV_EPT; ++i) xv[i] = ldg_f64_hint(x + c[i], polx);
-#pragma unroll
-        for (int i = 0; i < SPMV_EPT; ++i)
-            sprod[tid + i * SPMV_NT] = __dmul_rn(sprod[tid + i * SPMV_NT], xv[i]);
-    } else {
-        __syncthreads();
-        for (int e = tid; e < cnt; e += SPMV_NT)
-            sprod[e] = __dmul_rn(sprod[e], ldg_f64_hint(x + sidx[e], polx));
-    }
-    __syncthreads();
 
-    // ---- phase B: segmented reduction of the rows that end (or start) in this tile
-    TileCtx tc;
-    tc.k0 = k0;
-    tc.k1 = k1;
-    tc.r1 = r1;
-    tc.y = y;
-    tc.carry_slot = carry + t;
-    tc.accumulate = accumulate;
-    const uint64_t r_last = (r1 < rows) ? (uint64_t)r1 : (uint64_t)r1 - 1;  // carry row incl.
-    const uint64_t nrows_t = r_last - r0 + 1;
-    const uint32_t avg = (uint32_t)((uint64_t)cnt / nrows_t);
-    if (avg <= 6)
-        reduce_rows<P, 1>(tc, indptr, sprod, r0, r_last, &qcount, qrow, qs, qe);
-    else if (avg <= 12)
-        reduce_rows<P, 2>(tc, indptr, sprod, r0, r_last, &qcount, qrow, qs, qe);
-    else if (avg <= 24)
-        reduce_rows<P, 4>(tc, indptr, sprod, r0, r_last, &qcount, qrow, qs, qe);
-    else if (avg <= 48)
-        reduce_rows<P, 8>(tc, indptr, sprod, r0, r_last, &qcount, qrow, qs, qe);
-    else if (avg <= 96)
-        reduce_rows<P, 16>(tc, indptr, sprod, r0, r_last, &qcount, qrow, qs, qe);
-    else
-        reduce_rows<P, 32>(tc, indptr, sprod, r0, r_last, &qcount, qrow, qs, qe);
-    __syncthreads();
-    const int nq = qcount;  // rows too long for their lane group: one warp each
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int q = warp; q < nq; q += SPMV_NT / 32) {
-        double acc = 0.0;
-        for (int j = qs[q] + lane; j < qe[q]; j += 32) acc = __dadd_rn(acc, sprod[j]);
+    if (lane == 0) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-            acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-        if (lane == 0) emit_row(tc, qrow[q], acc);
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[warp][s], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    auto issue = [&](uint64_t t, int s) {  // lane 0 only; full tiles only
+        const uint64_t k0 = t * (uint64_t)WT;
+        if (k0 + WT <= nnz) {
+            unsigned char* st = wsm + (size_t)s * STAGE_BYTES;
+            mbar_expect_tx(&bars[warp][s], STAGE_BYTES);
+            bulk_g2s(st, data + k0, WT * 8, &bars[warp][s], pol_stream);
+            bulk_g2s(st + WT * 8, indices + k0, WT * 4, &bars[warp][s], pol_stream);
+        }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            const uint64_t t = gw + (uint64_t)s * GW;
+            if (t < n_tiles) issue(t, s);
+        }
+    }
+    uint32_t phases = 0;
+    int s = 0;
+    for (uint64_t t = gw; t < n_tiles; t += GW) {
+        const uint64_t k0 = t * (uint64_t)WT;
+        const uint64_t k1 = (k0 + WT < nnz) ? k0 + WT : nnz;
+        const int cnt = (int)(k1 - k0);
+        const bool full = cnt == WT;
+        double* sprod = (double*)(wsm + (size_t)s * STAGE_BYTES);
+        uint32_t* sidx = (uint32_t*)(wsm + (size_t)s * STAGE_BYTES + WT * 8);
+        // row range + first 32 row boundaries: issued before the TMA wait
+        const uint32_t r0 = tile_row[t], r1 = tile_row[t + 1];
+        const uint64_t r_last = (r1 < rows) ? (uint64_t)r1 : (uint64_t)r1 - 1;
+        const uint64_t rr = (uint64_t)r0 + lane;
+        const uint64_t b_first = rr <= r_last + 1 ? (uint64_t)indptr[rr] : 0;
+        if (full) {
+            mbar_wait(&bars[warp][s], (phases >> s) & 1u);
+            phases ^= 1u << s;
+            uint32_t c[EPL];
+            double xv[EPL];
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) c[i] = sidx[lane + i * 32];
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) xv[i] = ldg_f64_hint(x + c[i], polx);
+#pragma unroll
+            for (int i = 0; i < EPL; ++i)
+                sprod[lane + i * 32] = __dmul_rn(sprod[lane + i * 32], xv[i]);
+        } else {  // ragged last tile: guarded loads, no bulk copy past the arrays
+            for (int e = lane; e < cnt; e += 32)
+                sprod[e] = __dmul_rn(data[k0 + e], ldg_f64_hint(x + indices[k0 + e], polx));
+        }
+        __syncwarp();
+
+        TileCtx tc;
+        tc.k0 = k0;
+        tc.k1 = k1;
+        tc.r1 = r1;
+        tc.y = y;
+        tc.carry_slot = carry + t;
+        tc.accumulate = accumulate;
+        const uint32_t avg = (uint32_t)((uint64_t)cnt / (r_last - r0 + 1));
+        if (avg <= 6)
+            reduce_rows_warp<P, 1>(tc, indptr, sprod, r0, r_last, b_first, lane);
+        else if (avg <= 12)
+            reduce_rows_warp<P, 2>(tc, indptr, sprod, r0, r_last, b_first, lane);
+        else if (avg <= 24)
+            reduce_rows_warp<P, 4>(tc, indptr, sprod, r0, r_last, b_first, lane);
+        else if (avg <= 48)
+            reduce_rows_warp<P, 8>(tc, indptr, sprod, r0, r_last, b_first, lane);
+        else if (avg <= 96)
+            reduce_rows_warp<P, 16>(tc, indptr, sprod, r0, r_last, b_first, lane);
+        else
+            reduce_rows_warp<P, 32>(tc, indptr, sprod, r0, r_last, b_first, lane);
+        __syncwarp();
+        // refill this stage (generic-proxy accesses above must be ordered before the
+        // async-proxy writes of the next bulk copy)
+        const uint64_t tn = t + (uint64_t)STAGES * GW;
+        if (lane == 0 && tn < n_tiles) {
+            fence_proxy_async();
+            issue(tn, s);
+        }
+        s = (s + 1 == STAGES) ? 0 : s + 1;
     }
 }
 
@@ -276,22 +309,82 @@ __global__ void spmv_fixup_kernel(const uint32_t* __restrict__ tile_row,
     y[row] = __dadd_rn(y[row], sum);
 }
 
+// ---- launch configuration ---------------------------------------------------------
+struct SpmvVariant {
+    int wt, stages, nwarps, ctas_per_sm;
+};
+// default picked from the round-1 sweep (profiles/r1_spmv_variants.md);
+// SPRS_B200_SPMV_VARIANT="wt,stages,nwarps,ctas" overrides it for tuning runs.
+SpmvVariant spmv_variant() {
+    static SpmvVariant v = [] {
+        SpmvVariant d{512, 2, 8, 2};
+        if (const char* e = getenv("SPRS_B200_SPMV_VARIANT")) {
+            int a, b, c, g;
+            if (sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &g) == 4) d = SpmvVariant{a, b, c, g};
+        }
+        return d;
+    }();
+    return v;
+}
+
+template <typename P, int WT, int STAGES, int NWARPS>
+int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x, double* d_y,
+                   int accumulate, int ctas_per_sm, cudaStream_t s) {
+    auto kern = spmv_warp_kernel<P, WT, STAGES, NWARPS>;
+    const size_t smem = (size_t)NWARPS * STAGES * WT * 12;
+    static bool configured = false;
+    if (!configured) {
+        SPRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+        configured = true;
+    }
+    uint64_t grid = (uint64_t)ctx->sm_count * ctas_per_sm;
+    const uint64_t need = (m->n_tiles + NWARPS - 1) / NWARPS;
+    if (grid > need) grid = need;
+    kern<<<(unsigned)grid, NWARPS * 32, smem, s>>>((const P*)m->d_indptr, m->d_indices, m->d_data,
+                                                   m->d_tile_row, d_x, d_y, m->d_carry, m->nnz,
+                                                   (uint32_t)m->rows, m->n_tiles, accumulate);
+    return SPRS_B200_OK;
+}
+
+template <typename P>
+int launch_dispatch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x, double* d_y,
+                    int accumulate, cudaStream_t s) {
+    const SpmvVariant v = spmv_variant();
+#define SPMV_CASE(WT, ST, NW)                                                              \
+    if (v.wt == WT && v.stages == ST && v.nwarps == NW)                                    \
+        return launch_variant<P, WT, ST, NW>(ctx, m, d_x, d_y, accumulate, v.ctas_per_sm, s);
+    SPMV_CASE(512, 2, 8)
+    SPMV_CASE(512, 3, 8)
+    SPMV_CASE(512, 2, 16)
+    SPMV_CASE(512, 2, 4)
+    SPMV_CASE(256, 2, 8)
+    SPMV_CASE(256, 3, 8)
+    SPMV_CASE(256, 2, 16)
+    SPMV_CASE(256, 4, 16)
+    SPMV_CASE(1024, 2, 8)
+    SPMV_CASE(1024, 2, 4)
+#undef SPMV_CASE
+    SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "unknown SPRS_B200_SPMV_VARIANT");
+}
+
 }  // namespace
 
 int spmv_prepare(sprs_b200_ctx* ctx, sprs_b200_csmat* m, cudaStream_t s) {
     if (m->storage != SPRS_B200_CSR) return SPRS_B200_OK;  // CSC mirrors are converted first
-    m->n_tiles = m->nnz == 0 ? 1 : (m->nnz + SPMV_TILE - 1) / SPMV_TILE;
+    const uint32_t wt = (uint32_t)spmv_variant().wt;
+    m->n_tiles = m->nnz == 0 ? 1 : (m->nnz + wt - 1) / wt;
     SPRS_CUDA(ctx, cudaMalloc((void**)&m->d_tile_row, (m->n_tiles + 1) * sizeof(uint32_t)));
     SPRS_CUDA(ctx, cudaMalloc((void**)&m->d_carry, m->n_tiles * sizeof(double)));
     const uint64_t n = m->n_tiles + 1;
     const unsigned grid = (unsigned)((n + 255) / 256);
     if (m->indptr_bytes == 4)
         tile_row_kernel<uint32_t><<<grid, 256, 0, s>>>((const uint32_t*)m->d_indptr,
-                                                       (uint32_t)m->rows, m->n_tiles,
+                                                       (uint32_t)m->rows, m->n_tiles, wt,
                                                        m->d_tile_row);
     else
         tile_row_kernel<uint64_t><<<grid, 256, 0, s>>>((const uint64_t*)m->d_indptr,
-                                                       (uint32_t)m->rows, m->n_tiles,
+                                                       (uint32_t)m->rows, m->n_tiles, wt,
                                                        m->d_tile_row);
     ctx->launches += 1;
     SPRS_CUDA(ctx, cudaGetLastError());
@@ -304,17 +397,10 @@ int spmv_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
         SPRS_FAIL(ctx, SPRS_B200_ERR_STORAGE, "Storage mismatch: spmv needs a CSR mirror");
     if (m->rows == 0) return SPRS_B200_OK;
     if (!m->d_tile_row) SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "csmat has no SpMV partition");
-    if (m->n_tiles > 0x7fffffffull)
-        SPRS_FAIL(ctx, SPRS_B200_ERR_UNSUPPORTED, "too many tiles for one launch");
-    const unsigned grid = (unsigned)m->n_tiles;
     if (m->indptr_bytes == 4)
-        spmv_tile_kernel<uint32_t><<<grid, SPMV_NT, 0, s>>>(
-            (const uint32_t*)m->d_indptr, m->d_indices, m->d_data, m->d_tile_row, d_x, d_y,
-            m->d_carry, m->nnz, (uint32_t)m->rows, accumulate);
+        SPRS_TRY(launch_dispatch<uint32_t>(ctx, m, d_x, d_y, accumulate, s));
     else
-        spmv_tile_kernel<uint64_t><<<grid, SPMV_NT, 0, s>>>(
-            (const uint64_t*)m->d_indptr, m->d_indices, m->d_data, m->d_tile_row, d_x, d_y,
-            m->d_carry, m->nnz, (uint32_t)m->rows, accumulate);
+        SPRS_TRY(launch_dispatch<uint64_t>(ctx, m, d_x, d_y, accumulate, s));
     ctx->launches += 1;
     if (m->n_tiles > 1) {
         const unsigned fgrid = (unsigned)((m->n_tiles - 1 + 255) / 256);

@@ -197,7 +197,7 @@ def test_spmv_vs_oracle(sp, O, case):
 def test_spmv_short_rows_bit_exact(sp, O):
     """Tiles whose mean row length is <= 6 reduce each row in storage order with unfused
     mul/add -> identical bits to the reference's sequential sum (mul_acc.rs:28-30) for
-    every row that lies inside one 2048-nnz tile; rows cut by a tile boundary add their
+    every row that lies inside one SPMV_TILE-nnz tile; rows cut by a tile boundary add their
     two partial sums and are held to the tolerance gate instead."""
     rng = np.random.default_rng(11)
     ip, ind, d = rand_csr(rng, 20000, 5000, 3, empty_frac=0.2)
