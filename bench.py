@@ -194,7 +194,7 @@ def run_reference(args):
         from sprs_b200 import generate as G
         ctx = sp.Context.default(0)
         torch.cuda.set_device(0)
-        a = (G.rmat_csr if gen == "rmat" else G.rand_csr)(ctx, n, npr, seed=SEEDS[args.workload])
+        a = G.make_matrix(ctx, gen, n, npr, SEEDS[args.workload])
         x = G.normal_vector(ctx, n)
         hip, hind, hdat, rows = sample_rows_to_host(a, sample_nnz)
         hx = x.cpu().numpy()
@@ -273,7 +273,7 @@ def main():
 
     # ---- inputs, generated in HBM (every rank builds the same matrix, keeps its block)
     t_gen = time.time()
-    full = (G.rmat_csr if gen == "rmat" else G.rand_csr)(ctx, n, npr, seed=SEEDS[args.workload])
+    full = G.make_matrix(ctx, gen, n, npr, SEEDS[args.workload])
     nnz = full.nnz
     x = G.normal_vector(ctx, n)
     bounds = nnz_balanced_bounds(full.indptr, world)

@@ -146,6 +146,13 @@ def rmat_csr(ctx, n, nnz_per_row, seed=0x5EED0005, abc=(0.57, 0.19, 0.19), overs
     return _keys_to_csr(ctx, keys, n, n, seed)
 
 
+def make_matrix(ctx, gen, n, nnz_per_row, seed):
+    """Square n x n bench matrix: gen = "rmat" | "rand"."""
+    if gen == "rmat":
+        return rmat_csr(ctx, n, nnz_per_row, seed=seed)
+    return rand_csr(ctx, n, n, nnz_per_row, seed=seed)
+
+
 def normal_vector(ctx, n, seed=0x5EED1002):
     x = torch.empty(n, device=torch.device("cuda", ctx.device), dtype=torch.float64)
     ctx.check(ctx.lib.sprs_b200_gen_normal_from_keys(ctx.h, seed, None, n, _dptr(x),

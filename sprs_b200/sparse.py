@@ -200,6 +200,7 @@ class CsVec:
 class CsMat:
     """CsMatBase{storage, nrows, ncols, indptr, indices, data} (sparse.rs:94-109) with
     host arrays owned here (as Rust owns its Vecs) and a lazily-built device mirror."""
+    __array_ufunc__ = None  # let `ndarray @ CsMat` reach __rmatmul__ (dense.dot(&sparse))
 
     def __init__(self, shape, indptr, indices, data, storage=CSR, index_dtype=None, ctx=None):
         self.storage = storage

@@ -1,0 +1,75 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/sprs_b200.h declares,
+the Python binding covers all of them, the product never links the oracle, and it fails
+loudly (no fallback) when there is no GPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "sprs_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sprs_b200_\w+)\s*\(", src)))
+
+
+def test_header_symbols_exported_and_bound():
+    import sprs_b200
+    names = declared_symbols()
+    assert len(names) >= 35
+    lib = ctypes.CDLL(sprs_b200._lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "libsprs_b200.so does not export " + n
+    assert set(names) == set(sprs_b200._lib.PROTOTYPES), \
+        set(names) ^ set(sprs_b200._lib.PROTOTYPES)
+    sprs_b200._lib.load()
+    assert lib.sprs_b200_version() >= 100
+
+
+def test_product_does_not_link_oracle():
+    import sprs_b200
+    out = subprocess.run(["ldd", sprs_b200._lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+    for root, _, files in os.walk(os.path.join(ROOT, "sprs_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                txt = open(os.path.join(root, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+                assert "liboracle" not in txt, f
+
+
+def test_no_cpu_fallback_without_gpu():
+    import sprs_b200
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    with pytest.raises(sprs_b200.ThirdPartyError):
+        sprs_b200.Context(0)
+    import numpy as np
+    a = sprs_b200.CsMat.eye(3)
+    with pytest.raises(sprs_b200.ThirdPartyError):
+        a * np.ones(3)
+
+
+def test_host_structure_checks():
+    """check_compressed_structure (sparse.rs:300-369) runs on the host before any upload."""
+    import numpy as np
+    import sprs_b200 as sp
+    with pytest.raises(sp.SprsPanic):
+        sp.CsMat.new((2, 2), [0, 2, 1], [0, 1], [1., 2.])          # unsorted indptr
+    with pytest.raises(sp.SprsPanic):
+        sp.CsMat.new((2, 2), [0, 1, 2], [0, 5], [1., 2.])          # out of bounds
+    with pytest.raises(sp.SprsPanic):
+        sp.CsMat.new((1, 3), [0, 2], [2, 1], [1., 2.])             # unsorted indices
+    m = sp.CsMat.new((2, 3), [0, 1, 2], [2, 0], [1., 2.])
+    assert m.transpose_view().shape == (3, 2) and m.transpose_view().is_csc()
+    s = sp.CsMat.new((4, 4), [0, 1, 2, 3, 4], [0, 1, 2, 3], np.ones(4)).slice_outer(1, 3)
+    assert s.shape == (2, 4) and s.indptr[0] == 1 and s.nnz() == 2

@@ -14,7 +14,7 @@ from sprs_b200 import generate as G
 ctx = sp.Context.default(0)
 out = {}
 for name, gen, n, npr in %s:
-    a = (G.rmat_csr if gen == "rmat" else G.rand_csr)(ctx, n, npr)
+    a = G.make_matrix(ctx, gen, n, npr, 0x5EED0005 if gen == "rmat" else 0x5EED0002)
     x = G.normal_vector(ctx, n); y = torch.empty(n, device="cuda", dtype=torch.float64)
     for _ in range(5): G.spmv(ctx, a, x, y)
     torch.cuda.synchronize()
