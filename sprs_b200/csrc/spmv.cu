@@ -336,6 +336,10 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
     if (!configured) {
         SPRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)smem));
+        // without this the driver may pick a smaller shared-memory carve-out (more L1) and
+        // silently halve the resident CTAs of the small-stage variants
+        SPRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
     uint64_t grid = (uint64_t)ctx->sm_count * ctas_per_sm;
