@@ -190,8 +190,8 @@ __device__ __forceinline__ void reduce_rows_warp(const TileCtx& tc, const P* __r
     }
 }
 
-template <typename P, int WT, int STAGES, int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32)
+template <typename P, int WT, int STAGES, int NWARPS, int MINB>
+__global__ void __launch_bounds__(NWARPS * 32, MINB)
     spmv_warp_kernel(const P* __restrict__ indptr, const uint32_t* __restrict__ indices,
                      const double* __restrict__ data, const uint32_t* __restrict__ tile_row,
                      const double* __restrict__ x, double* __restrict__ y,
@@ -214,24 +214,37 @@ __global__ void __launch_bounds__(NWARPS * 32)
         fence_mbar_init();
     }
     __syncwarp();
-    auto issue = [&](uint64_t t, int s) {  // lane 0 only; full tiles only
-        const uint64_t k0 = t * (uint64_t)WT;
-        if (k0 + WT <= nnz) {
-            unsigned char* st = wsm + (size_t)s * STAGE_BYTES;
-            mbar_expect_tx(&bars[warp][s], STAGE_BYTES);
-            bulk_g2s(st, data + k0, WT * 8, &bars[warp][s], pol_stream);
-            bulk_g2s(st + WT * 8, indices + k0, WT * 4, &bars[warp][s], pol_stream);
-        }
-    };
+#define SPMV_ISSUE(T, S)                                                                    \
+    do { /* lane 0 only; full tiles only (the ragged last tile is loaded by hand) */        \
+        const uint64_t k0_ = (T) * (uint64_t)WT;                                            \
+        if (k0_ + WT <= nnz) {                                                              \
+            unsigned char* st_ = wsm + (size_t)(S) * STAGE_BYTES;                           \
+            mbar_expect_tx(&bars[warp][(S)], STAGE_BYTES);                                  \
+            bulk_g2s(st_, data + k0_, WT * 8, &bars[warp][(S)], pol_stream);                \
+            bulk_g2s(st_ + WT * 8, indices + k0_, WT * 4, &bars[warp][(S)], pol_stream);    \
+        }                                                                                   \
+    } while (0)
     if (lane == 0) {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             const uint64_t t = gw + (uint64_t)s * GW;
-            if (t < n_tiles) issue(t, s);
+            if (t < n_tiles) SPMV_ISSUE(t, s);
         }
     }
     uint32_t phases = 0;
     int s = 0;
+    // Row range and the first 32 row boundaries of a tile are fetched ONE TILE AHEAD, so the
+    // two dependent global loads (tile_row -> indptr) never stall the in-order issue in
+    // front of the gathers.
+    uint32_t r0 = 0, r1 = 0;
+    uint64_t b_first = 0;
+    if (gw < n_tiles) {
+        r0 = tile_row[gw];
+        r1 = tile_row[gw + 1];
+        const uint64_t rl = (r1 < rows) ? (uint64_t)r1 : (uint64_t)r1 - 1;
+        const uint64_t rr = (uint64_t)r0 + lane;
+        b_first = rr <= rl + 1 ? (uint64_t)indptr[rr] : 0;
+    }
     for (uint64_t t = gw; t < n_tiles; t += GW) {
         const uint64_t k0 = t * (uint64_t)WT;
         const uint64_t k1 = (k0 + WT < nnz) ? k0 + WT : nnz;
@@ -239,11 +252,9 @@ __global__ void __launch_bounds__(NWARPS * 32)
         const bool full = cnt == WT;
         double* sprod = (double*)(wsm + (size_t)s * STAGE_BYTES);
         uint32_t* sidx = (uint32_t*)(wsm + (size_t)s * STAGE_BYTES + WT * 8);
-        // row range + first 32 row boundaries: issued before the TMA wait
-        const uint32_t r0 = tile_row[t], r1 = tile_row[t + 1];
         const uint64_t r_last = (r1 < rows) ? (uint64_t)r1 : (uint64_t)r1 - 1;
-        const uint64_t rr = (uint64_t)r0 + lane;
-        const uint64_t b_first = rr <= r_last + 1 ? (uint64_t)indptr[rr] : 0;
+        const uint64_t tnext = t + GW;
+        uint32_t r0n = 0, r1n = 0;
         if (full) {
             mbar_wait(&bars[warp][s], (phases >> s) & 1u);
             phases ^= 1u << s;
@@ -253,14 +264,28 @@ __global__ void __launch_bounds__(NWARPS * 32)
             for (int i = 0; i < EPL; ++i) c[i] = sidx[lane + i * 32];
 #pragma unroll
             for (int i = 0; i < EPL; ++i) xv[i] = ldg_f64_hint(x + c[i], polx);
+            if (tnext < n_tiles) {  // next tile's row range: in flight behind the gathers
+                r0n = tile_row[tnext];
+                r1n = tile_row[tnext + 1];
+            }
 #pragma unroll
             for (int i = 0; i < EPL; ++i)
                 sprod[lane + i * 32] = __dmul_rn(sprod[lane + i * 32], xv[i]);
         } else {  // ragged last tile: guarded loads, no bulk copy past the arrays
             for (int e = lane; e < cnt; e += 32)
                 sprod[e] = __dmul_rn(data[k0 + e], ldg_f64_hint(x + indices[k0 + e], polx));
+            if (tnext < n_tiles) {
+                r0n = tile_row[tnext];
+                r1n = tile_row[tnext + 1];
+            }
         }
         __syncwarp();
+        uint64_t b_next = 0;
+        if (tnext < n_tiles) {  // boundaries of the next tile: in flight behind the reduction
+            const uint64_t rln = (r1n < rows) ? (uint64_t)r1n : (uint64_t)r1n - 1;
+            const uint64_t rr = (uint64_t)r0n + lane;
+            b_next = rr <= rln + 1 ? (uint64_t)indptr[rr] : 0;
+        }
 
         TileCtx tc;
         tc.k0 = k0;
@@ -288,11 +313,16 @@ __global__ void __launch_bounds__(NWARPS * 32)
         const uint64_t tn = t + (uint64_t)STAGES * GW;
         if (lane == 0 && tn < n_tiles) {
             fence_proxy_async();
-            issue(tn, s);
+            SPMV_ISSUE(tn, s);
         }
         s = (s + 1 == STAGES) ? 0 : s + 1;
+        r0 = r0n;
+        r1 = r1n;
+        b_first = b_next;
     }
 }
+
+#undef SPMV_ISSUE
 
 // carries: tile t left the partial sum of row tile_row[t+1] in carry[t]; consecutive
 // tiles with the same carry row form a run that is summed in tile order by its head.
@@ -327,10 +357,12 @@ SpmvVariant spmv_variant() {
     return v;
 }
 
-template <typename P, int WT, int STAGES, int NWARPS>
+template <typename P, int WT, int STAGES, int NWARPS, int CTAS>
 int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x, double* d_y,
-                   int accumulate, int ctas_per_sm, cudaStream_t s) {
-    auto kern = spmv_warp_kernel<P, WT, STAGES, NWARPS>;
+                   int accumulate, cudaStream_t s) {
+    // CTAS resident CTAs per SM is also the kernel's __launch_bounds__ minBlocks: it sets the
+    // register budget (ptxas otherwise picks ~40 registers and spills the gather buffers).
+    auto kern = spmv_warp_kernel<P, WT, STAGES, NWARPS, CTAS>;
     const size_t smem = (size_t)NWARPS * STAGES * WT * 12;
     static bool configured = false;
     if (!configured) {
@@ -342,7 +374,7 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
                                             cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
-    uint64_t grid = (uint64_t)ctx->sm_count * ctas_per_sm;
+    uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
     const uint64_t need = (m->n_tiles + NWARPS - 1) / NWARPS;
     if (grid > need) grid = need;
     kern<<<(unsigned)grid, NWARPS * 32, smem, s>>>((const P*)m->d_indptr, m->d_indices, m->d_data,
@@ -355,19 +387,21 @@ template <typename P>
 int launch_dispatch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x, double* d_y,
                     int accumulate, cudaStream_t s) {
     const SpmvVariant v = spmv_variant();
-#define SPMV_CASE(WT, ST, NW)                                                              \
-    if (v.wt == WT && v.stages == ST && v.nwarps == NW)                                    \
-        return launch_variant<P, WT, ST, NW>(ctx, m, d_x, d_y, accumulate, v.ctas_per_sm, s);
-    SPMV_CASE(512, 2, 8)
-    SPMV_CASE(512, 3, 8)
-    SPMV_CASE(512, 2, 16)
-    SPMV_CASE(512, 2, 4)
-    SPMV_CASE(256, 2, 8)
-    SPMV_CASE(256, 3, 8)
-    SPMV_CASE(256, 2, 16)
-    SPMV_CASE(256, 4, 16)
-    SPMV_CASE(1024, 2, 8)
-    SPMV_CASE(1024, 2, 4)
+#define SPMV_CASE(WT, ST, NW, CT)                                                         \
+    if (v.wt == WT && v.stages == ST && v.nwarps == NW && v.ctas_per_sm == CT)            \
+        return launch_variant<P, WT, ST, NW, CT>(ctx, m, d_x, d_y, accumulate, s);
+    SPMV_CASE(512, 2, 8, 2)
+    SPMV_CASE(512, 2, 16, 1)
+    SPMV_CASE(512, 1, 8, 4)
+    SPMV_CASE(256, 2, 8, 3)
+    SPMV_CASE(256, 2, 8, 4)
+    SPMV_CASE(256, 2, 16, 2)
+    SPMV_CASE(256, 3, 8, 3)
+    SPMV_CASE(256, 1, 8, 6)
+    SPMV_CASE(128, 2, 8, 4)
+    SPMV_CASE(128, 2, 8, 6)
+    SPMV_CASE(128, 3, 16, 3)
+    SPMV_CASE(128, 2, 16, 4)
 #undef SPMV_CASE
     SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "unknown SPRS_B200_SPMV_VARIANT");
 }
