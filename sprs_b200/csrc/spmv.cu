@@ -368,10 +368,15 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
     if (!configured) {
         SPRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)smem));
-        // without this the driver may pick a smaller shared-memory carve-out (more L1) and
-        // silently halve the resident CTAs of the small-stage variants
+        // Shared-memory carve-out = exactly what CTAS resident CTAs need, everything else
+        // stays L1: every in-flight gather holds an L1 line, so the gather rate is bounded
+        // by L1 lines / L2 latency (profiles/r1_spmv_notes.md).  A max-shared carve-out
+        // cost 40 % of the throughput; too small a carve-out would drop resident CTAs.
+        int carve = (int)(((smem + 1024) * CTAS * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (const char* e = getenv("SPRS_B200_SPMV_CARVEOUT")) carve = atoi(e);
+        if (carve > 100) carve = 100;
         SPRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                            cudaSharedmemCarveoutMaxShared));
+                                            carve));
         configured = true;
     }
     uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
@@ -391,17 +396,17 @@ int launch_dispatch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* 
     if (v.wt == WT && v.stages == ST && v.nwarps == NW && v.ctas_per_sm == CT)            \
         return launch_variant<P, WT, ST, NW, CT>(ctx, m, d_x, d_y, accumulate, s);
     SPMV_CASE(512, 2, 8, 2)
-    SPMV_CASE(512, 2, 16, 1)
-    SPMV_CASE(512, 1, 8, 4)
+    SPMV_CASE(512, 2, 8, 1)
+    SPMV_CASE(512, 1, 8, 2)
+    SPMV_CASE(256, 2, 8, 2)
     SPMV_CASE(256, 2, 8, 3)
     SPMV_CASE(256, 2, 8, 4)
-    SPMV_CASE(256, 2, 16, 2)
-    SPMV_CASE(256, 3, 8, 3)
+    SPMV_CASE(256, 1, 8, 4)
     SPMV_CASE(256, 1, 8, 6)
     SPMV_CASE(128, 2, 8, 4)
     SPMV_CASE(128, 2, 8, 6)
-    SPMV_CASE(128, 3, 16, 3)
-    SPMV_CASE(128, 2, 16, 4)
+    SPMV_CASE(128, 2, 8, 8)
+    SPMV_CASE(128, 1, 8, 8)
 #undef SPMV_CASE
     SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "unknown SPRS_B200_SPMV_VARIANT");
 }

@@ -1,0 +1,92 @@
+"""CPU tests (gloo, world_size 2) of the multi-GPU host logic in sprs_b200/dist.py: the
+nnz-balanced row partition and the unequal-slice all-gather of y.  The local product is
+done by the oracle here (the CUDA kernels need a GPU; tests may use the oracle)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_nnz_balanced_bounds_numpy_and_torch():
+    import torch
+    from sprs_b200.dist import nnz_balanced_bounds
+    rng = np.random.default_rng(0)
+    lens = (rng.pareto(1.1, 5000) * 20).astype(np.int64)  # skewed rows
+    ip = np.zeros(5001, dtype=np.int64)
+    np.cumsum(lens, out=ip[1:])
+    for parts in (1, 2, 3, 8):
+        b = nnz_balanced_bounds(ip, parts)
+        assert b[0] == 0 and b[-1] == 5000 and len(b) == parts + 1
+        assert all(b[i] <= b[i + 1] for i in range(parts))
+        assert b == nnz_balanced_bounds(torch.from_numpy(ip), parts)
+        per = [ip[b[i + 1]] - ip[b[i]] for i in range(parts)]
+        # every block within one (max) row of the ideal share
+        assert max(per) <= ip[-1] / parts + lens.max()
+    # non-zero-based indptr (a slice view) and degenerate shapes
+    assert nnz_balanced_bounds(ip[100:201], 2)[-1] == 100
+    assert nnz_balanced_bounds(np.zeros(1, np.int64), 4) == [0, 0, 0, 0, 0]
+    assert nnz_balanced_bounds(np.zeros(11, np.int64), 2) == [0, 0, 10]
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from conftest import rand_csr
+    from oracle import oracle as O
+    from sprs_b200.dist import RowPartitionedSpMV, nnz_balanced_bounds
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(123)  # same matrix on every rank
+        n = 3000
+        ip, ind, d = rand_csr(rng, n, n, 20, skew=True)
+        x = rng.standard_normal(n)
+        bounds = nnz_balanced_bounds(ip, world)
+        r0, r1 = bounds[rank], bounds[rank + 1]
+        s = int(ip[r0])
+
+        def local_spmv(xv, y_slice):  # slice_outer + proper_indptr, then the product
+            out = np.zeros(r1 - r0)
+            O.mul_acc_mat_vec_csr((ip[r0:r1 + 1] - s).astype(np.uint32), ind[s:int(ip[r1])],
+                                  d[s:int(ip[r1])], xv.numpy(), out)
+            y_slice.copy_(torch.from_numpy(out))
+
+        y = torch.full((n,), float("nan"), dtype=torch.float64)
+        op = RowPartitionedSpMV(bounds, rank, world, y, local_spmv, dist=dist)
+        got = op.step(torch.from_numpy(x)).numpy().copy()
+        ref = np.zeros(n)
+        O.mul_acc_mat_vec_csr(ip, ind, d, x, ref)
+        ok = bool(np.array_equal(got, ref))  # same sequential sums on every rank
+        # iterate: y of step k is the x of step k+1 on every rank (square matrix)
+        got2 = op.step(torch.from_numpy(got)).numpy().copy()
+        ref2 = np.zeros(n)
+        O.mul_acc_mat_vec_csr(ip, ind, d, ref, ref2)
+        ok = ok and bool(np.array_equal(got2, ref2))
+        q.put((rank, ok, bounds))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_partitioned_spmv_gloo_world2():
+    import torch.multiprocessing as mp
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)
+    assert res[0][2] == res[1][2] and 0 < res[0][2][1] < 3000
