@@ -92,6 +92,19 @@ __device__ __forceinline__ double ldg_f64_hint(const double* p, uint64_t policy)
     return v;
 }
 
+__device__ __forceinline__ uint32_t ldg_stream_u32(const uint32_t* p, uint64_t policy) {
+    uint32_t v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;"
+        : "=r"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ double ldg_stream_f64(const double* p, uint64_t policy) {
+    double v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;"
+        : "=d"(v) : "l"(p), "l"(policy));
+    return v;
+}
+
 // ---- partition: tile_row[t] = first row whose end lies beyond nnz position t*wt
 template <typename P>
 __global__ void tile_row_kernel(const P* __restrict__ indptr, uint32_t rows, uint64_t n_tiles,
@@ -198,19 +211,21 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
                      double* __restrict__ carry, uint64_t nnz, uint32_t rows, uint64_t n_tiles,
                      int accumulate) {
     constexpr int EPL = WT / 32;               // non-zeros per lane per tile
-    constexpr int STAGE_BYTES = WT * 12;
+    constexpr bool DIRECT = STAGES == 0;       // no TMA ring: stream through registers
+    constexpr int STAGE_BYTES = DIRECT ? WT * 8 : WT * 12;
+    constexpr int NST = DIRECT ? 1 : STAGES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bars[NWARPS][STAGES];
+    __shared__ __align__(8) uint64_t bars[NWARPS][NST];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* wsm = smem_raw + (size_t)warp * STAGES * STAGE_BYTES;
+    unsigned char* wsm = smem_raw + (size_t)warp * NST * STAGE_BYTES;
     const uint64_t gw = (uint64_t)blockIdx.x * NWARPS + warp;
     const uint64_t GW = (uint64_t)gridDim.x * NWARPS;
     const uint64_t pol_stream = policy_evict_first();
     const uint64_t polx = policy_evict_last();
 
-    if (lane == 0) {
+    if (!DIRECT && lane == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[warp][s], 1);
+        for (int s = 0; s < NST; ++s) mbar_init(&bars[warp][s], 1);
         fence_mbar_init();
     }
     __syncwarp();
@@ -224,9 +239,9 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
             bulk_g2s(st_ + WT * 8, indices + k0_, WT * 4, &bars[warp][(S)], pol_stream);    \
         }                                                                                   \
     } while (0)
-    if (lane == 0) {
+    if (!DIRECT && lane == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < NST; ++s) {
             const uint64_t t = gw + (uint64_t)s * GW;
             if (t < n_tiles) SPMV_ISSUE(t, s);
         }
@@ -255,7 +270,26 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
         const uint64_t r_last = (r1 < rows) ? (uint64_t)r1 : (uint64_t)r1 - 1;
         const uint64_t tnext = t + GW;
         uint32_t r0n = 0, r1n = 0;
-        if (full) {
+        if (full && DIRECT) {
+            // register path: coalesced streaming loads (no L1 allocation, L2 evict_first),
+            // products to the warp's 8*WT-byte shared buffer for the reduction
+            uint32_t c[EPL];
+            double v[EPL], xv[EPL];
+#pragma unroll
+            for (int i = 0; i < EPL; ++i)
+                c[i] = ldg_stream_u32(indices + k0 + lane + i * 32, pol_stream);
+#pragma unroll
+            for (int i = 0; i < EPL; ++i)
+                v[i] = ldg_stream_f64(data + k0 + lane + i * 32, pol_stream);
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) xv[i] = ldg_f64_hint(x + c[i], polx);
+            if (tnext < n_tiles) {
+                r0n = tile_row[tnext];
+                r1n = tile_row[tnext + 1];
+            }
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) sprod[lane + i * 32] = __dmul_rn(v[i], xv[i]);
+        } else if (full) {
             mbar_wait(&bars[warp][s], (phases >> s) & 1u);
             phases ^= 1u << s;
             uint32_t c[EPL];
@@ -310,12 +344,12 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
         __syncwarp();
         // refill this stage (generic-proxy accesses above must be ordered before the
         // async-proxy writes of the next bulk copy)
-        const uint64_t tn = t + (uint64_t)STAGES * GW;
-        if (lane == 0 && tn < n_tiles) {
+        const uint64_t tn = t + (uint64_t)NST * GW;
+        if (!DIRECT && lane == 0 && tn < n_tiles) {
             fence_proxy_async();
             SPMV_ISSUE(tn, s);
         }
-        s = (s + 1 == STAGES) ? 0 : s + 1;
+        s = (s + 1 == NST) ? 0 : s + 1;
         r0 = r0n;
         r1 = r1n;
         b_first = b_next;
@@ -347,7 +381,7 @@ struct SpmvVariant {
 // SPRS_B200_SPMV_VARIANT="wt,stages,nwarps,ctas" overrides it for tuning runs.
 SpmvVariant spmv_variant() {
     static SpmvVariant v = [] {
-        SpmvVariant d{512, 2, 8, 2};
+        SpmvVariant d{256, 2, 8, 3};
         if (const char* e = getenv("SPRS_B200_SPMV_VARIANT")) {
             int a, b, c, g;
             if (sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &g) == 4) d = SpmvVariant{a, b, c, g};
@@ -363,7 +397,7 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
     // CTAS resident CTAs per SM is also the kernel's __launch_bounds__ minBlocks: it sets the
     // register budget (ptxas otherwise picks ~40 registers and spills the gather buffers).
     auto kern = spmv_warp_kernel<P, WT, STAGES, NWARPS, CTAS>;
-    const size_t smem = (size_t)NWARPS * STAGES * WT * 12;
+    const size_t smem = STAGES == 0 ? (size_t)NWARPS * WT * 8 : (size_t)NWARPS * STAGES * WT * 12;
     static bool configured = false;
     if (!configured) {
         SPRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -395,18 +429,19 @@ int launch_dispatch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* 
 #define SPMV_CASE(WT, ST, NW, CT)                                                         \
     if (v.wt == WT && v.stages == ST && v.nwarps == NW && v.ctas_per_sm == CT)            \
         return launch_variant<P, WT, ST, NW, CT>(ctx, m, d_x, d_y, accumulate, s);
-    SPMV_CASE(512, 2, 8, 2)
-    SPMV_CASE(512, 2, 8, 1)
-    SPMV_CASE(512, 1, 8, 2)
-    SPMV_CASE(256, 2, 8, 2)
     SPMV_CASE(256, 2, 8, 3)
-    SPMV_CASE(256, 2, 8, 4)
-    SPMV_CASE(256, 1, 8, 4)
+    SPMV_CASE(256, 2, 8, 2)
     SPMV_CASE(256, 1, 8, 6)
-    SPMV_CASE(128, 2, 8, 4)
-    SPMV_CASE(128, 2, 8, 6)
-    SPMV_CASE(128, 2, 8, 8)
-    SPMV_CASE(128, 1, 8, 8)
+    SPMV_CASE(512, 1, 8, 2)
+    SPMV_CASE(256, 1, 8, 3)
+    SPMV_CASE(256, 1, 8, 4)
+    SPMV_CASE(384, 1, 8, 3)
+    SPMV_CASE(256, 0, 8, 3)
+    SPMV_CASE(256, 0, 8, 4)
+    SPMV_CASE(256, 0, 8, 6)
+    SPMV_CASE(512, 0, 8, 2)
+    SPMV_CASE(512, 0, 8, 3)
+    SPMV_CASE(128, 0, 8, 8)
 #undef SPMV_CASE
     SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "unknown SPRS_B200_SPMV_VARIANT");
 }

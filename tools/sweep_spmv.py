@@ -33,8 +33,9 @@ def main():
     workloads = [("rand_1m_32", "rand", 1_000_000, 32), ("rmat_10m_100", "rmat", 10_000_000, 100)]
     if len(sys.argv) > 1 and sys.argv[1] == "small":
         workloads = [("rand_1m_32", "rand", 1_000_000, 32), ("rmat_1m_100", "rmat", 1_000_000, 100)]
-    variants = ["512,2,8,2", "512,2,8,1", "512,1,8,2", "256,2,8,2", "256,2,8,3", "256,2,8,4",
-                "256,1,8,4", "256,1,8,6", "128,2,8,4", "128,2,8,6", "128,2,8,8", "128,1,8,8"]
+    variants = ["256,2,8,3", "256,2,8,2", "256,1,8,6", "512,1,8,2", "256,1,8,3", "256,1,8,4",
+                "384,1,8,3", "256,0,8,3", "256,0,8,4", "256,0,8,6", "512,0,8,2", "512,0,8,3",
+                "128,0,8,8"]
     if len(sys.argv) > 2:
         variants = sys.argv[2:]
     for v in variants:
