@@ -110,18 +110,6 @@ class ClockSampler:
                 "samples": len(inside)}
 
 
-def nnz_balanced_bounds(indptr_t, nparts):
-    """Row boundaries so every part holds ~nnz/nparts non-zeros (binary search in indptr;
-    slice_outer-style contiguous blocks)."""
-    import torch
-    nnz = int(indptr_t[-1].item())
-    rows = indptr_t.numel() - 1
-    targets = torch.tensor([(nnz * g) // nparts for g in range(1, nparts)],
-                           device=indptr_t.device, dtype=indptr_t.dtype)
-    cuts = torch.searchsorted(indptr_t, targets).tolist() if nparts > 1 else []
-    return [0] + [min(max(int(c), 0), rows) for c in cuts] + [rows]
-
-
 def sample_rows_to_host(a, target_nnz, nblocks=8):
     """A bounded sample of the SAME matrix for the CPU baseline: `nblocks` contiguous row
     blocks spread over the matrix, ~target_nnz non-zeros in total, as one host CSR."""
@@ -253,6 +241,7 @@ def main():
     import torch.distributed as dist
     import sprs_b200 as sp
     from sprs_b200 import generate as G
+    from sprs_b200.dist import RowPartitionedSpMV, nnz_balanced_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -290,12 +279,13 @@ def main():
         torch.cuda.empty_cache()
     t_gen = time.time() - t_gen
     y = torch.zeros(n, device=dev, dtype=torch.float64)
-    y_views = [y[bounds[g]:bounds[g + 1]] for g in range(world)]
+    local_nnz = a.nnz
+    op = RowPartitionedSpMV(bounds, rank, world, y, lambda xv, ys: G.spmv(ctx, a, xv, ys),
+                            dist=dist if world > 1 else None)
+    y_views = op.views
 
     def step():
-        G.spmv(ctx, a, x, y_views[rank])
-        if world > 1:
-            dist.all_gather(y_views, y_views[rank])
+        op.step(x)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -316,10 +306,9 @@ def main():
     e_start.record()
     for i in range(args.steps):
         evs[i][0].record()
-        G.spmv(ctx, a, x, y_views[rank])
+        op.compute(x)
         evs[i][1].record()
-        if world > 1:
-            dist.all_gather(y_views, y_views[rank])
+        op.exchange()
         evs[i][2].record()
     e_stop.record()
     torch.cuda.synchronize()
@@ -381,7 +370,7 @@ def main():
         # roofline of the dominant kernel (spmv_tile_kernel; the carry fix-up kernel rides in
         # the same event pair and is < 0.5 % of it): algorithmic bytes this rank's launch
         # moves / its mean duration.  Rank 0's block; blocks are nnz-balanced.
-        local_bytes = 12.0 * a_nnz_of(bounds, nnz, world) + 8.0 * (n / world)
+        local_bytes = 12.0 * local_nnz + 8.0 * rows_local
         achieved = local_bytes / (kern_ms_avg * 1e-3) / 1e9
         line = {
             "metric": "csr_spmv_f64_gflops", "value": gflops, "unit": "GFLOP/s",
@@ -399,7 +388,8 @@ def main():
                          "frac": achieved / hbm_peak, "traffic": None,
                          "kernel": "spmv_tile_kernel (+ spmv_fixup_kernel)",
                          "kernel_ms": kern_ms_avg, "peak_source": peak_src,
-                         "algorithmic_bytes": "12*nnz + 8*rows per launch"},
+                         "algorithmic_bytes": "12*nnz + 8*rows of this rank's block per launch",
+                         "variant": os.environ.get("SPRS_B200_SPMV_VARIANT", "default 256,2,8,3")},
             "collective_ms": coll_ms_avg,
             "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s",
                     "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * n * world,
@@ -414,10 +404,6 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-
-
-def a_nnz_of(bounds, nnz, world):
-    return nnz / world
 
 
 def bench_small_spmv(ctx, G, hbm_peak, dev):
