@@ -233,6 +233,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="N>1: all-gather of y fused into the SpMV kernel (peer stores over "
+                         "NVLink) or a separate NCCL all_gather")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -241,7 +244,7 @@ def main():
     import torch.distributed as dist
     import sprs_b200 as sp
     from sprs_b200 import generate as G
-    from sprs_b200.dist import RowPartitionedSpMV, nnz_balanced_bounds
+    from sprs_b200.dist import FusedAllGatherSpMV, RowPartitionedSpMV, nnz_balanced_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -255,7 +258,7 @@ def main():
     ctx = sp.Context.default(local)
     kind, n, npr, gen = WORKLOADS[args.workload]
     if kind != "spmv":
-        from sprs_b200 import bench_other
+        import bench_other
         return bench_other.run(args, ctx, kind, n, npr, gen, SEEDS[args.workload])
     peaks, peak_src = measured_peaks()
     hbm_peak = float(peaks["hbm_gbs"])
@@ -280,9 +283,15 @@ def main():
     t_gen = time.time() - t_gen
     y = torch.zeros(n, device=dev, dtype=torch.float64)
     local_nnz = a.nnz
-    op = RowPartitionedSpMV(bounds, rank, world, y, lambda xv, ys: G.spmv(ctx, a, xv, ys),
-                            dist=dist if world > 1 else None)
-    y_views = op.views
+    fused = world > 1 and args.exchange == "fused"
+    if fused:
+        op = FusedAllGatherSpMV(ctx, a.mirror, bounds, rank, world, n, dist, dev)
+        y = op.y
+        y_views = [y[bounds[g]:bounds[g + 1]] for g in range(world)]
+    else:
+        op = RowPartitionedSpMV(bounds, rank, world, y, lambda xv, ys: G.spmv(ctx, a, xv, ys),
+                                dist=dist if world > 1 else None)
+        y_views = op.views
 
     def step():
         op.step(x)
@@ -379,7 +388,10 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "n": n, "nnz": nnz, "nnz_per_row": npr,
                        "generator": gen, "index_bytes": 4, "partition": "nnz-balanced row blocks",
-                       "collective": "all_gather(y) NCCL" if world > 1 else "none",
+                       "collective": ("none" if world == 1 else
+                                      "all-gather of y fused into the SpMV kernel (peer stores "
+                                      "over NVLink) + 1-element NCCL all_reduce barrier"
+                                      if fused else "NCCL all_gather(y), unequal slices"),
                        "l2_policy": "inputs (%.1f GB) exceed L2 (126 MB); no flush needed" %
                                     (alg_bytes / 1e9),
                        "gen_seconds": round(t_gen, 1)},
@@ -402,6 +414,8 @@ def main():
         if extra:
             line["extra"] = extra
         print(json.dumps(line))
+    if fused:
+        op.close()
     if world > 1:
         dist.destroy_process_group()
 

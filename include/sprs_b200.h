@@ -153,6 +153,26 @@ int sprs_b200_spmm_rowmaj_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, co
 /* number of kernel launches the library has issued on this ctx (all entry points) */
 uint64_t sprs_b200_launch_count(const sprs_b200_ctx* ctx);
 
+/* ---- multi-GPU, one process per GPU (the reference has no multi-device code; the shard
+ * primitive is slice_outer, slicing.rs:65-89): each rank holds a contiguous row block as
+ * its own mirror, x is replicated, y (n entries) lives in a peer-mappable buffer per rank.
+ * peer_alloc returns the buffer and its 64-byte CUDA IPC handle; the caller ships handles to
+ * the other ranks (any transport), which map them with peer_open.
+ * spmv_allgather_dev: y[row_offset .. row_offset+rows) = A_local x, stored by the kernel
+ * into ALL n_targets buffers (d_y_bufs[0] must be this rank's own buffer, the others the
+ * peer mappings): the all-gather of y is fused into the SpMV.  The caller orders the next
+ * consumer of y after a cross-rank barrier on the same stream.                        */
+int sprs_b200_peer_alloc(sprs_b200_ctx* ctx, uint64_t bytes, void** d_ptr,
+                         unsigned char ipc_handle[64]);
+int sprs_b200_peer_open(sprs_b200_ctx* ctx, const unsigned char ipc_handle[64], void** d_ptr);
+int sprs_b200_peer_close(sprs_b200_ctx* ctx, void* d_ptr);
+int sprs_b200_peer_free(sprs_b200_ctx* ctx, void* d_ptr);
+int sprs_b200_copy_dev(sprs_b200_ctx* ctx, void* dst, const void* src, uint64_t bytes,
+                       void* stream);
+int sprs_b200_spmv_allgather_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
+                                 const double* d_x, uint64_t row_offset, int n_targets,
+                                 double* const* d_y_bufs, int accumulate, void* stream);
+
 /* ---- sparse x sparse: smmp::mul_csr_csr (smmp.rs:196-237), two calls so the
  * CALLER allocates the output Vecs, like symbolic -> numeric (smmp.rs:81,151).
  * symbolic: pattern of C = A*B; returns a plan and nnz(C).

@@ -47,6 +47,12 @@ PROTOTYPES = {
     "sprs_b200_spmv_dev": (_int, [_vp, _vp, _dp, _dp, _int, _vp]),
     "sprs_b200_spmm_rowmaj_dev": (_int, [_vp, _vp, _dp, _u64, _u64, _dp, _u64, _int, _vp]),
     "sprs_b200_launch_count": (_u64, [_vp]),
+    "sprs_b200_peer_alloc": (_int, [_vp, _u64, C.POINTER(_vp), C.c_char_p]),
+    "sprs_b200_peer_open": (_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
+    "sprs_b200_peer_close": (_int, [_vp, _vp]),
+    "sprs_b200_peer_free": (_int, [_vp, _vp]),
+    "sprs_b200_copy_dev": (_int, [_vp, _vp, _vp, _u64, _vp]),
+    "sprs_b200_spmv_allgather_dev": (_int, [_vp, _vp, _dp, _u64, _int, C.POINTER(_vp), _int, _vp]),
     "sprs_b200_spgemm_symbolic": (_int, [_vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_u64)]),
     "sprs_b200_spgemm_numeric": (_int, [_vp, _vp, _vp, _int, _vp, _int, _dp]),
     "sprs_b200_spgemm_numeric_dev": (_int, [_vp, _vp, C.POINTER(_vp)]),

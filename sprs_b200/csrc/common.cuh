@@ -75,10 +75,20 @@ static inline cudaStream_t pick_stream(sprs_b200_ctx*, void* stream) {
 int ctx_scratch(sprs_b200_ctx* ctx, int i, size_t bytes, void** out);
 int ctx_stage(sprs_b200_ctx* ctx, size_t bytes, void** out);
 
+// y targets of one SpMV: [0] = local y (already offset to this rank's first row), [1..n) =
+// the same position inside the peer GPUs' y buffers (CUDA IPC mappings).
+constexpr int SPMV_MAX_TARGETS = 8;
+struct SpmvTargets {
+    double* p[SPMV_MAX_TARGETS];
+    int n;
+};
+
 // ---- kernels' launch wrappers (defined in the .cu files) -----------------------
 int spmv_prepare(sprs_b200_ctx* ctx, sprs_b200_csmat* m, cudaStream_t s);
 int spmv_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x, double* d_y,
                 int accumulate, cudaStream_t s);
+int spmv_launch_targets(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
+                        const SpmvTargets& yt, int accumulate, cudaStream_t s);
 int spmm_rowmaj_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_b,
                        uint64_t ldb, uint64_t k, double* d_c, uint64_t ldc, int accumulate,
                        cudaStream_t s);

@@ -134,14 +134,25 @@ __global__ void tile_row_kernel(const P* __restrict__ indptr, uint32_t rows, uin
 struct TileCtx {
     uint64_t k0, k1;
     uint32_t r1;  // first row NOT owned (== carry row when < rows)
-    double* y;
+    const SpmvTargets* yt;  // the kernel parameter itself (constant bank, static indices)
     double* carry_slot;
     int accumulate;
 };
 
+// y[r] is written to every target buffer: target 0 is this GPU's own y; targets 1.. are the
+// peer GPUs' y buffers mapped through CUDA IPC (fused SpMV + all-gather over NVLink: the
+// result of a row leaves for the peers the moment it is reduced, overlapped with the rest
+// of the kernel, instead of a separate collective afterwards).
 __device__ __forceinline__ void emit_row(const TileCtx& tc, uint64_t r, double sum) {
     if (r < tc.r1) {
-        tc.y[r] = tc.accumulate ? __dadd_rn(tc.y[r], sum) : sum;
+        double* y0 = tc.yt->p[0] + r;
+        const double v = tc.accumulate ? __dadd_rn(*y0, sum) : sum;
+        *y0 = v;
+        if (tc.yt->n > 1) {
+#pragma unroll
+            for (int q = 1; q < SPMV_MAX_TARGETS; ++q)
+                if (q < tc.yt->n) tc.yt->p[q][r] = v;
+        }
     } else {
         *tc.carry_slot = sum;  // row continues in a later tile: spmv_fixup_kernel adds it
     }
@@ -207,7 +218,7 @@ template <typename P, int WT, int STAGES, int NWARPS, int MINB>
 __global__ void __launch_bounds__(NWARPS * 32, MINB)
     spmv_warp_kernel(const P* __restrict__ indptr, const uint32_t* __restrict__ indices,
                      const double* __restrict__ data, const uint32_t* __restrict__ tile_row,
-                     const double* __restrict__ x, double* __restrict__ y,
+                     const double* __restrict__ x, SpmvTargets yt,
                      double* __restrict__ carry, uint64_t nnz, uint32_t rows, uint64_t n_tiles,
                      int accumulate) {
     constexpr int EPL = WT / 32;               // non-zeros per lane per tile
@@ -325,7 +336,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
         tc.k0 = k0;
         tc.k1 = k1;
         tc.r1 = r1;
-        tc.y = y;
+        tc.yt = &yt;
         tc.carry_slot = carry + t;
         tc.accumulate = accumulate;
         const uint32_t avg = (uint32_t)((uint64_t)cnt / (r_last - r0 + 1));
@@ -361,7 +372,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
 // carries: tile t left the partial sum of row tile_row[t+1] in carry[t]; consecutive
 // tiles with the same carry row form a run that is summed in tile order by its head.
 __global__ void spmv_fixup_kernel(const uint32_t* __restrict__ tile_row,
-                                  const double* __restrict__ carry, double* __restrict__ y,
+                                  const double* __restrict__ carry, SpmvTargets yt,
                                   uint64_t n_tiles) {
     const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (t + 1 >= n_tiles) return;
@@ -370,7 +381,10 @@ __global__ void spmv_fixup_kernel(const uint32_t* __restrict__ tile_row,
     double sum = carry[t];
     for (uint64_t u = t + 1; u + 1 < n_tiles && tile_row[u + 1] == row; ++u)
         sum = __dadd_rn(sum, carry[u]);
-    y[row] = __dadd_rn(y[row], sum);
+    const double v = __dadd_rn(yt.p[0][row], sum);
+#pragma unroll
+    for (int q = 0; q < SPMV_MAX_TARGETS; ++q)
+        if (q < yt.n) yt.p[q][row] = v;
 }
 
 // ---- launch configuration ---------------------------------------------------------
@@ -392,8 +406,8 @@ SpmvVariant spmv_variant() {
 }
 
 template <typename P, int WT, int STAGES, int NWARPS, int CTAS>
-int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x, double* d_y,
-                   int accumulate, cudaStream_t s) {
+int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
+                   const SpmvTargets& yt, int accumulate, cudaStream_t s) {
     // CTAS resident CTAs per SM is also the kernel's __launch_bounds__ minBlocks: it sets the
     // register budget (ptxas otherwise picks ~40 registers and spills the gather buffers).
     auto kern = spmv_warp_kernel<P, WT, STAGES, NWARPS, CTAS>;
@@ -417,18 +431,18 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
     const uint64_t need = (m->n_tiles + NWARPS - 1) / NWARPS;
     if (grid > need) grid = need;
     kern<<<(unsigned)grid, NWARPS * 32, smem, s>>>((const P*)m->d_indptr, m->d_indices, m->d_data,
-                                                   m->d_tile_row, d_x, d_y, m->d_carry, m->nnz,
+                                                   m->d_tile_row, d_x, yt, m->d_carry, m->nnz,
                                                    (uint32_t)m->rows, m->n_tiles, accumulate);
     return SPRS_B200_OK;
 }
 
 template <typename P>
-int launch_dispatch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x, double* d_y,
-                    int accumulate, cudaStream_t s) {
+int launch_dispatch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
+                    const SpmvTargets& yt, int accumulate, cudaStream_t s) {
     const SpmvVariant v = spmv_variant();
 #define SPMV_CASE(WT, ST, NW, CT)                                                         \
     if (v.wt == WT && v.stages == ST && v.nwarps == NW && v.ctas_per_sm == CT)            \
-        return launch_variant<P, WT, ST, NW, CT>(ctx, m, d_x, d_y, accumulate, s);
+        return launch_variant<P, WT, ST, NW, CT>(ctx, m, d_x, yt, accumulate, s);
     SPMV_CASE(256, 2, 8, 3)
     SPMV_CASE(256, 2, 8, 2)
     SPMV_CASE(256, 1, 8, 6)
@@ -469,22 +483,31 @@ int spmv_prepare(sprs_b200_ctx* ctx, sprs_b200_csmat* m, cudaStream_t s) {
     return SPRS_B200_OK;
 }
 
-int spmv_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x, double* d_y,
-                int accumulate, cudaStream_t s) {
+int spmv_launch_targets(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
+                        const SpmvTargets& yt, int accumulate, cudaStream_t s) {
     if (m->storage != SPRS_B200_CSR)
         SPRS_FAIL(ctx, SPRS_B200_ERR_STORAGE, "Storage mismatch: spmv needs a CSR mirror");
     if (m->rows == 0) return SPRS_B200_OK;
     if (!m->d_tile_row) SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "csmat has no SpMV partition");
     if (m->indptr_bytes == 4)
-        SPRS_TRY(launch_dispatch<uint32_t>(ctx, m, d_x, d_y, accumulate, s));
+        SPRS_TRY(launch_dispatch<uint32_t>(ctx, m, d_x, yt, accumulate, s));
     else
-        SPRS_TRY(launch_dispatch<uint64_t>(ctx, m, d_x, d_y, accumulate, s));
+        SPRS_TRY(launch_dispatch<uint64_t>(ctx, m, d_x, yt, accumulate, s));
     ctx->launches += 1;
     if (m->n_tiles > 1) {
         const unsigned fgrid = (unsigned)((m->n_tiles - 1 + 255) / 256);
-        spmv_fixup_kernel<<<fgrid, 256, 0, s>>>(m->d_tile_row, m->d_carry, d_y, m->n_tiles);
+        spmv_fixup_kernel<<<fgrid, 256, 0, s>>>(m->d_tile_row, m->d_carry, yt, m->n_tiles);
         ctx->launches += 1;
     }
     SPRS_CUDA(ctx, cudaGetLastError());
     return SPRS_B200_OK;
+}
+
+int spmv_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x, double* d_y,
+                int accumulate, cudaStream_t s) {
+    SpmvTargets yt;
+    yt.n = 1;
+    yt.p[0] = d_y;
+    for (int q = 1; q < SPMV_MAX_TARGETS; ++q) yt.p[q] = nullptr;
+    return spmv_launch_targets(ctx, m, d_x, yt, accumulate, s);
 }

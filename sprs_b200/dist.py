@@ -78,3 +78,85 @@ class RowPartitionedSpMV:
         self.compute(x)
         self.exchange()
         return self.y
+
+
+class _DevPtr:
+    """Zero-copy torch view of a raw device allocation (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False),
+                                         "version": 2}
+
+
+class FusedAllGatherSpMV:
+    """Row-partitioned y = A x whose all-gather is fused into the SpMV kernel.
+
+    Every rank allocates its full-length y through sprs_b200_peer_alloc, ships the CUDA IPC
+    handle to the other ranks (torch.distributed object all-gather: plumbing), and maps
+    theirs.  step() launches ONE SpMV whose epilogue stores every finished row of this
+    rank's block into all `world` buffers over NVLink (sprs_b200_spmv_allgather_dev); a
+    stream-ordered 1-element all-reduce is the only remaining collective: it is the barrier
+    after which every rank's y is complete."""
+
+    def __init__(self, ctx, mirror, bounds, rank, world, n, dist, device):
+        import ctypes as C
+        import torch
+        self.ctx, self.mirror, self.bounds, self.rank, self.world = ctx, mirror, bounds, rank, world
+        self.dist, self.n = dist, n
+        lib = ctx.lib
+        own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        ctx.check(lib.sprs_b200_peer_alloc(ctx.h, 8 * max(n, 1), C.byref(own), handle))
+        self._own = own
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw))
+        self._peers = []
+        ptrs = [own.value]
+        for g in range(world):
+            if g == rank:
+                continue
+            p = C.c_void_p()
+            ctx.check(lib.sprs_b200_peer_open(ctx.h, handles[g], C.byref(p)))
+            self._peers.append(p)
+            ptrs.append(p.value)
+        self._targets = (C.c_void_p * len(ptrs))(*ptrs)
+        self.y = torch.as_tensor(_DevPtr(own.value, n), device=device)
+        self.y.zero_()
+        self._flag = torch.zeros(1, device=device)
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    @property
+    def rows_local(self):
+        return self.bounds[self.rank + 1] - self.bounds[self.rank]
+
+    def compute(self, x):
+        import ctypes as C
+        import torch
+        ctx = self.ctx
+        ctx.check(ctx.lib.sprs_b200_spmv_allgather_dev(
+            ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()), self.bounds[self.rank],
+            len(self._targets), self._targets, 0,
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def exchange(self):
+        if self.world > 1:
+            self.dist.all_reduce(self._flag)  # barrier: all peers' rows have landed
+
+    def step(self, x):
+        self.compute(x)
+        self.exchange()
+        return self.y
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        for p in self._peers:
+            self.ctx.lib.sprs_b200_peer_close(self.ctx.h, p)
+        self._peers = []
+        if self._own:
+            self.y = None
+            self.ctx.lib.sprs_b200_peer_free(self.ctx.h, self._own)
+            self._own = None
