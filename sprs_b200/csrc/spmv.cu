@@ -378,9 +378,28 @@ __global__ void spmv_fixup_kernel(const uint32_t* __restrict__ tile_row,
     if (t + 1 >= n_tiles) return;
     const uint32_t row = tile_row[t + 1];
     if (t > 0 && tile_row[t] == row) return;  // not the head of its run
+    // tile_row is sorted: the run [t, end) of tiles whose carry row is `row` ends at the
+    // first u with tile_row[u + 1] > row.  Binary search, then a load-independent sum in
+    // tile order (a hub row of 1e6 non-zeros is a run of ~4000 tiles: the old
+    // load-compare-branch loop made this kernel 7 % of the step).
+    uint64_t lo = t + 1, hi = n_tiles - 1;  // candidates for `end` (carry rows exist for u < n_tiles-1)
+    for (uint64_t step = 1; lo + step < hi; step <<= 1) {  // gallop: most runs are 1-2 tiles
+        if (tile_row[lo + step + 1] > row) {
+            hi = lo + step;
+            break;
+        }
+        lo += step;  // tiles lo .. lo+step still carry `row`... see invariant below
+    }
+    while (lo < hi) {
+        const uint64_t mid = lo + (hi - lo) / 2;
+        if (tile_row[mid + 1] > row)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
     double sum = carry[t];
-    for (uint64_t u = t + 1; u + 1 < n_tiles && tile_row[u + 1] == row; ++u)
-        sum = __dadd_rn(sum, carry[u]);
+#pragma unroll 8
+    for (uint64_t u = t + 1; u < lo; ++u) sum = __dadd_rn(sum, carry[u]);
     const double v = __dadd_rn(yt.p[0][row], sum);
 #pragma unroll
     for (int q = 0; q < SPMV_MAX_TARGETS; ++q)
