@@ -303,7 +303,8 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
-    if rank == 0:
+    use_sampler = rank == 0 and not os.environ.get("SPRS_BENCH_NO_SAMPLER")
+    if use_sampler:
         sampler.start()
         time.sleep(0.15)
     # ---- timed region: K steps, CUDA events on the launching stream, max over ranks
@@ -313,23 +314,33 @@ def main():
     tw0 = time.time()
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record()
+    cpu_t = []
     for i in range(args.steps):
+        cpu_t.append(time.perf_counter())
         evs[i][0].record()
         op.compute(x)
         evs[i][1].record()
         op.exchange()
         evs[i][2].record()
+    cpu_t.append(time.perf_counter())
     e_stop.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     tw1 = time.time()
-    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
+    clocks = sampler.stop(tw0, tw1) if use_sampler else None
     launches = ctx.launches - launches0
     total_ms = e_start.elapsed_time(e_stop)
     kern_ms = [evs[i][0].elapsed_time(evs[i][1]) for i in range(args.steps)]
     coll_ms = [evs[i][1].elapsed_time(evs[i][2]) for i in range(args.steps)]
+    if os.environ.get("SPRS_BENCH_DEBUG"):
+        gaps = [evs[i][2].elapsed_time(evs[i + 1][0]) for i in range(args.steps - 1)]
+        print("[rank %d] kern %s\n[rank %d] coll %s\n[rank %d] gap  %s\n[rank %d] cpu_enqueue_ms %s" % (
+            rank, ["%.2f" % v for v in kern_ms], rank, ["%.2f" % v for v in coll_ms], rank,
+            ["%.2f" % v for v in gaps], rank,
+            ["%.2f" % ((cpu_t[i + 1] - cpu_t[i]) * 1e3) for i in range(args.steps)]),
+            file=sys.stderr, flush=True)
     t = torch.tensor([total_ms, statistics.mean(kern_ms), statistics.mean(coll_ms)],
                      device=dev, dtype=torch.float64)
     if world > 1:

@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(NT)
 }
 
 // ---- numeric, large rows: dense accumulator slot in global memory + bitmap --------
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(1024)
     num_large_kernel(const uint32_t* __restrict__ a_ip, const uint32_t* __restrict__ a_idx,
                      const double* __restrict__ a_val, const uint32_t* __restrict__ b_ip,
                      const uint32_t* __restrict__ b_idx, const double* __restrict__ b_val,
@@ -353,11 +353,12 @@ __global__ void __launch_bounds__(NT)
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t chunk_total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nt = blockDim.x, nwarps = blockDim.x >> 5;  // 256..1024 threads
     for (uint32_t li = blockIdx.x; li < n_list; li += gridDim.x) {
         const uint32_t r = list[li];
-        for (uint32_t i = threadIdx.x; i < words; i += NT) bm[i] = 0;
+        for (uint32_t i = threadIdx.x; i < words; i += nt) bm[i] = 0;
         __syncthreads();
-        for (uint32_t k = a_ip[r] + warp, e = a_ip[r + 1]; k < e; k += WARPS) {
+        for (uint32_t k = a_ip[r] + warp, e = a_ip[r + 1]; k < e; k += nwarps) {
             const uint32_t br = a_idx[k];
             const double av = a_val[k];
             for (uint32_t p = b_ip[br] + lane, pe = b_ip[br + 1]; p < pe; p += 32) {
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(NT)
         __syncthreads();
         // ordered extraction: walk the bitmap 256 words at a time
         uint64_t out = c_ip[r];
-        for (uint32_t w0 = 0; w0 < words; w0 += NT) {
+        for (uint32_t w0 = 0; w0 < words; w0 += nt) {
             const uint32_t w = w0 + threadIdx.x;
             uint32_t bits = w < words ? bm[w] : 0u;
             const uint32_t c = __popc(bits);
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(NT)
             if (lane == 31) wsum[warp] = inc;
             __syncthreads();
             if (warp == 0) {
-                uint32_t v = lane < WARPS ? wsum[lane] : 0u, vi = v;
+                uint32_t v = lane < (int)nwarps ? wsum[lane] : 0u, vi = v;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t u = __shfl_up_sync(0xffffffffu, vi, o);
@@ -447,9 +448,14 @@ int plan_large(sprs_b200_ctx* ctx, uint64_t cols, uint32_t n_large, bool need_ac
                LargeWorkspace* w, cudaStream_t s) {
     w->words = (uint32_t)((cols + 31) / 32);
     unsigned grid = (unsigned)std::min<uint64_t>(n_large, (uint64_t)ctx->sm_count * 2);
-    if (need_acc) {  // bound the dense slots to ~8 GB
+    if (need_acc) {
+        // The dense accumulators take f64 atomics from every product: keep ALL live slots
+        // inside ~3/4 of L2 so the atomics resolve in L2 instead of DRAM (the first version
+        // used 2 slots per SM = 1.2 GB at 500k columns and ran DRAM-bound), and give each
+        // row a 1024-thread CTA instead.
         const uint64_t per = cols * sizeof(double);
-        const uint64_t cap = std::max<uint64_t>(1, (8ull << 30) / std::max<uint64_t>(per, 1));
+        const uint64_t budget = ctx->l2_bytes ? (uint64_t)ctx->l2_bytes * 3 / 4 : (64ull << 20);
+        const uint64_t cap = std::max<uint64_t>(4, budget / std::max<uint64_t>(per, 1));
         grid = (unsigned)std::min<uint64_t>(grid, cap);
     }
     if (grid == 0) grid = 1;
@@ -505,7 +511,8 @@ int run_numeric(sprs_b200_ctx* ctx, sprs_b200_spgemm* p, uint32_t* d_cidx, doubl
                                      (int)w.smem) != cudaSuccess)
                 st = SPRS_B200_ERR_CUDA;
         if (st == SPRS_B200_OK) {
-            num_large_kernel<<<w.grid, NT, w.smem, s>>>(
+            const unsigned big_nt = w.grid < (unsigned)ctx->sm_count ? 1024 : NT;
+            num_large_kernel<<<w.grid, big_nt, w.smem, s>>>(
                 a_ip, a->d_indices, a->d_data, b_ip, b->d_indices, b->d_data, p->d_cptr, l2,
                 h_cnt[2], w.words, p->cols, w.bitmaps, w.acc, d_cidx, d_cval);
             ctx->launches += 1;
