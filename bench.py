@@ -244,7 +244,8 @@ def main():
     import torch.distributed as dist
     import sprs_b200 as sp
     from sprs_b200 import generate as G
-    from sprs_b200.dist import FusedAllGatherSpMV, RowPartitionedSpMV, nnz_balanced_bounds
+    from sprs_b200.dist import (FusedAllGatherSpMV, RowPartitionedSpMV, fit_row_cost,
+                                nnz_balanced_bounds)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -270,7 +271,28 @@ def main():
     x = G.normal_vector(ctx, n)
     bounds = nnz_balanced_bounds(full.indptr, world)
     r0, r1 = bounds[rank], bounds[rank + 1]
+    row_cost = 0.0
     if world > 1:
+        # calibrate the partition: time this rank's nnz-balanced block, fit
+        # t = alpha*nnz + beta*rows over the ranks, re-cut with rows weighted by beta/alpha
+        a = full.slice_rows(r0, r1)
+        yt = torch.empty(max(r1 - r0, 1), device=dev, dtype=torch.float64)
+        for _ in range(2):
+            G.spmv(ctx, a, x, yt)
+        ce0, ce1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ce0.record()
+        for _ in range(3):
+            G.spmv(ctx, a, x, yt)
+        ce1.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([a.nnz, r1 - r0, ce0.elapsed_time(ce1) / 3e3], device=dev,
+                            dtype=torch.float64)
+        allm = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allm, mine)
+        row_cost = fit_row_cost([m.tolist() for m in allm])
+        del a, yt
+        bounds = nnz_balanced_bounds(full.indptr, world, row_cost=row_cost)
+        r0, r1 = bounds[rank], bounds[rank + 1]
         a = full.slice_rows(r0, r1)
     else:
         a = full
@@ -299,14 +321,15 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    use_sampler = rank == 0 and not os.environ.get("SPRS_BENCH_NO_SAMPLER")
+    if use_sampler:  # started BEFORE the barrier so that no rank enters the timed region late
+        sampler.start()
+        time.sleep(0.05)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    use_sampler = rank == 0 and not os.environ.get("SPRS_BENCH_NO_SAMPLER")
-    if use_sampler:
-        sampler.start()
-        time.sleep(0.15)
+
     # ---- timed region: K steps, CUDA events on the launching stream, max over ranks
     launches0 = ctx.launches
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
@@ -398,7 +421,9 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "n": n, "nnz": nnz, "nnz_per_row": npr,
-                       "generator": gen, "index_bytes": 4, "partition": "nnz-balanced row blocks",
+                       "generator": gen, "index_bytes": 4,
+                       "partition": "contiguous row blocks balanced on nnz + %.2f*rows "
+                                    "(row cost fitted from per-rank timings)" % row_cost,
                        "collective": ("none" if world == 1 else
                                       "all-gather of y fused into the SpMV kernel (peer stores "
                                       "over NVLink) + 1-element NCCL all_reduce barrier"

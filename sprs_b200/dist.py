@@ -10,10 +10,14 @@ NCCL on GPUs, gloo in the CPU tests (tests/test_dist_gloo.py).
 import numpy as np
 
 
-def nnz_balanced_bounds(indptr, nparts):
-    """Row cut points r_0=0 <= r_1 <= ... <= r_nparts=rows with ~nnz/nparts non-zeros per
-    block: r_g = first row whose start offset reaches g*nnz/nparts (binary search in
-    indptr).  Accepts a numpy array or a torch tensor (any device)."""
+def nnz_balanced_bounds(indptr, nparts, row_cost=0.0):
+    """Row cut points r_0=0 <= r_1 <= ... <= r_nparts=rows with equal COST per block, where
+    cost(rows [a,b)) = nnz(a,b) + row_cost*(b-a): r_g = first row whose cost prefix reaches
+    g*total/nparts (binary search in the monotone prefix indptr[r] + row_cost*r).
+    row_cost = 0 balances non-zeros only; a positive row_cost (in non-zero equivalents,
+    fitted from timings by fit_row_cost) accounts for the per-row work -- indptr reads, y
+    stores, short-row reductions -- that makes sparse row ranges slower per non-zero.
+    Accepts a numpy array or a torch tensor (any device)."""
     try:
         import torch
         is_torch = isinstance(indptr, torch.Tensor)
@@ -25,7 +29,14 @@ def nnz_balanced_bounds(indptr, nparts):
         ip = indptr.to(torch.int64)
         base = int(ip[0].item())
         nnz = int(ip[-1].item()) - base
-        if nparts > 1:
+        if nparts > 1 and row_cost > 0:
+            cost = (ip - base).to(torch.float64) + row_cost * torch.arange(
+                rows + 1, device=ip.device, dtype=torch.float64)
+            total = float(cost[-1].item())
+            targets = torch.tensor([total * g / nparts for g in range(1, nparts)],
+                                   device=ip.device, dtype=torch.float64)
+            cuts = torch.searchsorted(cost, targets).tolist()
+        elif nparts > 1:
             targets = torch.tensor([base + (nnz * g) // nparts for g in range(1, nparts)],
                                    device=ip.device, dtype=torch.int64)
             cuts = torch.searchsorted(ip, targets).tolist()
@@ -35,11 +46,30 @@ def nnz_balanced_bounds(indptr, nparts):
         ip = np.asarray(indptr).astype(np.int64)
         base = int(ip[0])
         nnz = int(ip[-1]) - base
-        cuts = [int(np.searchsorted(ip, base + (nnz * g) // nparts)) for g in range(1, nparts)]
+        if row_cost > 0:
+            cost = (ip - base).astype(np.float64) + row_cost * np.arange(rows + 1)
+            cuts = [int(np.searchsorted(cost, cost[-1] * g / nparts)) for g in range(1, nparts)]
+        else:
+            cuts = [int(np.searchsorted(ip, base + (nnz * g) // nparts))
+                    for g in range(1, nparts)]
     bounds = [0] + [min(max(int(c), 0), rows) for c in cuts] + [rows]
     for i in range(1, len(bounds)):  # keep monotone
         bounds[i] = max(bounds[i], bounds[i - 1])
     return bounds
+
+
+def fit_row_cost(samples):
+    """Least-squares fit of t = alpha*nnz + beta*rows over (nnz, rows, seconds) samples (one
+    per rank); returns beta/alpha = the cost of one row in non-zero equivalents, clamped to
+    [0, 64].  With fewer than two distinct samples returns 0."""
+    a = np.array([[s[0], s[1]] for s in samples], dtype=np.float64)
+    t = np.array([s[2] for s in samples], dtype=np.float64)
+    if len(samples) < 2 or np.linalg.matrix_rank(a) < 2:
+        return 0.0
+    (alpha, beta), *_ = np.linalg.lstsq(a, t, rcond=None)
+    if alpha <= 0:
+        return 0.0
+    return float(min(max(beta / alpha, 0.0), 64.0))
 
 
 class RowPartitionedSpMV:

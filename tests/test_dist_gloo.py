@@ -32,6 +32,25 @@ def test_nnz_balanced_bounds_numpy_and_torch():
     assert nnz_balanced_bounds(np.zeros(11, np.int64), 2) == [0, 0, 10]
 
 
+def test_row_cost_partition_and_fit():
+    from sprs_b200.dist import fit_row_cost, nnz_balanced_bounds
+    import torch
+    # first half: 10 heavy rows; second half: 10000 light rows with the same total nnz
+    lens = np.concatenate([np.full(10, 1000), np.ones(10000, dtype=np.int64)])
+    ip = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=ip[1:])
+    assert nnz_balanced_bounds(ip, 2)[1] == 10
+    b = nnz_balanced_bounds(ip, 2, row_cost=4.0)  # rows cost 4 nnz each: cut moves right
+    assert b[1] > 10 and b == nnz_balanced_bounds(torch.from_numpy(ip), 2, row_cost=4.0)
+    cost = lambda r0, r1: (ip[r1] - ip[r0]) + 4.0 * (r1 - r0)
+    assert abs(cost(0, b[1]) - cost(b[1], len(lens))) <= 1000 + 4
+    # fit: t = 2e-9*nnz + 1e-8*rows  ->  row cost 5 nnz
+    samples = [(5e8, 1e5, 2e-9 * 5e8 + 1e-8 * 1e5), (5e8, 9e6, 2e-9 * 5e8 + 1e-8 * 9e6)]
+    assert abs(fit_row_cost(samples) - 5.0) < 1e-6
+    assert fit_row_cost(samples[:1]) == 0.0
+    assert fit_row_cost([(1e6, 10, 1.0), (1e6, 20, 0.5)]) == 0.0  # negative beta clamps to 0
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
