@@ -448,14 +448,11 @@ int plan_large(sprs_b200_ctx* ctx, uint64_t cols, uint32_t n_large, bool need_ac
                LargeWorkspace* w, cudaStream_t s) {
     w->words = (uint32_t)((cols + 31) / 32);
     unsigned grid = (unsigned)std::min<uint64_t>(n_large, (uint64_t)ctx->sm_count * 2);
-    if (need_acc) {
-        // The dense accumulators take f64 atomics from every product: keep ALL live slots
-        // inside ~3/4 of L2 so the atomics resolve in L2 instead of DRAM (the first version
-        // used 2 slots per SM = 1.2 GB at 500k columns and ran DRAM-bound), and give each
-        // row a 1024-thread CTA instead.
+    if (need_acc) {  // bound the dense slots to ~8 GB
+        // (tried: only as many slots as fit in L2, with 1024-thread CTAs -- 2.8x SLOWER on
+        // config 4, profiles/r1_bench_spgemm_b.json; parallelism matters more than locality)
         const uint64_t per = cols * sizeof(double);
-        const uint64_t budget = ctx->l2_bytes ? (uint64_t)ctx->l2_bytes * 3 / 4 : (64ull << 20);
-        const uint64_t cap = std::max<uint64_t>(4, budget / std::max<uint64_t>(per, 1));
+        const uint64_t cap = std::max<uint64_t>(1, (8ull << 30) / std::max<uint64_t>(per, 1));
         grid = (unsigned)std::min<uint64_t>(grid, cap);
     }
     if (grid == 0) grid = 1;

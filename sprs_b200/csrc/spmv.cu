@@ -134,7 +134,8 @@ __global__ void tile_row_kernel(const P* __restrict__ indptr, uint32_t rows, uin
 struct TileCtx {
     uint64_t k0, k1;
     uint32_t r1;  // first row NOT owned (== carry row when < rows)
-    const SpmvTargets* yt;  // the kernel parameter itself (constant bank, static indices)
+    double* y;    // this GPU's y (target 0)
+    const SpmvTargets* yt;  // MULTI only: the kernel parameter itself (constant bank)
     double* carry_slot;
     int accumulate;
 };
@@ -143,12 +144,12 @@ struct TileCtx {
 // peer GPUs' y buffers mapped through CUDA IPC (fused SpMV + all-gather over NVLink: the
 // result of a row leaves for the peers the moment it is reduced, overlapped with the rest
 // of the kernel, instead of a separate collective afterwards).
+template <bool MULTI>
 __device__ __forceinline__ void emit_row(const TileCtx& tc, uint64_t r, double sum) {
     if (r < tc.r1) {
-        double* y0 = tc.yt->p[0] + r;
-        const double v = tc.accumulate ? __dadd_rn(*y0, sum) : sum;
-        *y0 = v;
-        if (tc.yt->n > 1) {
+        const double v = tc.accumulate ? __dadd_rn(tc.y[r], sum) : sum;
+        tc.y[r] = v;
+        if (MULTI) {
 #pragma unroll
             for (int q = 1; q < SPMV_MAX_TARGETS; ++q)
                 if (q < tc.yt->n) tc.yt->p[q][r] = v;
@@ -160,7 +161,7 @@ __device__ __forceinline__ void emit_row(const TileCtx& tc, uint64_t r, double s
 
 // Reduce rows [r0, r_last] of one warp tile with groups of G lanes per row.  Row
 // boundaries come 31 rows at a time: lane L holds indptr[rbase + L].
-template <typename P, int G>
+template <typename P, int G, bool MULTI>
 __device__ __forceinline__ void reduce_rows_warp(const TileCtx& tc, const P* __restrict__ indptr,
                                                  const double* sprod, uint32_t r0,
                                                  uint64_t r_last, uint64_t b_first, int lane) {
@@ -193,7 +194,7 @@ __device__ __forceinline__ void reduce_rows_warp(const TileCtx& tc, const P* __r
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1)
                 acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-            if (gl == 0 && valid && !is_long) emit_row(tc, rbase + j, acc);
+            if (gl == 0 && valid && !is_long) emit_row<MULTI>(tc, rbase + j, acc);
             if (G < 32) {  // rows too long for their group: the whole warp takes them
                 unsigned pending = __ballot_sync(0xffffffffu, gl == 0 && valid && is_long);
                 while (pending) {
@@ -207,14 +208,73 @@ __device__ __forceinline__ void reduce_rows_warp(const TileCtx& tc, const P* __r
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1)
                         a2 = __dadd_rn(a2, __shfl_xor_sync(0xffffffffu, a2, o));
-                    if (lane == 0) emit_row(tc, rbase + jj, a2);
+                    if (lane == 0) emit_row<MULTI>(tc, rbase + jj, a2);
                 }
             }
         }
     }
 }
 
-template <typename P, int WT, int STAGES, int NWARPS, int MINB>
+// Register-path reduction for tiles that touch at most 8 rows (the bulk of the non-zeros of
+// long-row matrices): the products never go to shared memory.  Each lane adds its EPL
+// products into up to 8 per-row partials (its element e = lane + 32*i belongs to row j iff
+// bl_j <= e < bl_{j+1}), then ONE multi-value butterfly reduces the 8 partials across the
+// warp in 18 shuffles (xor 16 / 8 / 4 halve the number of live values, xor 2 / 1 finish);
+// lane 4*j ends up with the sum of row j.  Versus the shared-memory path this removes the
+// product store + reload and ~3/4 of the shuffles -- all of them L1TEX/MIO wavefronts, the
+// pipe the gathers saturate (profiles/r1_spmv_notes.md section 4).  Deterministic order.
+template <int EPL, bool MULTI>
+__device__ __forceinline__ void reduce_rows_regs(const TileCtx& tc, const double (&p)[EPL],
+                                                 int bl, uint32_t r0, int nrows, int lane) {
+    constexpr unsigned FULL = 0xffffffffu;
+    double part[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[j] = 0.0;
+    int lo = __shfl_sync(FULL, bl, 0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j < nrows) {  // warp-uniform
+            const int hi = __shfl_sync(FULL, bl, j + 1);
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) {
+                const int e = lane + 32 * i;
+                part[j] = (e >= lo && e < hi) ? __dadd_rn(part[j], p[i]) : part[j];
+            }
+            lo = hi;
+        }
+    }
+    double v4[4], v2[2], v;
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double send = up ? part[j] : part[j + 4];
+            const double keep = up ? part[j + 4] : part[j];
+            v4[j] = __dadd_rn(keep, __shfl_xor_sync(FULL, send, 16));
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double send = up ? v4[j] : v4[j + 2];
+            const double keep = up ? v4[j + 2] : v4[j];
+            v2[j] = __dadd_rn(keep, __shfl_xor_sync(FULL, send, 8));
+        }
+    }
+    {
+        const bool up = lane & 4;
+        const double send = up ? v2[0] : v2[1];
+        const double keep = up ? v2[1] : v2[0];
+        v = __dadd_rn(keep, __shfl_xor_sync(FULL, send, 4));
+    }
+    v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 2));
+    v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 1));
+    const int row = lane >> 2;  // 4*bit4 + 2*bit3 + bit2
+    if ((lane & 3) == 0 && row < nrows) emit_row<MULTI>(tc, (uint64_t)r0 + row, v);
+}
+
+template <typename P, int WT, int STAGES, int NWARPS, int MINB, bool MULTI>
 __global__ void __launch_bounds__(NWARPS * 32, MINB)
     spmv_warp_kernel(const P* __restrict__ indptr, const uint32_t* __restrict__ indices,
                      const double* __restrict__ data, const uint32_t* __restrict__ tile_row,
@@ -281,6 +341,9 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
         const uint64_t r_last = (r1 < rows) ? (uint64_t)r1 : (uint64_t)r1 - 1;
         const uint64_t tnext = t + GW;
         uint32_t r0n = 0, r1n = 0;
+        const int nrows_t = (r_last - r0 + 1) > 64 ? 64 : (int)(r_last - r0 + 1);
+        const bool regpath = full && nrows_t <= 8;  // warp-uniform
+        double preg[EPL];
         if (full && DIRECT) {
             // register path: coalesced streaming loads (no L1 allocation, L2 evict_first),
             // products to the warp's 8*WT-byte shared buffer for the reduction
@@ -298,8 +361,13 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
                 r0n = tile_row[tnext];
                 r1n = tile_row[tnext + 1];
             }
+            if (regpath) {
 #pragma unroll
-            for (int i = 0; i < EPL; ++i) sprod[lane + i * 32] = __dmul_rn(v[i], xv[i]);
+                for (int i = 0; i < EPL; ++i) preg[i] = __dmul_rn(v[i], xv[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) sprod[lane + i * 32] = __dmul_rn(v[i], xv[i]);
+            }
         } else if (full) {
             mbar_wait(&bars[warp][s], (phases >> s) & 1u);
             phases ^= 1u << s;
@@ -313,9 +381,14 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
                 r0n = tile_row[tnext];
                 r1n = tile_row[tnext + 1];
             }
+            if (regpath) {
 #pragma unroll
-            for (int i = 0; i < EPL; ++i)
-                sprod[lane + i * 32] = __dmul_rn(sprod[lane + i * 32], xv[i]);
+                for (int i = 0; i < EPL; ++i) preg[i] = __dmul_rn(sprod[lane + i * 32], xv[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < EPL; ++i)
+                    sprod[lane + i * 32] = __dmul_rn(sprod[lane + i * 32], xv[i]);
+            }
         } else {  // ragged last tile: guarded loads, no bulk copy past the arrays
             for (int e = lane; e < cnt; e += 32)
                 sprod[e] = __dmul_rn(data[k0 + e], ldg_f64_hint(x + indices[k0 + e], polx));
@@ -336,22 +409,31 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
         tc.k0 = k0;
         tc.k1 = k1;
         tc.r1 = r1;
+        tc.y = yt.p[0];
         tc.yt = &yt;
         tc.carry_slot = carry + t;
         tc.accumulate = accumulate;
         const uint32_t avg = (uint32_t)((uint64_t)cnt / (r_last - r0 + 1));
-        if (avg <= 6)
-            reduce_rows_warp<P, 1>(tc, indptr, sprod, r0, r_last, b_first, lane);
+        if (regpath) {
+            // tile-local row boundaries: lane L holds clamp(indptr[r0+L] - k0, 0, WT), WT beyond
+            int bl = WT;
+            if (lane <= nrows_t) {
+                const uint64_t bb = b_first > k0 ? b_first - k0 : 0;
+                bl = bb < (uint64_t)WT ? (int)bb : WT;
+            }
+            reduce_rows_regs<EPL, MULTI>(tc, preg, bl, r0, nrows_t, lane);
+        } else if (avg <= 6)
+            reduce_rows_warp<P, 1, MULTI>(tc, indptr, sprod, r0, r_last, b_first, lane);
         else if (avg <= 12)
-            reduce_rows_warp<P, 2>(tc, indptr, sprod, r0, r_last, b_first, lane);
+            reduce_rows_warp<P, 2, MULTI>(tc, indptr, sprod, r0, r_last, b_first, lane);
         else if (avg <= 24)
-            reduce_rows_warp<P, 4>(tc, indptr, sprod, r0, r_last, b_first, lane);
+            reduce_rows_warp<P, 4, MULTI>(tc, indptr, sprod, r0, r_last, b_first, lane);
         else if (avg <= 48)
-            reduce_rows_warp<P, 8>(tc, indptr, sprod, r0, r_last, b_first, lane);
+            reduce_rows_warp<P, 8, MULTI>(tc, indptr, sprod, r0, r_last, b_first, lane);
         else if (avg <= 96)
-            reduce_rows_warp<P, 16>(tc, indptr, sprod, r0, r_last, b_first, lane);
+            reduce_rows_warp<P, 16, MULTI>(tc, indptr, sprod, r0, r_last, b_first, lane);
         else
-            reduce_rows_warp<P, 32>(tc, indptr, sprod, r0, r_last, b_first, lane);
+            reduce_rows_warp<P, 32, MULTI>(tc, indptr, sprod, r0, r_last, b_first, lane);
         __syncwarp();
         // refill this stage (generic-proxy accesses above must be ordered before the
         // async-proxy writes of the next bulk copy)
@@ -429,9 +511,11 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
                    const SpmvTargets& yt, int accumulate, cudaStream_t s) {
     // CTAS resident CTAs per SM is also the kernel's __launch_bounds__ minBlocks: it sets the
     // register budget (ptxas otherwise picks ~40 registers and spills the gather buffers).
-    auto kern = spmv_warp_kernel<P, WT, STAGES, NWARPS, CTAS>;
+    auto kern = yt.n > 1 ? spmv_warp_kernel<P, WT, STAGES, NWARPS, CTAS, true>
+                         : spmv_warp_kernel<P, WT, STAGES, NWARPS, CTAS, false>;
     const size_t smem = STAGES == 0 ? (size_t)NWARPS * WT * 8 : (size_t)NWARPS * STAGES * WT * 12;
-    static bool configured = false;
+    static bool configured_single = false, configured_multi = false;
+    bool& configured = yt.n > 1 ? configured_multi : configured_single;
     if (!configured) {
         SPRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)smem));
