@@ -131,6 +131,8 @@ __global__ void tile_row_kernel(const P* __restrict__ indptr, uint32_t rows, uin
     tile_row[t] = lo;
 }
 
+constexpr int SPMV_REG_ROWS = 16;  // tiles touching <= this many rows reduce in registers
+
 struct TileCtx {
     uint64_t k0, k1;
     uint32_t r1;  // first row NOT owned (== carry row when < rows)
@@ -225,16 +227,18 @@ __device__ __forceinline__ void reduce_rows_warp(const TileCtx& tc, const P* __r
 // pipe the gathers saturate (profiles/r1_spmv_notes.md section 4).  Deterministic order.
 template <int EPL, bool MULTI>
 __device__ __forceinline__ void reduce_rows_regs(const TileCtx& tc, const double (&p)[EPL],
-                                                 int bl, uint32_t r0, int nrows, int lane) {
+                                                 int bl, uint32_t r0, int jbase, int nrows,
+                                                 int lane) {
+    // rows jbase .. jbase+nrows-1 of the tile (nrows <= 8); bl: lane L = boundary of row L
     constexpr unsigned FULL = 0xffffffffu;
     double part[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) part[j] = 0.0;
-    int lo = __shfl_sync(FULL, bl, 0);
+    int lo = __shfl_sync(FULL, bl, jbase);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         if (j < nrows) {  // warp-uniform
-            const int hi = __shfl_sync(FULL, bl, j + 1);
+            const int hi = __shfl_sync(FULL, bl, jbase + j + 1);
 #pragma unroll
             for (int i = 0; i < EPL; ++i) {
                 const int e = lane + 32 * i;
@@ -271,7 +275,7 @@ __device__ __forceinline__ void reduce_rows_regs(const TileCtx& tc, const double
     v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 2));
     v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 1));
     const int row = lane >> 2;  // 4*bit4 + 2*bit3 + bit2
-    if ((lane & 3) == 0 && row < nrows) emit_row<MULTI>(tc, (uint64_t)r0 + row, v);
+    if ((lane & 3) == 0 && row < nrows) emit_row<MULTI>(tc, (uint64_t)r0 + jbase + row, v);
 }
 
 template <typename P, int WT, int STAGES, int NWARPS, int MINB, bool MULTI>
@@ -342,7 +346,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
         const uint64_t tnext = t + GW;
         uint32_t r0n = 0, r1n = 0;
         const int nrows_t = (r_last - r0 + 1) > 64 ? 64 : (int)(r_last - r0 + 1);
-        const bool regpath = full && nrows_t <= 8;  // warp-uniform
+        const bool regpath = full && nrows_t <= SPMV_REG_ROWS;  // warp-uniform
         double preg[EPL];
         if (full && DIRECT) {
             // register path: coalesced streaming loads (no L1 allocation, L2 evict_first),
@@ -421,7 +425,9 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
                 const uint64_t bb = b_first > k0 ? b_first - k0 : 0;
                 bl = bb < (uint64_t)WT ? (int)bb : WT;
             }
-            reduce_rows_regs<EPL, MULTI>(tc, preg, bl, r0, nrows_t, lane);
+            for (int jb = 0; jb < nrows_t; jb += 8)
+                reduce_rows_regs<EPL, MULTI>(tc, preg, bl, r0, jb,
+                                             nrows_t - jb < 8 ? nrows_t - jb : 8, lane);
         } else if (avg <= 6)
             reduce_rows_warp<P, 1, MULTI>(tc, indptr, sprod, r0, r_last, b_first, lane);
         else if (avg <= 12)
@@ -496,7 +502,7 @@ struct SpmvVariant {
 // SPRS_B200_SPMV_VARIANT="wt,stages,nwarps,ctas" overrides it for tuning runs.
 SpmvVariant spmv_variant() {
     static SpmvVariant v = [] {
-        SpmvVariant d{256, 2, 8, 3};
+        SpmvVariant d{256, 0, 8, 3};
         if (const char* e = getenv("SPRS_B200_SPMV_VARIANT")) {
             int a, b, c, g;
             if (sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &g) == 4) d = SpmvVariant{a, b, c, g};
@@ -546,19 +552,19 @@ int launch_dispatch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* 
 #define SPMV_CASE(WT, ST, NW, CT)                                                         \
     if (v.wt == WT && v.stages == ST && v.nwarps == NW && v.ctas_per_sm == CT)            \
         return launch_variant<P, WT, ST, NW, CT>(ctx, m, d_x, yt, accumulate, s);
+    SPMV_CASE(256, 0, 8, 3)
     SPMV_CASE(256, 2, 8, 3)
     SPMV_CASE(256, 2, 8, 2)
-    SPMV_CASE(256, 1, 8, 6)
-    SPMV_CASE(512, 1, 8, 2)
     SPMV_CASE(256, 1, 8, 3)
     SPMV_CASE(256, 1, 8, 4)
     SPMV_CASE(384, 1, 8, 3)
-    SPMV_CASE(256, 0, 8, 3)
+    SPMV_CASE(512, 1, 8, 2)
     SPMV_CASE(256, 0, 8, 4)
-    SPMV_CASE(256, 0, 8, 6)
+    SPMV_CASE(256, 0, 16, 2)
+    SPMV_CASE(384, 0, 8, 3)
     SPMV_CASE(512, 0, 8, 2)
     SPMV_CASE(512, 0, 8, 3)
-    SPMV_CASE(128, 0, 8, 8)
+    SPMV_CASE(256, 0, 8, 2)
 #undef SPMV_CASE
     SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "unknown SPRS_B200_SPMV_VARIANT");
 }
