@@ -131,7 +131,9 @@ __global__ void tile_row_kernel(const P* __restrict__ indptr, uint32_t rows, uin
     tile_row[t] = lo;
 }
 
-constexpr int SPMV_REG_ROWS = 16;  // tiles touching <= this many rows reduce in registers
+constexpr int SPMV_REG_ROWS = 9;  // tiles touching <= this many rows reduce in registers
+// (8 rows through the multi-value butterfly + one more -- typically the row cut by the tile
+// end -- through a plain one; a two-pass 16-row version measured slower, sweep v6)
 
 struct TileCtx {
     uint64_t k0, k1;
@@ -235,6 +237,19 @@ __device__ __forceinline__ void reduce_rows_regs(const TileCtx& tc, const double
 #pragma unroll
     for (int j = 0; j < 8; ++j) part[j] = 0.0;
     int lo = __shfl_sync(FULL, bl, jbase);
+    if (nrows > 8) {  // ninth row: everything from boundary 8 to boundary 9, plain butterfly
+        const int lo8 = __shfl_sync(FULL, bl, jbase + 8), hi8 = __shfl_sync(FULL, bl, jbase + 9);
+        double ex = 0.0;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+            const int e = lane + 32 * i;
+            ex = (e >= lo8 && e < hi8) ? __dadd_rn(ex, p[i]) : ex;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ex = __dadd_rn(ex, __shfl_xor_sync(FULL, ex, o));
+        if (lane == 0) emit_row<MULTI>(tc, (uint64_t)r0 + jbase + 8, ex);
+        nrows = 8;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         if (j < nrows) {  // warp-uniform
@@ -425,9 +440,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
                 const uint64_t bb = b_first > k0 ? b_first - k0 : 0;
                 bl = bb < (uint64_t)WT ? (int)bb : WT;
             }
-            for (int jb = 0; jb < nrows_t; jb += 8)
-                reduce_rows_regs<EPL, MULTI>(tc, preg, bl, r0, jb,
-                                             nrows_t - jb < 8 ? nrows_t - jb : 8, lane);
+            reduce_rows_regs<EPL, MULTI>(tc, preg, bl, r0, 0, nrows_t, lane);
         } else if (avg <= 6)
             reduce_rows_warp<P, 1, MULTI>(tc, indptr, sprod, r0, r_last, b_first, lane);
         else if (avg <= 12)
