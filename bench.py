@@ -437,7 +437,7 @@ def main():
                          "kernel": "spmv_tile_kernel (+ spmv_fixup_kernel)",
                          "kernel_ms": kern_ms_avg, "peak_source": peak_src,
                          "algorithmic_bytes": "12*nnz + 8*rows of this rank's block per launch",
-                         "variant": os.environ.get("SPRS_B200_SPMV_VARIANT", "default 256,2,8,3")},
+                         "variant": os.environ.get("SPRS_B200_SPMV_VARIANT", "default 384,1,8,3 (wt,stages,warps,ctas/SM)")},
             "collective_ms": coll_ms_avg,
             "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s",
                     "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * n * world,

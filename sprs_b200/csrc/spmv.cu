@@ -515,7 +515,7 @@ struct SpmvVariant {
 // SPRS_B200_SPMV_VARIANT="wt,stages,nwarps,ctas" overrides it for tuning runs.
 SpmvVariant spmv_variant() {
     static SpmvVariant v = [] {
-        SpmvVariant d{256, 0, 8, 3};
+        SpmvVariant d{384, 1, 8, 3};
         if (const char* e = getenv("SPRS_B200_SPMV_VARIANT")) {
             int a, b, c, g;
             if (sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &g) == 4) d = SpmvVariant{a, b, c, g};
