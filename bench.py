@@ -233,9 +233,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
-                    help="N>1: all-gather of y fused into the SpMV kernel (peer stores over "
-                         "NVLink) or a separate NCCL all_gather")
+    ap.add_argument("--exchange", default="overlap", choices=["overlap", "fused", "nccl"],
+                    help="N>1 all-gather of y: 'overlap' = row block cut into chunks, each "
+                         "chunk's y slice pushed to the peers by DMA copies on a second stream "
+                         "while the next chunk computes; 'fused' = the SpMV kernel itself stores "
+                         "every finished row into the peers' buffers; 'nccl' = one NCCL "
+                         "all_gather after the kernel")
+    ap.add_argument("--chunks", type=int, default=4)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -244,8 +248,8 @@ def main():
     import torch.distributed as dist
     import sprs_b200 as sp
     from sprs_b200 import generate as G
-    from sprs_b200.dist import (FusedAllGatherSpMV, RowPartitionedSpMV, fit_row_cost,
-                                nnz_balanced_bounds)
+    from sprs_b200.dist import (FusedAllGatherSpMV, OverlappedAllGatherSpMV, RowPartitionedSpMV,
+                                fit_row_cost, nnz_balanced_bounds)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -305,8 +309,13 @@ def main():
     t_gen = time.time() - t_gen
     y = torch.zeros(n, device=dev, dtype=torch.float64)
     local_nnz = a.nnz
-    fused = world > 1 and args.exchange == "fused"
-    if fused:
+    fused = world > 1 and args.exchange in ("fused", "overlap")
+    if world > 1 and args.exchange == "overlap":
+        op = OverlappedAllGatherSpMV(ctx, a, bounds, rank, world, n, dist, dev,
+                                     chunks=args.chunks, row_cost=row_cost)
+        y = op.y
+        y_views = [y[bounds[g]:bounds[g + 1]] for g in range(world)]
+    elif fused:
         op = FusedAllGatherSpMV(ctx, a.mirror, bounds, rank, world, n, dist, dev)
         y = op.y
         y_views = [y[bounds[g]:bounds[g + 1]] for g in range(world)]
@@ -424,10 +433,15 @@ def main():
                        "generator": gen, "index_bytes": 4,
                        "partition": "contiguous row blocks balanced on nnz + %.2f*rows "
                                     "(row cost fitted from per-rank timings)" % row_cost,
-                       "collective": ("none" if world == 1 else
-                                      "all-gather of y fused into the SpMV kernel (peer stores "
-                                      "over NVLink) + 1-element NCCL all_reduce barrier"
-                                      if fused else "NCCL all_gather(y), unequal slices"),
+                       "collective": ("none" if world == 1 else {
+                           "overlap": "all-gather of y overlapped with compute: %d row chunks, "
+                                      "each slice pushed to the peers by P2P DMA copies on a "
+                                      "second stream + 1-element NCCL all_reduce barrier "
+                                      "(roofline.kernel_ms then covers the whole step)"
+                                      % args.chunks,
+                           "fused": "all-gather of y fused into the SpMV kernel (peer stores "
+                                    "over NVLink) + 1-element NCCL all_reduce barrier",
+                           "nccl": "NCCL all_gather(y), unequal slices"}[args.exchange]),
                        "l2_policy": "inputs (%.1f GB) exceed L2 (126 MB); no flush needed" %
                                     (alg_bytes / 1e9),
                        "gen_seconds": round(t_gen, 1)},

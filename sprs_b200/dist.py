@@ -190,3 +190,98 @@ class FusedAllGatherSpMV:
             self.y = None
             self.ctx.lib.sprs_b200_peer_free(self.ctx.h, self._own)
             self._own = None
+
+
+class OverlappedAllGatherSpMV:
+    """Row-partitioned y = A x with the all-gather of y overlapped with the compute.
+
+    This rank's row block is cut into `chunks` sub-blocks (cost-balanced).  The SpMV of
+    sub-block c runs on the compute stream; as soon as it finishes (event), the copy stream
+    pushes that slice of y into every peer's y buffer with peer-to-peer copies (CUDA IPC
+    mappings, DMA engines over NVLink -- no SM time), while sub-block c+1 is computing.
+    Only the last slice's push and one 1-element all-reduce (the barrier after which every
+    rank's y is complete) are exposed."""
+
+    def __init__(self, ctx, local, bounds, rank, world, n, dist, device, chunks=4, row_cost=0.0):
+        import ctypes as C
+        import torch
+        self.ctx, self.rank, self.world, self.dist, self.n = ctx, rank, world, dist, n
+        self.bounds = bounds
+        lib = ctx.lib
+        own = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        ctx.check(lib.sprs_b200_peer_alloc(ctx.h, 8 * max(n, 1), C.byref(own), handle))
+        self._own = own
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw))
+        self._peers = []
+        for g in range(world):
+            if g == rank:
+                continue
+            p = C.c_void_p()
+            ctx.check(lib.sprs_b200_peer_open(ctx.h, handles[g], C.byref(p)))
+            self._peers.append(p)
+        self.y = torch.as_tensor(_DevPtr(own.value, n), device=device)
+        self.y.zero_()
+        # sub-blocks of the local block
+        chunks = max(1, min(chunks, max(local.rows, 1)))
+        cb = nnz_balanced_bounds(local.indptr, chunks, row_cost=row_cost)
+        self.sub = []
+        r0 = bounds[rank]
+        for c in range(chunks):
+            if cb[c + 1] > cb[c]:
+                blk = local if chunks == 1 else local.slice_rows(cb[c], cb[c + 1])
+                self.sub.append((r0 + cb[c], r0 + cb[c + 1], blk))
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.events = [torch.cuda.Event() for _ in self.sub]
+        self.done = torch.cuda.Event()
+        self._flag = torch.zeros(1, device=device)
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    @property
+    def rows_local(self):
+        return self.bounds[self.rank + 1] - self.bounds[self.rank]
+
+    def step(self, x):
+        import ctypes as C
+        import torch
+        ctx, lib = self.ctx, self.ctx.lib
+        cur = torch.cuda.current_stream()
+        cs = self.copy_stream
+        xp = C.c_void_p(x.data_ptr())
+        for i, (a0, a1, blk) in enumerate(self.sub):
+            ctx.check(lib.sprs_b200_spmv_dev(ctx.h, blk.mirror.h, xp,
+                                             C.c_void_p(self._own.value + 8 * a0), 0,
+                                             C.c_void_p(cur.cuda_stream)))
+            if self.world > 1:
+                self.events[i].record(cur)
+                cs.wait_event(self.events[i])
+                for p in self._peers:
+                    ctx.check(lib.sprs_b200_copy_dev(
+                        ctx.h, C.c_void_p(p.value + 8 * a0), C.c_void_p(self._own.value + 8 * a0),
+                        8 * (a1 - a0), C.c_void_p(cs.cuda_stream)))
+        if self.world > 1:
+            self.done.record(cs)
+            cur.wait_event(self.done)
+            self.dist.all_reduce(self._flag)  # barrier: every peer's pushes have landed
+        return self.y
+
+    def compute(self, x):  # bench.py times compute and exchange together for this mode
+        self.step(x)
+
+    def exchange(self):
+        pass
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        for p in self._peers:
+            self.ctx.lib.sprs_b200_peer_close(self.ctx.h, p)
+        self._peers = []
+        if self._own:
+            self.y = None
+            self.ctx.lib.sprs_b200_peer_free(self.ctx.h, self._own)
+            self._own = None

@@ -1,6 +1,7 @@
-"""2-GPU test of the row-partitioned SpMV (needs >= 2 GPUs; skipped on a 1-GPU box): both
-exchange modes -- NCCL all_gather and the all-gather fused into the kernel through CUDA IPC
-peer stores -- must reproduce the single-GPU result on every rank."""
+"""2-GPU test of the row-partitioned SpMV (needs >= 2 GPUs; skipped on a 1-GPU box): all
+exchange modes -- NCCL all_gather, the all-gather fused into the kernel through CUDA IPC peer
+stores, and the chunked compute / peer-copy overlap -- must reproduce the single-GPU result
+on every rank."""
 import os
 import socket
 import sys
@@ -18,7 +19,8 @@ def _worker(rank, world, port, q):
     import torch.distributed as dist
     import sprs_b200 as sp
     from sprs_b200 import generate as G
-    from sprs_b200.dist import FusedAllGatherSpMV, RowPartitionedSpMV, nnz_balanced_bounds
+    from sprs_b200.dist import (FusedAllGatherSpMV, OverlappedAllGatherSpMV, RowPartitionedSpMV,
+                                nnz_balanced_bounds)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -49,6 +51,16 @@ def _worker(rank, world, port, q):
             oks.append(bool(((g2 - ref).abs() <= 1e-9 * scale).all()))
             dist.barrier()
         fop.close()
+        oop = OverlappedAllGatherSpMV(ctx, a, bounds, rank, world, n, dist, dev, chunks=3)
+        for _ in range(3):
+            oop.y.fill_(float("nan"))
+            torch.cuda.synchronize()
+            dist.barrier()
+            g3 = oop.step(x)
+            torch.cuda.synchronize()
+            oks.append(bool(((g3 - ref).abs() <= 1e-9 * scale).all()))
+            dist.barrier()
+        oop.close()
         q.put((rank, ok_nccl, all(oks)))
     finally:
         dist.destroy_process_group()
