@@ -407,7 +407,10 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item())
     # parity spot-check of the e2e result against the device-resident result
-    ok = bool(torch.equal(hy[:rows_local].to(dev), y_views[rank]))
+    ref_y = y_views[rank]
+    got_y = hy[:rows_local].to(dev)
+    # same kernel, but the chunked exchange tiles sub-blocks separately: compare to rounding
+    ok = bool(((got_y - ref_y).abs() <= 1e-9 * (ref_y.abs().max() + 1e-300)).all())
 
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra and args.workload == "spmv_rmat_10m":
