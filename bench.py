@@ -233,7 +233,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
-    ap.add_argument("--exchange", default="overlap", choices=["overlap", "fused", "nccl"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "overlap", "fused", "push", "nccl"],
                     help="N>1 all-gather of y: 'overlap' = row block cut into chunks, each "
                          "chunk's y slice pushed to the peers by DMA copies on a second stream "
                          "while the next chunk computes; 'fused' = the SpMV kernel itself stores "
@@ -248,8 +248,8 @@ def main():
     import torch.distributed as dist
     import sprs_b200 as sp
     from sprs_b200 import generate as G
-    from sprs_b200.dist import (FusedAllGatherSpMV, OverlappedAllGatherSpMV, RowPartitionedSpMV,
-                                fit_row_cost, nnz_balanced_bounds)
+    from sprs_b200.dist import (FusedAllGatherSpMV, OverlappedAllGatherSpMV, PushAllGatherSpMV,
+                                RowPartitionedSpMV, fit_row_cost, nnz_balanced_bounds)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -303,26 +303,70 @@ def main():
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline:
         cpu_base = cpu_spmv_baseline(full, x, 1 << 27)
+    t_gen = time.time() - t_gen
+    if args.exchange == "auto":
+        # measured on one 8-GPU box (profiles/r1_multi_gpu.md): the in-kernel peer stores win
+        # from 4 GPUs up; at 2 GPUs a separate NCCL all_gather is ~5 % faster
+        args.exchange = "fused" if world >= 4 else "nccl"
+    fused = world > 1 and args.exchange in ("fused", "overlap", "push")
+
+    def make_op(a_blk, bnds):
+        if world > 1 and args.exchange == "overlap":
+            o = OverlappedAllGatherSpMV(ctx, a_blk, bnds, rank, world, n, dist, dev,
+                                        chunks=args.chunks, row_cost=row_cost)
+        elif fused:
+            cls = PushAllGatherSpMV if args.exchange == "push" else FusedAllGatherSpMV
+            o = cls(ctx, a_blk.mirror, bnds, rank, world, n, dist, dev)
+        else:
+            yb = torch.zeros(n, device=dev, dtype=torch.float64)
+            o = RowPartitionedSpMV(bnds, rank, world, yb,
+                                   lambda xv, ys: G.spmv(ctx, a_blk, xv, ys),
+                                   dist=dist if world > 1 else None)
+        return o
+
+    op = make_op(a, bounds)
+    rebalanced = 0
     if world > 1:
+        # measured re-balancing with the REAL operator (the fused kernel's remote stores
+        # change the per-row cost): up to two rounds of equal-time re-cuts
+        for _ in range(2):
+            for _ in range(2):
+                op.step(x)
+            ce0, ce1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tsum = 0.0
+            for _ in range(4):
+                torch.cuda.synchronize()
+                dist.barrier()
+                ce0.record()
+                op.compute(x)
+                ce1.record()
+                op.exchange()
+                torch.cuda.synchronize()
+                tsum += ce0.elapsed_time(ce1)
+            mine = torch.tensor([tsum / 4], device=dev, dtype=torch.float64)
+            allt = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allt, mine)
+            times = [float(t.item()) for t in allt]
+            if max(times) <= 1.03 * (sum(times) / world):
+                break
+            from sprs_b200.dist import rebalance_bounds
+            nb = rebalance_bounds(full.indptr, bounds, times, row_cost=row_cost)
+            if nb == bounds:
+                break
+            if hasattr(op, "close"):
+                op.close()
+            del op, a
+            torch.cuda.empty_cache()
+            bounds = nb
+            r0, r1 = bounds[rank], bounds[rank + 1]
+            a = full.slice_rows(r0, r1)
+            op = make_op(a, bounds)
+            rebalanced += 1
         del full
         torch.cuda.empty_cache()
-    t_gen = time.time() - t_gen
-    y = torch.zeros(n, device=dev, dtype=torch.float64)
+    y = op.y
+    y_views = [y[bounds[g]:bounds[g + 1]] for g in range(world)]
     local_nnz = a.nnz
-    fused = world > 1 and args.exchange in ("fused", "overlap")
-    if world > 1 and args.exchange == "overlap":
-        op = OverlappedAllGatherSpMV(ctx, a, bounds, rank, world, n, dist, dev,
-                                     chunks=args.chunks, row_cost=row_cost)
-        y = op.y
-        y_views = [y[bounds[g]:bounds[g + 1]] for g in range(world)]
-    elif fused:
-        op = FusedAllGatherSpMV(ctx, a.mirror, bounds, rank, world, n, dist, dev)
-        y = op.y
-        y_views = [y[bounds[g]:bounds[g + 1]] for g in range(world)]
-    else:
-        op = RowPartitionedSpMV(bounds, rank, world, y, lambda xv, ys: G.spmv(ctx, a, xv, ys),
-                                dist=dist if world > 1 else None)
-        y_views = op.views
 
     def step():
         op.step(x)
@@ -435,7 +479,8 @@ def main():
             "config": {"workload": args.workload, "n": n, "nnz": nnz, "nnz_per_row": npr,
                        "generator": gen, "index_bytes": 4,
                        "partition": "contiguous row blocks balanced on nnz + %.2f*rows "
-                                    "(row cost fitted from per-rank timings)" % row_cost,
+                                    "(row cost fitted from per-rank timings), then %d measured "
+                                    "equal-time re-cut(s)" % (row_cost, rebalanced),
                        "collective": ("none" if world == 1 else {
                            "overlap": "all-gather of y overlapped with compute: %d row chunks, "
                                       "each slice pushed to the peers by P2P DMA copies on a "
@@ -444,6 +489,9 @@ def main():
                                       % args.chunks,
                            "fused": "all-gather of y fused into the SpMV kernel (peer stores "
                                     "over NVLink) + 1-element NCCL all_reduce barrier",
+                           "push": "SpMV, then one push kernel storing this rank's y slice into "
+                                   "every peer buffer (coalesced NVLink stores) + 1-element "
+                                   "NCCL all_reduce barrier",
                            "nccl": "NCCL all_gather(y), unequal slices"}[args.exchange]),
                        "l2_policy": "inputs (%.1f GB) exceed L2 (126 MB); no flush needed" %
                                     (alg_bytes / 1e9),

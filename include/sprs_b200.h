@@ -169,6 +169,10 @@ int sprs_b200_peer_close(sprs_b200_ctx* ctx, void* d_ptr);
 int sprs_b200_peer_free(sprs_b200_ctx* ctx, void* d_ptr);
 int sprs_b200_copy_dev(sprs_b200_ctx* ctx, void* dst, const void* src, uint64_t bytes,
                        void* stream);
+/* all-gather "put": copy y[row_offset .. row_offset+rows) of this rank's buffer into the same
+ * position of n_peers peer buffers with one kernel (coalesced stores over NVLink).        */
+int sprs_b200_peer_push_dev(sprs_b200_ctx* ctx, const double* d_y_own, uint64_t row_offset,
+                            uint64_t rows, int n_peers, double* const* d_y_peers, void* stream);
 int sprs_b200_spmv_allgather_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
                                  const double* d_x, uint64_t row_offset, int n_targets,
                                  double* const* d_y_bufs, int accumulate, void* stream);

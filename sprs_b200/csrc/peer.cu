@@ -8,7 +8,48 @@
 // so the transfer overlaps the rest of the compute; only a stream-ordered barrier remains.
 #include "common.cuh"
 
+namespace {
+// Push `count` doubles starting at row_off from this GPU's y into the same position of every
+// peer buffer (own all-gather "put"): coalesced 8-byte loads, n_peers coalesced stores each.
+__global__ void __launch_bounds__(256)
+    peer_push_kernel(const double* __restrict__ src, SpmvTargets dst, uint64_t count) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += 4 * stride) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (i + u * stride < count) ? src[i + u * stride] : 0.0;
+#pragma unroll
+        for (int q = 0; q < SPMV_MAX_TARGETS; ++q)
+            if (q < dst.n) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i + u * stride < count) dst.p[q][i + u * stride] = v[u];
+            }
+    }
+}
+}  // namespace
+
 extern "C" {
+
+int sprs_b200_peer_push_dev(sprs_b200_ctx* ctx, const double* d_y_own, uint64_t row_offset,
+                            uint64_t rows, int n_peers, double* const* d_y_peers, void* stream) {
+    if (!ctx || !d_y_own || (n_peers && !d_y_peers)) return SPRS_B200_ERR_ARGUMENT;
+    if (n_peers < 0 || n_peers > SPMV_MAX_TARGETS)
+        SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "n_peers must be 0..%d", SPMV_MAX_TARGETS);
+    if (rows == 0 || n_peers == 0) return SPRS_B200_OK;
+    SpmvTargets dst;
+    dst.n = n_peers;
+    for (int q = 0; q < SPMV_MAX_TARGETS; ++q)
+        dst.p[q] = q < n_peers ? d_y_peers[q] + row_offset : nullptr;
+    uint64_t blocks = (rows + 1023) / 1024;
+    const uint64_t cap = (uint64_t)ctx->sm_count * 2;
+    if (blocks > cap) blocks = cap;
+    peer_push_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_y_own + row_offset, dst,
+                                                                        rows);
+    ctx->launches += 1;
+    SPRS_CUDA(ctx, cudaGetLastError());
+    return SPRS_B200_OK;
+}
 
 int sprs_b200_peer_alloc(sprs_b200_ctx* ctx, uint64_t bytes, void** d_ptr,
                          unsigned char ipc_handle[64]) {

@@ -58,6 +58,37 @@ def nnz_balanced_bounds(indptr, nparts, row_cost=0.0):
     return bounds
 
 
+def rebalance_bounds(indptr, bounds, times, row_cost=0.0):
+    """One step of measured load balancing: given the time each rank spent on its current
+    block, assume time is spread inside a block in proportion to the cost nnz + row_cost*rows,
+    build the cumulative-time curve over all rows (piecewise linear in cost, slope = the
+    rank's measured seconds per cost unit) and cut it into equal shares."""
+    import torch
+    ip = indptr.to(torch.int64) if isinstance(indptr, torch.Tensor) else torch.from_numpy(
+        np.asarray(indptr).astype(np.int64))
+    rows = ip.shape[0] - 1
+    cost = (ip - ip[0]).to(torch.float64) + row_cost * torch.arange(rows + 1, device=ip.device,
+                                                                    dtype=torch.float64)
+    T = torch.zeros(rows + 1, device=ip.device, dtype=torch.float64)
+    acc = 0.0
+    for g in range(len(bounds) - 1):
+        b0, b1 = bounds[g], bounds[g + 1]
+        if b1 <= b0:
+            continue
+        c0, c1 = float(cost[b0]), float(cost[b1])
+        rate = times[g] / max(c1 - c0, 1e-300)
+        T[b0:b1 + 1] = acc + rate * (cost[b0:b1 + 1] - c0)
+        acc += times[g]
+    nparts = len(bounds) - 1
+    targets = torch.tensor([acc * g / nparts for g in range(1, nparts)], device=ip.device,
+                           dtype=torch.float64)
+    cuts = torch.searchsorted(T, targets).tolist() if nparts > 1 else []
+    nb = [0] + [min(max(int(c), 0), rows) for c in cuts] + [rows]
+    for i in range(1, len(nb)):
+        nb[i] = max(nb[i], nb[i - 1])
+    return nb
+
+
 def fit_row_cost(samples):
     """Least-squares fit of t = alpha*nnz + beta*rows over (nnz, rows, seconds) samples (one
     per rank); returns beta/alpha = the cost of one row in non-zero equivalents, clamped to
@@ -190,6 +221,40 @@ class FusedAllGatherSpMV:
             self.y = None
             self.ctx.lib.sprs_b200_peer_free(self.ctx.h, self._own)
             self._own = None
+
+
+class PushAllGatherSpMV(FusedAllGatherSpMV):
+    """Row-partitioned y = A x; the all-gather is this library's own "put": after the
+    (single-target) SpMV, one push kernel copies the rank's y slice into every peer buffer
+    with coalesced stores over NVLink, then the 1-element all-reduce barrier.  Same peer
+    buffers and set-up as FusedAllGatherSpMV; trades the in-kernel overlap for an SpMV that
+    is not slowed down by remote stores."""
+
+    def compute(self, x):
+        import ctypes as C
+        import torch
+        ctx = self.ctx
+        s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        r0 = self.bounds[self.rank]
+        ctx.check(ctx.lib.sprs_b200_spmv_dev(ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()),
+                                             C.c_void_p(self._own.value + 8 * r0), 0, s))
+
+    def exchange(self):
+        import ctypes as C
+        import torch
+        if self.world <= 1:
+            return
+        ctx = self.ctx
+        s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        peers = (C.c_void_p * len(self._peers))(*[p.value for p in self._peers])
+        ctx.check(ctx.lib.sprs_b200_peer_push_dev(ctx.h, self._own, self.bounds[self.rank],
+                                                  self.rows_local, len(self._peers), peers, s))
+        self.dist.all_reduce(self._flag)
+
+    def step(self, x):
+        self.compute(x)
+        self.exchange()
+        return self.y
 
 
 class OverlappedAllGatherSpMV:

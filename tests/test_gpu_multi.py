@@ -19,8 +19,8 @@ def _worker(rank, world, port, q):
     import torch.distributed as dist
     import sprs_b200 as sp
     from sprs_b200 import generate as G
-    from sprs_b200.dist import (FusedAllGatherSpMV, OverlappedAllGatherSpMV, RowPartitionedSpMV,
-                                nnz_balanced_bounds)
+    from sprs_b200.dist import (FusedAllGatherSpMV, OverlappedAllGatherSpMV, PushAllGatherSpMV,
+                                RowPartitionedSpMV, nnz_balanced_bounds)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -61,6 +61,16 @@ def _worker(rank, world, port, q):
             oks.append(bool(((g3 - ref).abs() <= 1e-9 * scale).all()))
             dist.barrier()
         oop.close()
+        pop = PushAllGatherSpMV(ctx, a.mirror, bounds, rank, world, n, dist, dev)
+        for _ in range(3):
+            pop.y.fill_(float("nan"))
+            torch.cuda.synchronize()
+            dist.barrier()
+            g4 = pop.step(x)
+            torch.cuda.synchronize()
+            oks.append(bool(((g4 - ref).abs() <= 1e-9 * scale).all()))
+            dist.barrier()
+        pop.close()
         q.put((rank, ok_nccl, all(oks)))
     finally:
         dist.destroy_process_group()
