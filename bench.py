@@ -15,10 +15,8 @@ spgemm_rmat_500k (config 4).  One JSON line is printed by rank 0.
 """
 import argparse
 import json
-import math
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time

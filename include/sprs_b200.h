@@ -90,6 +90,15 @@ int sprs_b200_csmat_download(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, void*
 int sprs_b200_csmat_device_arrays(const sprs_b200_csmat* m, const void** d_indptr,
                                   int* indptr_bytes, const uint32_t** d_indices,
                                   const double** d_data);
+/* TriMatBase::to_csr (sprs/src/sparse/triplet_iter.rs:127-224): COO triplets in any order,
+ * duplicates allowed -> CSR mirror with ascending unique columns per row, duplicate entries
+ * SUMMED (in insertion order).  Host arrays (index width 4 or 8) or device u32 arrays.   */
+int sprs_b200_csmat_from_triplets(sprs_b200_ctx* ctx, uint64_t rows, uint64_t cols, uint64_t n,
+                                  const void* row_inds, const void* col_inds, int index_bytes,
+                                  const double* data, sprs_b200_csmat** out);
+int sprs_b200_csmat_from_triplets_dev(sprs_b200_ctx* ctx, uint64_t rows, uint64_t cols,
+                                      uint64_t n, const uint32_t* d_row, const uint32_t* d_col,
+                                      const double* d_val, sprs_b200_csmat** out);
 /* check_compressed_structure (sprs/src/sparse.rs:300-369) on the device: counts outer
  * dims with a decreasing indptr, an out-of-range index or non-ascending indices. */
 int sprs_b200_csmat_check_structure(sprs_b200_ctx* ctx, const sprs_b200_csmat* m,

@@ -35,6 +35,10 @@ PROTOTYPES = {
     "sprs_b200_csmat_download": (_int, [_vp, _vp, _vp, _int, _vp, _int, _dp]),
     "sprs_b200_csmat_device_arrays": (_int, [_vp, C.POINTER(_vp), C.POINTER(_int),
                                              C.POINTER(_vp), C.POINTER(_vp)]),
+    "sprs_b200_csmat_from_triplets": (_int, [_vp, _u64, _u64, _u64, _vp, _vp, _int, _dp,
+                                             C.POINTER(_vp)]),
+    "sprs_b200_csmat_from_triplets_dev": (_int, [_vp, _u64, _u64, _u64, _vp, _vp, _vp,
+                                                 C.POINTER(_vp)]),
     "sprs_b200_csmat_check_structure": (_int, [_vp, _vp, C.POINTER(_u64)]),
     "sprs_b200_csmat_to_other_storage": (_int, [_vp, _vp, C.POINTER(_vp)]),
     "sprs_b200_mul_acc_mat_vec_csr": (_int, [_vp, _vp, _dp, _u64, _dp, _u64]),

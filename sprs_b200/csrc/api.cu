@@ -322,7 +322,24 @@ int sprs_b200_csmat_free(sprs_b200_csmat* m) {
     }
     if (m->d_tile_row) cudaFree(m->d_tile_row);
     if (m->d_carry) cudaFree(m->d_carry);
+    if (m->csr_cache) sprs_b200_csmat_free(m->csr_cache);
     delete m;
+    return SPRS_B200_OK;
+}
+
+// CSR view of a mirror for the product kernels: the mirror itself, or (CSC) its cached
+// device conversion -- same sums in the same order (ascending column per output element).
+static int csr_of(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const sprs_b200_csmat** out) {
+    if (m->storage == SPRS_B200_CSR) {
+        *out = m;
+        return SPRS_B200_OK;
+    }
+    if (!m->csr_cache) {
+        sprs_b200_csmat* t = nullptr;
+        SPRS_TRY(sprs_b200_csmat_to_other_storage(ctx, m, &t));
+        m->csr_cache = t;
+    }
+    *out = m->csr_cache;
     return SPRS_B200_OK;
 }
 
@@ -361,6 +378,69 @@ int sprs_b200_csmat_device_arrays(const sprs_b200_csmat* m, const void** d_indpt
     if (d_indices) *d_indices = m->d_indices;
     if (d_data) *d_data = m->d_data;
     return SPRS_B200_OK;
+}
+
+static int finish_triplets(sprs_b200_ctx* ctx, sprs_b200_csmat* t, int st, sprs_b200_csmat** out) {
+    if (st == SPRS_B200_OK) st = spmv_prepare(ctx, t, ctx->stream);
+    if (st == SPRS_B200_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        sprs_b200_set_error(ctx, "from_triplets: kernel failed");
+        st = SPRS_B200_ERR_CUDA;
+    }
+    if (st != SPRS_B200_OK) {
+        sprs_b200_csmat_free(t);
+        return st;
+    }
+    *out = t;
+    return SPRS_B200_OK;
+}
+
+int sprs_b200_csmat_from_triplets_dev(sprs_b200_ctx* ctx, uint64_t rows, uint64_t cols,
+                                      uint64_t n, const uint32_t* d_row, const uint32_t* d_col,
+                                      const double* d_val, sprs_b200_csmat** out) {
+    if (!ctx || !out || (n && (!d_row || !d_col || !d_val))) return SPRS_B200_ERR_ARGUMENT;
+    *out = nullptr;
+    SPRS_CUDA(ctx, cudaSetDevice(ctx->device));
+    auto* t = new sprs_b200_csmat();
+    return finish_triplets(ctx, t, triplets_to_csr_launch(ctx, rows, cols, n, d_row, d_col, d_val,
+                                                         t, ctx->stream), out);
+}
+
+int sprs_b200_csmat_from_triplets(sprs_b200_ctx* ctx, uint64_t rows, uint64_t cols, uint64_t n,
+                                  const void* row_inds, const void* col_inds, int index_bytes,
+                                  const double* data, sprs_b200_csmat** out) {
+    if (!ctx || !out || (n && (!row_inds || !col_inds || !data))) return SPRS_B200_ERR_ARGUMENT;
+    *out = nullptr;
+    if (index_bytes != 4 && index_bytes != 8)
+        SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "bad index width");
+    if (rows > 0xffffffffull || cols > 0xffffffffull || n >= 0xffffffffull)
+        SPRS_FAIL(ctx, SPRS_B200_ERR_INDEX_RANGE, "from_triplets: needs nnz, rows, cols < 2^32");
+    SPRS_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    uint32_t *d_row = nullptr, *d_col = nullptr;
+    double* d_val = nullptr;
+    int st = SPRS_B200_OK;
+    auto* t = new sprs_b200_csmat();
+    do {
+        if (cudaMalloc((void**)&d_row, n * 4 + 16) != cudaSuccess ||
+            cudaMalloc((void**)&d_col, n * 4 + 16) != cudaSuccess ||
+            cudaMalloc((void**)&d_val, n * 8 + 16) != cudaSuccess) {
+            sprs_b200_set_error(ctx, "from_triplets: cudaMalloc failed");
+            st = SPRS_B200_ERR_CUDA;
+            break;
+        }
+        if ((st = upload_indexlike(ctx, row_inds, index_bytes, n, 0, d_row, 4, s)) != SPRS_B200_OK) break;
+        if ((st = upload_indexlike(ctx, col_inds, index_bytes, n, 0, d_col, 4, s)) != SPRS_B200_OK) break;
+        if (n && cudaMemcpyAsync(d_val, data, n * 8, cudaMemcpyHostToDevice, s) != cudaSuccess) {
+            st = SPRS_B200_ERR_CUDA;
+            break;
+        }
+        st = triplets_to_csr_launch(ctx, rows, cols, n, d_row, d_col, d_val, t, s);
+    } while (0);
+    cudaStreamSynchronize(s);
+    if (d_row) cudaFree(d_row);
+    if (d_col) cudaFree(d_col);
+    if (d_val) cudaFree(d_val);
+    return finish_triplets(ctx, t, st, out);
 }
 
 int sprs_b200_csmat_check_structure(sprs_b200_ctx* ctx, const sprs_b200_csmat* m,
@@ -440,12 +520,8 @@ static int spmv_host(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, int want_st
     if ((x_len && !x) || (y_len && !y)) return SPRS_B200_ERR_ARGUMENT;
     SPRS_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    const sprs_b200_csmat* csr = mat;
-    sprs_b200_csmat* tmp = nullptr;
-    if (mat->storage == SPRS_B200_CSC) {  // same sums in the same order (ascending column)
-        SPRS_TRY(sprs_b200_csmat_to_other_storage(ctx, mat, &tmp));
-        csr = tmp;
-    }
+    const sprs_b200_csmat* csr = nullptr;
+    SPRS_TRY(csr_of(ctx, mat, &csr));
     int st = SPRS_B200_OK;
     do {
         void *d_x = nullptr, *d_y = nullptr;
@@ -470,7 +546,6 @@ static int spmv_host(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, int want_st
             st = SPRS_B200_ERR_CUDA;
         }
     } while (0);
-    if (tmp) sprs_b200_csmat_free(tmp);
     return st;
 }
 
@@ -507,12 +582,8 @@ static int dense_host(sprs_b200_ctx* ctx, const sprs_b200_csmat* lhs, int want_s
     if (!rhs || !out) return SPRS_B200_ERR_ARGUMENT;
     SPRS_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    const sprs_b200_csmat* csr = lhs;
-    sprs_b200_csmat* tmp = nullptr;
-    if (lhs->storage == SPRS_B200_CSC) {
-        SPRS_TRY(sprs_b200_csmat_to_other_storage(ctx, lhs, &tmp));
-        csr = tmp;
-    }
+    const sprs_b200_csmat* csr = nullptr;
+    SPRS_TRY(csr_of(ctx, lhs, &csr));
     // Pack views on the host into the pinned staging buffer in the kernel's layout:
     // row-major (rowmaj) or column-major (colmaj).  O(size) copies, no arithmetic.
     const size_t nb = (size_t)rhs_rows * k, nc = (size_t)out_rows * k;
@@ -573,7 +644,6 @@ static int dense_host(sprs_b200_ctx* ctx, const sprs_b200_csmat* lhs, int want_s
                     out[(int64_t)r * out_rs + (int64_t)c * out_cs] = hc[c * out_rows + r];
         }
     } while (0);
-    if (tmp) sprs_b200_csmat_free(tmp);
     return st;
 }
 

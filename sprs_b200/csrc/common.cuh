@@ -39,6 +39,9 @@ struct sprs_b200_csmat {
     uint32_t* d_tile_row = nullptr;
     double* d_carry = nullptr;
     uint64_t n_tiles = 0;
+    // CSC mirrors only: the CSR conversion the product kernels run on, built on first use
+    // by the host-buffer entry points and kept until the mirror is freed.
+    mutable sprs_b200_csmat* csr_cache = nullptr;
 };
 
 #define SPRS_FAIL(ctx, code, ...)                                  \
@@ -92,6 +95,9 @@ int spmv_launch_targets(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const doub
 int spmm_rowmaj_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_b,
                        uint64_t ldb, uint64_t k, double* d_c, uint64_t ldc, int accumulate,
                        cudaStream_t s);
+int triplets_to_csr_launch(sprs_b200_ctx* ctx, uint64_t rows, uint64_t cols, uint64_t n,
+                           const uint32_t* d_row, const uint32_t* d_col, const double* d_val,
+                           sprs_b200_csmat* out, cudaStream_t s);
 int transpose_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, sprs_b200_csmat* out,
                      cudaStream_t s);
 

@@ -410,10 +410,121 @@ __global__ void __launch_bounds__(1024)
     }
 }
 
+// ---- numeric, large rows with a moderate A row (<= PANEL_MAX_A non-zeros): dense f64
+// accumulation in SHARED memory, one column panel of PANEL_W columns at a time.  Per A
+// non-zero a cursor (shared memory) remembers how far its (sorted) B row has been consumed,
+// so every B entry is read once and lands in the panel that owns its column; panels are
+// extracted in order, so the row comes out sorted.  No global atomics: the first version's
+// dense accumulators in global memory (1.2 GB for 296 CTAs) made this phase 77 % of the
+// whole SpGEMM (profiles/r1_launches_spgemm_breakdown.txt).
+constexpr uint32_t PANEL_W = 20480;       // columns per panel: 160 KB of f64 accumulators
+constexpr uint32_t PANEL_MAX_A = 4096;    // cursors: 16 KB
+constexpr size_t PANEL_SMEM = PANEL_W * 8 + PANEL_W / 8 + PANEL_MAX_A * 4;
+
+__global__ void __launch_bounds__(NT)
+    num_panel_kernel(const uint32_t* __restrict__ a_ip, const uint32_t* __restrict__ a_idx,
+                     const double* __restrict__ a_val, const uint32_t* __restrict__ b_ip,
+                     const uint32_t* __restrict__ b_idx, const double* __restrict__ b_val,
+                     const uint64_t* __restrict__ c_ip, const uint32_t* __restrict__ list,
+                     uint32_t n_list, uint32_t cols, uint32_t* __restrict__ c_idx,
+                     double* __restrict__ c_val) {
+    extern __shared__ __align__(16) unsigned char dyn_raw[];
+    double* acc = (double*)dyn_raw;                                  // PANEL_W
+    uint32_t* bm = (uint32_t*)(dyn_raw + (size_t)PANEL_W * 8);        // PANEL_W / 32 words
+    uint32_t* cursor = bm + PANEL_W / 32;                             // PANEL_MAX_A
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t chunk_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < PANEL_W; i += NT) acc[i] = 0.0;   // stays zero between rows
+    for (uint32_t i = threadIdx.x; i < PANEL_W / 32; i += NT) bm[i] = 0;
+    __syncthreads();
+    for (uint32_t li = blockIdx.x; li < n_list; li += gridDim.x) {
+        const uint32_t r = list[li];
+        const uint32_t a0 = a_ip[r], na = a_ip[r + 1] - a0;
+        for (uint32_t kk = threadIdx.x; kk < na; kk += NT) cursor[kk] = b_ip[a_idx[a0 + kk]];
+        __syncthreads();
+        uint64_t out = c_ip[r];
+        for (uint32_t p0 = 0; p0 < cols; p0 += PANEL_W) {
+            const uint32_t p1 = (cols - p0 > PANEL_W) ? p0 + PANEL_W : cols;
+            for (uint32_t kk = warp; kk < na; kk += WARPS) {
+                const uint32_t br = a_idx[a0 + kk];
+                const double av = a_val[a0 + kk];
+                const uint32_t end = b_ip[br + 1];
+                uint32_t pos = cursor[kk];
+                while (pos < end) {
+                    const uint32_t p = pos + lane;
+                    const uint32_t c = p < end ? b_idx[p] : 0xffffffffu;
+                    const bool take = c < p1;  // columns ascend: takers are a prefix of the lanes
+                    if (take) {
+                        atomicAdd(&acc[c - p0], __dmul_rn(av, b_val[p]));
+                        atomicOr(&bm[(c - p0) >> 5], 1u << ((c - p0) & 31));
+                    }
+                    const uint32_t nt = __popc(__ballot_sync(0xffffffffu, take));
+                    pos += nt;
+                    if (nt < 32) break;
+                }
+                if (lane == 0) cursor[kk] = pos;
+            }
+            __syncthreads();
+            // ordered extraction of this panel (also re-zeroes what it touched)
+            const uint32_t words = (p1 - p0 + 31) / 32;
+            for (uint32_t w0 = 0; w0 < words; w0 += NT) {
+                const uint32_t w = w0 + threadIdx.x;
+                uint32_t bits = w < words ? bm[w] : 0u;
+                if (w < words) bm[w] = 0;
+                const uint32_t c = __popc(bits);
+                uint32_t inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += u;
+                }
+                if (lane == 31) wsum[warp] = inc;
+                __syncthreads();
+                if (warp == 0) {
+                    uint32_t v = lane < WARPS ? wsum[lane] : 0u, vi = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t u = __shfl_up_sync(0xffffffffu, vi, o);
+                        if (lane >= o) vi += u;
+                    }
+                    wsum[lane] = vi - v;
+                    if (lane == 31) chunk_total = vi;
+                }
+                __syncthreads();
+                uint64_t o = out + wsum[warp] + inc - c;
+                while (bits) {
+                    const uint32_t b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const uint32_t lc = w * 32 + b;
+                    c_idx[o] = p0 + lc;
+                    c_val[o] = acc[lc];
+                    acc[lc] = 0.0;
+                    ++o;
+                }
+                out += chunk_total;
+                __syncthreads();
+            }
+        }
+    }
+}
+
 template <typename TIn, typename TOut>
 __global__ void widen_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, uint64_t n) {
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i < n) out[i] = (TOut)in[i];
+}
+
+// split the numeric "large" list by the length of the A row: short A rows -> panel kernel
+__global__ void split_large_kernel(const uint32_t* __restrict__ a_ip, const uint32_t* __restrict__ list,
+                                   uint32_t n_list, uint32_t max_a, uint32_t* __restrict__ panel_list,
+                                   uint32_t* __restrict__ hub_list, uint32_t* __restrict__ counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_list) return;
+    const uint32_t r = list[i];
+    const bool hub = a_ip[r + 1] - a_ip[r] > max_a;
+    const uint32_t pos = atomicAdd(&counters[hub ? 4 : 3], 1u);
+    (hub ? hub_list : panel_list)[pos] = r;
 }
 
 inline unsigned grid_for(uint64_t n) { return (unsigned)((n + 255) / 256); }
@@ -501,21 +612,51 @@ int run_numeric(sprs_b200_ctx* ctx, sprs_b200_spgemm* p, uint32_t* d_cidx, doubl
         ctx->launches += 1;
     }
     if (h_cnt[2]) {
-        LargeWorkspace w;
-        int st = plan_large(ctx, p->cols, h_cnt[2], true, &w, s);
-        if (st == SPRS_B200_OK && w.smem)
-            if (cudaFuncSetAttribute(num_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)w.smem) != cudaSuccess)
+        // lists[0 .. rows) and [rows .. 2 rows) are free again once small / medium have been
+        // LAUNCHED?  No -- they are still being read; use fresh scratch for the split lists.
+        uint32_t* split = nullptr;
+        SPRS_CUDA(ctx, cudaMalloc((void**)&split, 2ull * h_cnt[2] * sizeof(uint32_t)));
+        uint32_t *panel_list = split, *hub_list = split + h_cnt[2];
+        split_large_kernel<<<grid_for(h_cnt[2]), 256, 0, s>>>(a_ip, l2, h_cnt[2], PANEL_MAX_A,
+                                                             panel_list, hub_list, p->d_counters);
+        ctx->launches += 1;
+        uint32_t h2[8];
+        cudaMemcpyAsync(h2, p->d_counters, sizeof(h2), cudaMemcpyDeviceToHost, s);
+        int st = cudaStreamSynchronize(s) == cudaSuccess ? SPRS_B200_OK : SPRS_B200_ERR_CUDA;
+        const uint32_t n_panel = h2[3], n_hub = h2[4];
+        if (st == SPRS_B200_OK && n_panel) {
+            if (cudaFuncSetAttribute(num_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)PANEL_SMEM) != cudaSuccess)
                 st = SPRS_B200_ERR_CUDA;
-        if (st == SPRS_B200_OK) {
-            const unsigned big_nt = w.grid < (unsigned)ctx->sm_count ? 1024 : NT;
-            num_large_kernel<<<w.grid, big_nt, w.smem, s>>>(
-                a_ip, a->d_indices, a->d_data, b_ip, b->d_indices, b->d_data, p->d_cptr, l2,
-                h_cnt[2], w.words, p->cols, w.bitmaps, w.acc, d_cidx, d_cval);
-            ctx->launches += 1;
-            if (cudaStreamSynchronize(s) != cudaSuccess) st = SPRS_B200_ERR_CUDA;
+            else {
+                const unsigned g = std::min<unsigned>(n_panel, (unsigned)ctx->sm_count);
+                num_panel_kernel<<<g, NT, PANEL_SMEM, s>>>(a_ip, a->d_indices, a->d_data, b_ip,
+                                                           b->d_indices, b->d_data, p->d_cptr,
+                                                           panel_list, n_panel, (uint32_t)p->cols,
+                                                           d_cidx, d_cval);
+                ctx->launches += 1;
+            }
         }
-        free_large(w);
+        if (st == SPRS_B200_OK && n_hub) {
+            LargeWorkspace w;
+            st = plan_large(ctx, p->cols, n_hub, true, &w, s);
+            if (st == SPRS_B200_OK && w.smem)
+                if (cudaFuncSetAttribute(num_large_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)w.smem) != cudaSuccess)
+                    st = SPRS_B200_ERR_CUDA;
+            if (st == SPRS_B200_OK) {
+                const unsigned big_nt = w.grid < (unsigned)ctx->sm_count ? 1024 : NT;
+                num_large_kernel<<<w.grid, big_nt, w.smem, s>>>(
+                    a_ip, a->d_indices, a->d_data, b_ip, b->d_indices, b->d_data, p->d_cptr,
+                    hub_list, n_hub, w.words, p->cols, w.bitmaps, w.acc, d_cidx, d_cval);
+                ctx->launches += 1;
+                if (cudaStreamSynchronize(s) != cudaSuccess) st = SPRS_B200_ERR_CUDA;
+            }
+            free_large(w);
+        }
+        if (cudaStreamSynchronize(s) != cudaSuccess) st = SPRS_B200_ERR_CUDA;
+        cudaFree(split);
         if (st != SPRS_B200_OK) SPRS_FAIL(ctx, st, "spgemm numeric (large rows) failed");
     }
     SPRS_CUDA(ctx, cudaGetLastError());

@@ -134,6 +134,96 @@ __global__ void narrow_kernel(const TIn* __restrict__ in, TOut* __restrict__ out
 
 inline unsigned grid_for(uint64_t n) { return (unsigned)((n + 255) / 256); }
 
+// Stable LSD radix sort of n (key, pos) pairs on `key_bits` bits; pos_in == nullptr means
+// pos = 0..n-1.  Uses the caller's ping-pong buffers; returns pointers to the sorted arrays.
+struct SortBuffers {
+    uint32_t *kbuf[2] = {nullptr, nullptr}, *pbuf[2] = {nullptr, nullptr}, *hist = nullptr;
+    uint64_t* offs = nullptr;
+    uint32_t nblocks = 0;
+    int alloc(uint64_t n) {
+        nblocks = (uint32_t)((n + RS_CHUNK - 1) / RS_CHUNK);
+        if (cudaMalloc((void**)&kbuf[0], n * 4) != cudaSuccess ||
+            cudaMalloc((void**)&kbuf[1], n * 4) != cudaSuccess ||
+            cudaMalloc((void**)&pbuf[0], n * 4) != cudaSuccess ||
+            cudaMalloc((void**)&pbuf[1], n * 4) != cudaSuccess ||
+            cudaMalloc((void**)&hist, 256ull * nblocks * 4) != cudaSuccess ||
+            cudaMalloc((void**)&offs, (256ull * nblocks + 1) * 8) != cudaSuccess)
+            return SPRS_B200_ERR_CUDA;
+        return SPRS_B200_OK;
+    }
+    void release() {
+        for (int i = 0; i < 2; ++i) {
+            if (kbuf[i]) cudaFree(kbuf[i]);
+            if (pbuf[i]) cudaFree(pbuf[i]);
+            kbuf[i] = pbuf[i] = nullptr;
+        }
+        if (hist) cudaFree(hist);
+        if (offs) cudaFree(offs);
+        hist = nullptr;
+        offs = nullptr;
+    }
+};
+
+int bits_for(uint64_t range) {
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < range) ++bits;
+    return bits;
+}
+
+int stable_sort_pairs(sprs_b200_ctx* ctx, SortBuffers& b, const uint32_t* keys_in,
+                      const uint32_t* pos_in, uint64_t n, int key_bits, cudaStream_t s,
+                      const uint32_t** keys_out, const uint32_t** pos_out) {
+    const int passes = (key_bits + 7) / 8;
+    const uint32_t* kin = keys_in;
+    const uint32_t* pin = pos_in;
+    // never scatter into the buffer currently being read
+    int w = (kin == b.kbuf[0] || pin == b.pbuf[0]) ? 1 : 0;
+    for (int p = 0; p < passes; ++p) {
+        rs_hist_kernel<<<b.nblocks, RS_NT, 0, s>>>(kin, n, 8 * p, b.hist, b.nblocks);
+        ctx->launches += 1;
+        SPRS_TRY((device_exclusive_scan<uint32_t, uint64_t>(ctx, b.hist, 256ull * b.nblocks,
+                                                            b.offs, s)));
+        rs_scatter_kernel<<<b.nblocks, RS_NT, 0, s>>>(kin, pin, n, 8 * p, b.offs, b.nblocks,
+                                                      b.kbuf[w], b.pbuf[w]);
+        ctx->launches += 1;
+        kin = b.kbuf[w];
+        pin = b.pbuf[w];
+        w ^= 1;
+    }
+    *keys_out = kin;
+    *pos_out = pin;
+    SPRS_CUDA(ctx, cudaGetLastError());
+    return SPRS_B200_OK;
+}
+
+// ---- COO -> CSR helpers (TriMatBase::to_csr, sprs/src/sparse/triplet_iter.rs:127-224)
+__global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ pos,
+                                  uint64_t n, uint32_t* __restrict__ dst) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[pos[i]];
+}
+__global__ void head_flags_kernel(const uint32_t* __restrict__ row, const uint32_t* __restrict__ col,
+                                  uint64_t n, uint32_t* __restrict__ flag) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (i == 0 || row[i] != row[i - 1] || col[i] != col[i - 1]) ? 1u : 0u;
+}
+// one thread per run head: sums the duplicates in sorted (= insertion) order, like the
+// reference's duplicate summation (triplet_iter.rs:143-176), writes the unique entry
+__global__ void compress_runs_kernel(const uint32_t* __restrict__ row, const uint32_t* __restrict__ col,
+                                     const uint32_t* __restrict__ pos, const uint32_t* __restrict__ flag,
+                                     const uint64_t* __restrict__ uidx, const double* __restrict__ vals,
+                                     uint64_t n, uint32_t* __restrict__ out_idx,
+                                     double* __restrict__ out_val, uint32_t* __restrict__ row_counts) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    double sum = vals[pos[i]];
+    for (uint64_t j = i + 1; j < n && !flag[j]; ++j) sum = __dadd_rn(sum, vals[pos[j]]);
+    const uint64_t u = uidx[i];
+    out_idx[u] = col[i];
+    out_val[u] = sum;
+    atomicAdd(&row_counts[row[i]], 1u);
+}
+
 }  // namespace
 
 int transpose_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, sprs_b200_csmat* t,
@@ -165,8 +255,7 @@ int transpose_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, sprs_b200_csm
     SPRS_CUDA(ctx, cudaMalloc((void**)&counts, (inner + 1) * sizeof(uint32_t)));
     SPRS_CUDA(ctx, cudaMalloc((void**)&ip64, (inner + 1) * sizeof(uint64_t)));
     int st = SPRS_B200_OK;
-    uint32_t *kbuf[2] = {nullptr, nullptr}, *pbuf[2] = {nullptr, nullptr}, *hist = nullptr;
-    uint64_t* offs = nullptr;
+    SortBuffers sb;
     do {
         cudaError_t e = cudaMemsetAsync(counts, 0, (inner + 1) * sizeof(uint32_t), s);
         if (e != cudaSuccess) { st = SPRS_B200_ERR_CUDA; break; }
@@ -183,34 +272,14 @@ int transpose_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, sprs_b200_csm
         if (nnz == 0) break;
 
         // ---- stable LSD radix sort of (inner index, position)
-        int bits = 1;
-        while (bits < 32 && (1ull << bits) < inner) ++bits;
-        const int passes = (bits + 7) / 8;
-        const uint32_t nblocks = (uint32_t)((nnz + RS_CHUNK - 1) / RS_CHUNK);
-        if (cudaMalloc((void**)&kbuf[0], nnz * 4) != cudaSuccess ||
-            cudaMalloc((void**)&kbuf[1], nnz * 4) != cudaSuccess ||
-            cudaMalloc((void**)&pbuf[0], nnz * 4) != cudaSuccess ||
-            cudaMalloc((void**)&pbuf[1], nnz * 4) != cudaSuccess ||
-            cudaMalloc((void**)&hist, 256ull * nblocks * 4) != cudaSuccess ||
-            cudaMalloc((void**)&offs, (256ull * nblocks + 1) * 8) != cudaSuccess) {
+        if ((st = sb.alloc(nnz)) != SPRS_B200_OK) {
             sprs_b200_set_error(ctx, "to_other_storage: cudaMalloc failed");
-            st = SPRS_B200_ERR_CUDA;
             break;
         }
-        const uint32_t* kin = m->d_indices;
-        const uint32_t* pin = nullptr;
-        for (int p = 0; p < passes && st == SPRS_B200_OK; ++p) {
-            rs_hist_kernel<<<nblocks, RS_NT, 0, s>>>(kin, nnz, 8 * p, hist, nblocks);
-            ctx->launches += 1;
-            st = device_exclusive_scan<uint32_t, uint64_t>(ctx, hist, 256ull * nblocks, offs, s);
-            if (st != SPRS_B200_OK) break;
-            rs_scatter_kernel<<<nblocks, RS_NT, 0, s>>>(kin, pin, nnz, 8 * p, offs, nblocks,
-                                                        kbuf[p & 1], pbuf[p & 1]);
-            ctx->launches += 1;
-            kin = kbuf[p & 1];
-            pin = pbuf[p & 1];
-        }
-        if (st != SPRS_B200_OK) break;
+        const uint32_t *kin = nullptr, *pin = nullptr;
+        if ((st = stable_sort_pairs(ctx, sb, m->d_indices, nullptr, nnz, bits_for(inner), s, &kin,
+                                    &pin)) != SPRS_B200_OK)
+            break;
         if (m->indptr_bytes == 4)
             gather_transposed_kernel<uint32_t><<<grid_for(nnz), 256, 0, s>>>(
                 pin, nnz, (const uint32_t*)m->d_indptr, (uint32_t)m->outer, m->d_data,
@@ -229,11 +298,100 @@ int transpose_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, sprs_b200_csm
     }
     cudaFree(counts);
     cudaFree(ip64);
-    for (int i = 0; i < 2; ++i) {
-        if (kbuf[i]) cudaFree(kbuf[i]);
-        if (pbuf[i]) cudaFree(pbuf[i]);
-    }
-    if (hist) cudaFree(hist);
-    if (offs) cudaFree(offs);
+    sb.release();
+    return st;
+}
+
+// COO (device arrays, any order, duplicates allowed) -> CSR mirror with ascending unique
+// column indices per row and duplicates summed: TriMatBase::to_csr
+// (sprs/src/sparse/triplet_iter.rs:127-224).  Two stable radix sorts (by column, then by
+// row) give the (row, col) order; duplicates are summed in insertion order.
+int triplets_to_csr_launch(sprs_b200_ctx* ctx, uint64_t rows, uint64_t cols, uint64_t n,
+                           const uint32_t* d_row, const uint32_t* d_col, const double* d_val,
+                           sprs_b200_csmat* t, cudaStream_t s) {
+    if (n >= 0xffffffffull || rows > 0xffffffffull || cols > 0xffffffffull)
+        SPRS_FAIL(ctx, SPRS_B200_ERR_INDEX_RANGE, "from_triplets: needs nnz, rows, cols < 2^32");
+    t->ctx = ctx;
+    t->storage = SPRS_B200_CSR;
+    t->rows = rows;
+    t->cols = cols;
+    t->outer = rows;
+    t->inner = cols;
+    t->indptr_bytes = 4;
+    t->owns = true;
+    t->nnz = 0;
+    SPRS_CUDA(ctx, cudaMalloc(&t->d_indptr, (rows + 1) * sizeof(uint32_t) + 16));
+    uint32_t *counts = nullptr, *row_s = nullptr, *col_s = nullptr, *flag = nullptr;
+    uint64_t *ip64 = nullptr, *uidx = nullptr;
+    SortBuffers sb;
+    int st = SPRS_B200_OK;
+    do {
+        if (cudaMalloc((void**)&counts, (rows + 1) * 4) != cudaSuccess ||
+            cudaMalloc((void**)&ip64, (rows + 1) * 8) != cudaSuccess) {
+            st = SPRS_B200_ERR_CUDA;
+            break;
+        }
+        cudaMemsetAsync(counts, 0, (rows + 1) * 4, s);
+        uint64_t n_unique = 0;
+        if (n) {
+            if (cudaMalloc((void**)&row_s, n * 4) != cudaSuccess ||
+                cudaMalloc((void**)&col_s, n * 4) != cudaSuccess ||
+                cudaMalloc((void**)&flag, n * 4) != cudaSuccess ||
+                cudaMalloc((void**)&uidx, (n + 1) * 8) != cudaSuccess ||
+                sb.alloc(n) != SPRS_B200_OK) {
+                st = SPRS_B200_ERR_CUDA;
+                break;
+            }
+            const uint32_t *k1 = nullptr, *p1 = nullptr, *k2 = nullptr, *p2 = nullptr;
+            if ((st = stable_sort_pairs(ctx, sb, d_col, nullptr, n, bits_for(cols), s, &k1, &p1)) !=
+                SPRS_B200_OK)
+                break;
+            gather_u32_kernel<<<grid_for(n), 256, 0, s>>>(d_row, p1, n, row_s);  // row in col order
+            if ((st = stable_sort_pairs(ctx, sb, row_s, p1, n, bits_for(rows), s, &k2, &p2)) !=
+                SPRS_B200_OK)
+                break;
+            gather_u32_kernel<<<grid_for(n), 256, 0, s>>>(d_col, p2, n, col_s);
+            head_flags_kernel<<<grid_for(n), 256, 0, s>>>(k2, col_s, n, flag);
+            ctx->launches += 3;
+            if ((st = device_exclusive_scan<uint32_t, uint64_t>(ctx, flag, n, uidx, s)) != SPRS_B200_OK)
+                break;
+            if (cudaMemcpyAsync(&n_unique, uidx + n, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                cudaStreamSynchronize(s) != cudaSuccess) {
+                st = SPRS_B200_ERR_CUDA;
+                break;
+            }
+            if (cudaMalloc((void**)&t->d_indices, n_unique * 4 + 16) != cudaSuccess ||
+                cudaMalloc((void**)&t->d_data, n_unique * 8 + 16) != cudaSuccess) {
+                st = SPRS_B200_ERR_CUDA;
+                break;
+            }
+            compress_runs_kernel<<<grid_for(n), 256, 0, s>>>(k2, col_s, p2, flag, uidx, d_val, n,
+                                                            t->d_indices, t->d_data, counts);
+            ctx->launches += 1;
+        } else {
+            if (cudaMalloc((void**)&t->d_indices, 16) != cudaSuccess ||
+                cudaMalloc((void**)&t->d_data, 16) != cudaSuccess) {
+                st = SPRS_B200_ERR_CUDA;
+                break;
+            }
+        }
+        t->nnz = n_unique;
+        if ((st = device_exclusive_scan<uint32_t, uint64_t>(ctx, counts, rows, ip64, s)) != SPRS_B200_OK)
+            break;
+        narrow_kernel<uint64_t, uint32_t><<<grid_for(rows + 1), 256, 0, s>>>(
+            ip64, (uint32_t*)t->d_indptr, rows + 1);
+        ctx->launches += 1;
+    } while (0);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (st == SPRS_B200_OK && e == cudaSuccess) e = cudaGetLastError();
+    if (st == SPRS_B200_OK && e != cudaSuccess) st = SPRS_B200_ERR_CUDA;
+    if (st == SPRS_B200_ERR_CUDA) sprs_b200_set_error(ctx, "from_triplets: CUDA allocation or kernel failed");
+    if (counts) cudaFree(counts);
+    if (ip64) cudaFree(ip64);
+    if (row_s) cudaFree(row_s);
+    if (col_s) cudaFree(col_s);
+    if (flag) cudaFree(flag);
+    if (uidx) cudaFree(uidx);
+    sb.release();
     return st;
 }

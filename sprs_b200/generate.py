@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .sparse import CSR, Context, DeviceCsMat
+from .sparse import DeviceCsMat
 
 SENTINEL = -1  # UINT64_MAX read as int64
 

@@ -229,6 +229,27 @@ class CsMat:
         return cls(shape, indptr, indices, data, CSC, **kw)
 
     @classmethod
+    def from_triplets(cls, shape, row_inds, col_inds, data, index_dtype=np.uint64, ctx=None):
+        """TriMat::new + to_csr (sprs/src/sparse/triplet.rs, triplet_iter.rs:127-224): COO in
+        any order, duplicate entries summed, built by the device radix sort."""
+        ctx = ctx or Context.default()
+        r = np.ascontiguousarray(row_inds, dtype=np.uint64)
+        c = np.ascontiguousarray(col_inds, dtype=np.uint64)
+        d = np.ascontiguousarray(data, dtype=np.float64)
+        if not (r.shape == c.shape == d.shape):
+            raise SprsPanic("row_inds, col_inds and data must have the same length")
+        if r.size and (int(r.max()) >= shape[0] or int(c.max()) >= shape[1]):
+            raise SprsPanic("Out of bounds index")
+        h = C.c_void_p()
+        ctx.check(ctx.lib.sprs_b200_csmat_from_triplets(ctx.h, shape[0], shape[1], r.size, _ptr(r),
+                                                        _ptr(c), 8, _ptr(d), C.byref(h)))
+        dev = DeviceCsMat(ctx, h)
+        ip, ind, dat = dev.download(index_dtype)
+        m = cls(shape, ip, ind, dat, CSR, ctx=ctx)
+        m._dev = dev
+        return m
+
+    @classmethod
     def eye(cls, n, **kw):
         return cls((n, n), np.arange(n + 1), np.arange(n), np.ones(n), CSR, **kw)
 

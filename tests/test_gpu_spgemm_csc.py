@@ -274,3 +274,30 @@ def test_spgemm_rmat_properties_full_size(sp):
     bad = C_.c_uint64(1)
     ctx.check(ctx.lib.sprs_b200_csmat_check_structure(ctx.h, cm, C_.byref(bad)))
     assert bad.value == 0
+
+
+@pytest.mark.parametrize("shape,n", [((1, 1), 1), ((50, 70), 400), ((3000, 2000), 60000),
+                                     ((200000, 300000), 500000), ((10, 10), 0)])
+def test_from_triplets_vs_scipy(sp, shape, n):
+    """TriMat -> CSR (triplet_iter.rs:127-224): unsorted COO with duplicates -> sorted unique
+    columns per row, duplicates summed.  Structure exact vs scipy's coo->csr, values to
+    rounding (the summation order of duplicates is unspecified in the reference too)."""
+    rng = np.random.default_rng(shape[0] + n)
+    r = rng.integers(0, shape[0], n)
+    c = rng.integers(0, shape[1], n)
+    if n > 10:  # force duplicates
+        r[: n // 5] = r[n // 5: 2 * (n // 5)]
+        c[: n // 5] = c[n // 5: 2 * (n // 5)]
+    d = rng.standard_normal(n)
+    m = sp.CsMat.from_triplets(shape, r, c, d)
+    ref = sp_.coo_matrix((d, (r, c)), shape=shape).tocsr()
+    ref.sum_duplicates()
+    ref.sort_indices()
+    assert np.array_equal(m.indptr, ref.indptr) and np.array_equal(m.indices, ref.indices)
+    absref = sp_.coo_matrix((np.abs(d), (r, c)), shape=shape).tocsr()
+    absref.sum_duplicates()
+    absref.sort_indices()
+    assert np.all(np.abs(m.data - ref.data) <= 1e-12 * absref.data + 1e-300)
+    if n:
+        x = rng.standard_normal(shape[1])
+        assert np.allclose(m * x, ref @ x, rtol=1e-9, atol=1e-9)

@@ -1,6 +1,6 @@
 """2+ rank probe: NCCL small all_reduce latency and 80 MB uneven all_gather time, with and
 without the NVML sampling thread that bench.py runs on rank 0."""
-import os, sys, time, threading
+import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
