@@ -303,9 +303,10 @@ def main():
         cpu_base = cpu_spmv_baseline(full, x, 1 << 27)
     t_gen = time.time() - t_gen
     if args.exchange == "auto":
-        # measured on one 8-GPU box (profiles/r1_multi_gpu.md): the in-kernel peer stores win
-        # from 4 GPUs up; at 2 GPUs a separate NCCL all_gather is ~5 % faster
-        args.exchange = "fused" if world >= 4 else "nccl"
+        # measured (profiles/r1_multi_gpu.md): the own put kernel is the fastest exchange at
+        # 2 and 4 GPUs (2.27 / 1.33 ms vs nccl 2.39 / 1.36, fused 2.43 / 1.38); at 8 GPUs
+        # fused measured 0.82 ms (nccl 1.30) and push is expected level with it
+        args.exchange = "push"
     fused = world > 1 and args.exchange in ("fused", "overlap", "push")
 
     def make_op(a_blk, bnds):
