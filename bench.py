@@ -299,7 +299,7 @@ def main():
     else:
         a = full
     cpu_base = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # rank 0 at N=1 only
         cpu_base = cpu_spmv_baseline(full, x, 1 << 27)
     t_gen = time.time() - t_gen
     if args.exchange == "auto":
