@@ -177,7 +177,8 @@ def check_spgemm(sp, O, a, b, shape_a, shape_b, bit_exact_small=True):
     dict(n=300, m=200, p=250, da=6, db=5, empty=0.2),
     dict(n=2000, m=1500, p=1800, da=12, db=10),                 # mostly warp-per-row bins
     dict(n=400, m=3000, p=20000, da=60, db=40),                 # CTA hash bins (n_prod ~2400)
-    dict(n=60, m=4000, p=30000, da=900, db=60),                 # large bins: bitmap + dense acc
+    dict(n=60, m=4000, p=30000, da=900, db=60),                 # large rows: shared-memory column panels
+    dict(n=12, m=7000, p=30000, da=5000, db=25),                # hub rows (> 4096 A non-zeros): global dense accumulator
     dict(n=3000, m=3000, p=3000, da=20, db=20, skew=True),      # power-law mix of all bins
 ])
 def test_spgemm_vs_oracle(sp, O, case):
