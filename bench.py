@@ -300,7 +300,10 @@ def main():
         a = full
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:  # rank 0 at N=1 only
-        cpu_base = cpu_spmv_baseline(full, x, 1 << 27)
+        try:
+            cpu_base = cpu_spmv_baseline(full, x, 1 << 27)
+        except Exception as e:  # a reported baseline must never take the GPU number down
+            cpu_base = {"error": repr(e)}
     t_gen = time.time() - t_gen
     if args.exchange == "auto":
         # measured (profiles/r1_multi_gpu.md): the own put kernel is the fastest exchange at
@@ -457,9 +460,12 @@ def main():
 
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra and args.workload == "spmv_rmat_10m":
-        del a, full
-        torch.cuda.empty_cache()
-        extra = bench_small_spmv(ctx, G, hbm_peak, dev)
+        try:
+            del a, full
+            torch.cuda.empty_cache()
+            extra = bench_small_spmv(ctx, G, hbm_peak, dev)
+        except Exception as e:
+            extra = {"error": repr(e)}
 
     if rank == 0:
         flops = 2.0 * nnz
