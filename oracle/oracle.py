@@ -137,6 +137,21 @@ def convert_mat_storage(outer, inner, indptr, indices, data):
     return oip, oind, od
 
 
+def triplets_to_csr(shape, row_inds, col_inds, data, index_dtype=np.uint32):
+    """triplet_iter.rs:127-224 TriMat::to_csr: returns (indptr, indices, data)."""
+    ri = np.ascontiguousarray(row_inds, dtype=index_dtype)
+    ci = np.ascontiguousarray(col_inds, dtype=index_dtype)
+    v = np.ascontiguousarray(data, dtype=np.float64)
+    n = len(ri)
+    ip = np.zeros(shape[0] + 1, dtype=index_dtype)
+    ind = np.empty(max(n, 1), dtype=index_dtype)
+    d = np.empty(max(n, 1), dtype=np.float64)
+    f = getattr(lib(), "oracle_triplets_to_csr_" + _suffix(ip, ind))
+    f.restype = C.c_size_t
+    k = f(C.c_size_t(shape[0]), C.c_size_t(n), _p(ri), _p(ci), _p(v), _p(ip), _p(ind), _p(d))
+    return ip, ind[:k].copy(), d[:k].copy()
+
+
 def mul_csr_csr(a_shape, a, b_shape, b, threads=0):
     """smmp.rs:196-416.  a, b = (indptr, indices, data); threads=0 -> the
     reference's Automatic rule, n -> Fixed(n).  Returns (indptr, indices, data)."""

@@ -205,6 +205,49 @@ void convert_mat_storage(size_t outer, size_t inner, const P* indptr,
     for (size_t i = 0; i <= inner; ++i) std::swap(o_indptr[i], last);
 }
 
+// triplet_iter.rs:127-224  TriMatIter::into_cs (CSR arm): sort the (row, col, value)
+// records by (row, col), add each duplicate into the slot of its first occurrence, build
+// indptr while walking.  The reference sorts with sort_unstable_by_key, so the order in
+// which duplicates are added is unspecified there; std::stable_sort (insertion order) is
+// one of its valid outcomes and is what the device path reproduces.
+template <class I, class P>
+size_t triplets_to_csr(size_t rows, size_t n, const I* ri, const I* ci, const double* v,
+                       P* indptr, I* indices, double* data) {
+    struct Rec { I r, c; double v; };
+    std::vector<Rec> rc(n);
+    for (size_t k = 0; k < n; ++k) rc[k] = Rec{ri[k], ci[k], v[k]};
+    std::stable_sort(rc.begin(), rc.end(), [](const Rec& a, const Rec& b) {
+        return a.r != b.r ? a.r < b.r : a.c < b.c;
+    });
+    size_t slot = 0, cur_outer = 0;
+    for (size_t o = 0; o <= rows; ++o) indptr[o] = 0;
+    for (size_t rec = 0; rec < n; ++rec) {
+        if (rec > 0) {
+            if (rc[rec - 1].r == rc[rec].r && rc[rec - 1].c == rc[rec].c) {
+                rc[slot].v = rc[slot].v + rc[rec].v;  // duplicate: add into the current slot
+            } else {
+                slot += 1;
+                rc[slot] = rc[rec];
+            }
+        }
+        const size_t new_outer = rc[rec].r;
+        while (new_outer > cur_outer) {
+            indptr[cur_outer + 1] = (P)slot;
+            cur_outer += 1;
+        }
+    }
+    if (n > 0) slot += 1;
+    while (rows > cur_outer) {
+        indptr[cur_outer + 1] = (P)slot;
+        cur_outer += 1;
+    }
+    for (size_t k = 0; k < slot; ++k) {
+        indices[k] = rc[k].c;
+        data[k] = rc[k].v;
+    }
+    return slot;
+}
+
 // ---------------------------------------------------------------------------
 // smmp.rs:81-131  symbolic : pattern of C = A*B for a chunk of A rows.
 // `seen` has b_cols entries.  Appends to c_indices; c_indptr has a_rows+1
@@ -418,6 +461,11 @@ SpgemmResult<I, P>* mul_csr_csr(size_t a_rows, size_t a_cols, size_t b_cols,
                                                      const I* ind, const double* d, P* oip,     \
                                                      I* oind, double* od) {                     \
         convert_mat_storage<I, P>(outer, inner, ip, ind, d, oip, oind, od);                     \
+    }                                                                                           \
+    extern "C" size_t oracle_triplets_to_csr_##SUF(size_t rows, size_t n, const I* ri,            \
+                                                   const I* ci, const double* v, P* ip, I* ind,  \
+                                                   double* d) {                                  \
+        return triplets_to_csr<I, P>(rows, n, ri, ci, v, ip, ind, d);                            \
     }                                                                                           \
     extern "C" void* oracle_mul_csr_csr_##SUF(size_t ar, size_t ac, size_t bc, const P* aip,    \
                                               const I* aind, const double* ad, const P* bip,    \

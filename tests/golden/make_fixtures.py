@@ -10,6 +10,7 @@ DATA (not code) from the reference's tests; each entry cites where it lives:
   sprs/src/sparse/smmp.rs:476-513    zero-row / empty edge cases
   sprs/src/sparse/csmat.rs:3047-3052 issue_99 (10x1 * 1x9)
   sprs/src/lib.rs:54-73              README example eye(5) * CsVec
+  sprs/src/sparse/triplet.rs:342-453, 571-580   TriMat -> CSR/CSC KATs
 
 The reference is Rust and cannot run in this image (no cargo), so these
 fixtures -- not a live run of the reference -- are what pins the oracle.
@@ -111,6 +112,24 @@ F["kat_readme_eye"] = {"n": 5, "x": {"dim": 5, "indices": [0, 2, 4], "data": [1.
 F["kat_edge"] = {
     "zero_rows": {"a_shape": [0, 11], "b_shape": [11, 11], "c_shape": [0, 11], "c_nnz": 0},
     "issue_99": {"a_shape": [10, 1], "b_shape": [1, 9], "c_shape": [10, 9], "c_nnz": 0}}
+# ---- sprs/src/sparse/triplet.rs:342-453 TriMat KATs (expected matrices are given as CSC)
+_tri_expected_csc = csmat("CSC", (4, 4), [0, 2, 3, 4, 6], [0, 1, 0, 3, 2, 3],
+                          [1., 3., 2., 5., 4., 6.])
+F["kat_triplets"] = {
+    "incremental": {"shape": [4, 4], "rows": [0, 0, 1, 2, 3, 3], "cols": [0, 1, 0, 3, 2, 3],
+                    "data": [1., 2., 3., 4., 5., 6.], "expected_csc": _tri_expected_csc},
+    "unordered": {"shape": [4, 4], "rows": [0, 0, 1, 2, 3, 3], "cols": [1, 0, 0, 3, 3, 2],
+                  "data": [2., 1., 3., 4., 6., 5.], "expected_csc": _tri_expected_csc},
+    "additions": {"shape": [4, 4], "rows": [0, 0, 3, 1, 2, 3, 3], "cols": [1, 0, 2, 0, 3, 3, 2],
+                  "data": [2., 1., 3., 3., 4., 6., 2.], "expected_csc": _tri_expected_csc},
+    "from_vecs": {"shape": [5, 4], "rows": [0, 0, 1, 2, 3, 3, 4, 4],
+                  "cols": [0, 1, 0, 3, 2, 3, 1, 3], "data": [1., 2., 3., 4., 5., 6., 7., 8.],
+                  "expected_csc": csmat("CSC", (5, 4), [0, 2, 4, 5, 8],
+                                        [0, 1, 0, 4, 3, 2, 3, 4],
+                                        [1., 3., 2., 7., 5., 4., 6., 8.])},
+    # triplet.rs:571-580 triplet_empty_lines (gh#170), first part
+    "empty": {"shape": [2, 4], "rows": [], "cols": [], "data": [],
+              "expected_csr_indptr": [0, 0, 0]}}
 # ---- sprs/src/sparse/prod.rs:604-605 layout-sweep tolerances
 F["assert_close"] = {"rtol": 1e-7, "atol": 1e-12}
 
@@ -140,6 +159,11 @@ def main():
     for k in ("kat_mul_csr_vec", "kat_mul_csc_vec"):
         y = to_scipy(F[k]["mat"]) @ np.array(F[k]["x"])
         assert np.abs(y - np.array(F[k]["expected"])).max() < F[k]["epsilon"]
+    for name, k in F["kat_triplets"].items():
+        if "expected_csc" in k:
+            got = sp.coo_matrix((k["data"], (k["rows"], k["cols"])), shape=tuple(k["shape"])).tocsc()
+            got.sum_duplicates()
+            assert same(got, k["expected_csc"]), name
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sprs_fixtures.json")
     with open(out, "w") as f:
         json.dump(F, f, indent=1)

@@ -302,3 +302,19 @@ def test_from_triplets_vs_scipy(sp, shape, n):
     if n:
         x = rng.standard_normal(shape[1])
         assert np.allclose(m * x, ref @ x, rtol=1e-9, atol=1e-9)
+
+
+def test_triplet_kats(sp, fixtures, O):
+    """triplet.rs:342-453 triplet_incremental / unordered / additions / from_vecs and
+    :571-580 triplet_empty_lines, through the device COO->CSR path."""
+    for name, k in fixtures["kat_triplets"].items():
+        m = sp.CsMat.from_triplets(tuple(k["shape"]), k["rows"], k["cols"], k["data"])
+        assert m.is_csr() and m.shape == tuple(k["shape"])
+        if "expected_csc" in k:
+            e = csmat(sp, k["expected_csc"])
+            assert m.to_csc() == e, name          # csr_to_csc == expected (triplet.rs:392-394)
+            oip, oind, od = O.triplets_to_csr(k["shape"], k["rows"], k["cols"], k["data"], np.uint64)
+            assert m.indptr.tolist() == oip.tolist() and m.indices.tolist() == oind.tolist()
+            assert m.data.tolist() == od.tolist(), name
+        else:
+            assert m.indptr.tolist() == k["expected_csr_indptr"] and m.nnz() == 0

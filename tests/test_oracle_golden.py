@@ -254,3 +254,19 @@ def test_random_vs_scipy(seed):
     y = np.zeros(n)
     O.mul_acc_mat_vec_csr(*a, x, y)
     assert np.allclose(y, A @ x, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("I", [np.uint32, np.uint64])
+def test_triplets_to_csr(fixtures, I):
+    """triplet.rs:342-453 triplet_incremental / unordered / additions / from_vecs and
+    :571-580 triplet_empty_lines: TriMat::to_csr == expected CSC converted to CSR."""
+    for name, k in fixtures["kat_triplets"].items():
+        ip, ind, d = O.triplets_to_csr(k["shape"], k["rows"], k["cols"], k["data"], I)
+        if "expected_csc" in k:
+            e = k["expected_csc"]
+            eip, eind, ed = mat_arrays(e, I)
+            rip, rind, rd = O.convert_mat_storage(e["shape"][1], e["shape"][0], eip, eind, ed)
+            assert ip.tolist() == rip.tolist(), name
+            assert ind.tolist() == rind.tolist() and d.tolist() == rd.tolist(), name
+        else:
+            assert ip.tolist() == k["expected_csr_indptr"] and len(ind) == 0 and len(d) == 0
