@@ -191,7 +191,8 @@ int sprs_b200_spmv_allgather_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
  * symbolic: pattern of C = A*B; returns a plan and nnz(C).
  * numeric : fills caller arrays: indptr (A.rows+1), indices (nnzC, ascending per
  *           row, structural zeros kept -- smmp.rs:109-129), data (nnzC).
- * Both operands must be CSR with A.cols == B.rows (else DIMENSION / STORAGE).     */
+ * Both operands must be CSR with A.cols == B.rows (else DIMENSION / STORAGE).
+ * The plan BORROWS both operand mirrors: keep them alive until spgemm_free.         */
 int sprs_b200_spgemm_symbolic(sprs_b200_ctx* ctx, const sprs_b200_csmat* a,
                               const sprs_b200_csmat* b, sprs_b200_spgemm** plan,
                               uint64_t* nnz_c);

@@ -533,8 +533,9 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
     auto kern = yt.n > 1 ? spmv_warp_kernel<P, WT, STAGES, NWARPS, CTAS, true>
                          : spmv_warp_kernel<P, WT, STAGES, NWARPS, CTAS, false>;
     const size_t smem = STAGES == 0 ? (size_t)NWARPS * WT * 8 : (size_t)NWARPS * STAGES * WT * 12;
-    static bool configured_single = false, configured_multi = false;
-    bool& configured = yt.n > 1 ? configured_multi : configured_single;
+    // function attributes are per device: remember them per (device, kernel flavour)
+    static bool configured_flags[64][2] = {};
+    bool& configured = configured_flags[ctx->device & 63][yt.n > 1 ? 1 : 0];
     if (!configured) {
         SPRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)smem));
