@@ -307,9 +307,10 @@ def main():
     t_gen = time.time() - t_gen
     if args.exchange == "auto":
         # measured (profiles/r1_multi_gpu.md): the own put kernel is the fastest exchange at
-        # 2 and 4 GPUs (2.27 / 1.33 ms vs nccl 2.39 / 1.36, fused 2.43 / 1.38); at 8 GPUs
-        # fused measured 0.82 ms (nccl 1.30) and push is expected level with it
-        args.exchange = "push"
+        # 2 and 4 GPUs (2.27 / 1.33 ms vs nccl 2.39 / 1.36, fused 2.43 / 1.38); its cost grows
+        # with the bytes pushed (~0.14 ms at 40 MB, ~0.22 ms at 60 MB), while at 8 GPUs the
+        # fused kernel measured 0.82 ms against 0.61 ms of pure compute -> fused from 6 GPUs up
+        args.exchange = "fused" if world >= 6 else "push"
     fused = world > 1 and args.exchange in ("fused", "overlap", "push")
 
     def make_op(a_blk, bnds):
