@@ -117,3 +117,19 @@ def test_spmm_1m_k64_full_size(sp, O):
         O.csr_mulacc_dense_rowmaj(np.array([0, e - s], np.uint32), np.arange(e - s, dtype=np.uint32),
                                   cv, bsub, ref)
         assert np.array_equal(c[r].cpu().numpy(), ref[0]), r
+
+
+def test_matrix_market_to_device(sp):
+    """io.rs:682-695 read_symmetric_matrix_market: file -> TriMat (host parser) -> device
+    COO->CSR -> CSC equals the reference's expected matrix; simple.mm round-trips."""
+    import os
+    from sprs_b200 import io as mm
+    data = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "matrix_market")
+    csc = mm.read_matrix_market(os.path.join(data, "symmetric.mm")).to_csc()
+    expected = sp.CsMat.new_csc((5, 5), [0, 1, 3, 4, 6, 8], [0, 1, 3, 2, 1, 4, 3, 4],
+                                [1., 10.5, 2.505e2, 1.5e-2, 2.505e2, 3.332e1, 3.332e1, 1.2e1])
+    assert csc == expected
+    csr = mm.read_matrix_market(os.path.join(data, "simple.mm")).to_csr()
+    assert csr.nnz() == 8 and csr.indptr.tolist() == [0, 2, 3, 4, 7, 8]
+    assert csr.indices.tolist() == [0, 3, 1, 2, 1, 3, 4, 4]
+    assert csr.data.tolist() == [1., 6., 10.5, 1.5e-2, 2.505e2, -2.8e2, 3.332e1, 1.2e1]
