@@ -73,3 +73,19 @@ def test_host_structure_checks():
     assert m.transpose_view().shape == (3, 2) and m.transpose_view().is_csc()
     s = sp.CsMat.new((4, 4), [0, 1, 2, 3, 4], [0, 1, 2, 3], np.ones(4)).slice_outer(1, 3)
     assert s.shape == (2, 4) and s.indptr[0] == 1 and s.nnz() == 2
+
+
+def test_cpp_host_mirror_logic_without_gpu():
+    """C++ host mirror (include/sprs_b200.hpp): structure checks, views and the panics that
+    fire before any device work; the product itself must fail loudly without a GPU."""
+    exe = os.path.join(ROOT, "tests", "cpp", "test_host_logic")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.dirname(exe)])
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    r = subprocess.run([exe] + (["gpu"] if has_gpu else []), capture_output=True, text=True,
+                       timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
