@@ -206,6 +206,50 @@ int sprs_b200_spgemm_numeric_dev(sprs_b200_ctx* ctx, sprs_b200_spgemm* plan,
 uint64_t sprs_b200_spgemm_nprod(const sprs_b200_spgemm* plan);
 int sprs_b200_spgemm_free(sprs_b200_spgemm* plan);
 
+/* ---- BiCGSTAB with device-resident vectors ---------------
+ * Replaces sprs::linalg::bicgstab::BiCGSTAB<f64> (linalg/bicgstab.rs:95-300): `new`
+ * (:120-146) computes r = b - A x0, rhat = p = r, err = |r|, rho = err^2; `step`
+ * (:198-234), `soft_restart` (:177-184), `hard_restart` (:186-196) and `solve`
+ * (:151-175) follow the reference operation by operation (unfused multiply/add; dot
+ * products summed in a fixed order, so repeatable, but not the reference's strictly
+ * sequential order: values agree to rounding).  x, r, rhat, p, b stay in HBM across
+ * iterations; a step moves three 16-byte scalar pairs to the host.
+ * The matrix may be CSR or CSC (both sum A*v in ascending column order) and must be
+ * square with n rows (else DIMENSION, the reference's "Dimension mismatch" panic).  The
+ * solver BORROWS the matrix mirror: keep it alive until bicgstab_free.  x0 and b are
+ * copied (host pointers for _new, device pointers for _new_dev).                      */
+typedef struct sprs_b200_bicgstab sprs_b200_bicgstab;
+enum {
+    SPRS_B200_BICGSTAB_X = 0,    /* x()    latest solution            (bicgstab.rs:272) */
+    SPRS_B200_BICGSTAB_R = 1,    /* r()    latest residual            (:282)            */
+    SPRS_B200_BICGSTAB_RHAT = 2, /* rhat() reference direction        (:290)            */
+    SPRS_B200_BICGSTAB_P = 3,    /* p()    step direction             (:295)            */
+    SPRS_B200_BICGSTAB_B = 4     /* b()    the objective vector       (:277)            */
+};
+int sprs_b200_bicgstab_new(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, const double* x0,
+                           const double* b, uint64_t n, sprs_b200_bicgstab** out);
+int sprs_b200_bicgstab_new_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
+                               const double* d_x0, const double* d_b, uint64_t n,
+                               sprs_b200_bicgstab** out);
+int sprs_b200_bicgstab_free(sprs_b200_bicgstab* s);
+/* one iteration; *err_out (optional) = the running error estimate |r| */
+int sprs_b200_bicgstab_step(sprs_b200_bicgstab* s, double* err_out);
+int sprs_b200_bicgstab_soft_restart(sprs_b200_bicgstab* s);
+int sprs_b200_bicgstab_hard_restart(sprs_b200_bicgstab* s);
+/* up to max_iter steps; *converged = 1 (Ok) when the TRUE error |b - A x| < tol was
+ * confirmed by a hard restart, 0 (Err) when the iteration limit was reached.          */
+int sprs_b200_bicgstab_solve(sprs_b200_bicgstab* s, double tol, uint64_t max_iter,
+                             int* converged);
+int sprs_b200_bicgstab_set_restart_threshold(sprs_b200_bicgstab* s, double thresh);
+/* counts = {iteration_count, soft_restart_count, hard_restart_count};
+ * scalars = {err, rho, soft_restart_threshold}; either may be NULL                    */
+int sprs_b200_bicgstab_stats(const sprs_b200_bicgstab* s, uint64_t counts[3],
+                             double scalars[3]);
+/* copy vector `which` (enum above) to a host array of len == n */
+int sprs_b200_bicgstab_get(const sprs_b200_bicgstab* s, int which, double* out, uint64_t len);
+/* borrowed device pointer to vector `which` (valid until bicgstab_free) */
+int sprs_b200_bicgstab_get_dev(const sprs_b200_bicgstab* s, int which, const double** d_out);
+
 /* ---- synthetic inputs, generated in HBM (sprs-rand/src/lib.rs:24-81
  * gives the uniform distribution; R-MAT is this repo's definition).  Each writes
  * `count` 64-bit keys (row<<32 | col) for candidate edges [first, first+count);

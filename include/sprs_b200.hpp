@@ -18,6 +18,7 @@
 // a call into libsprs_b200.so -- there is no CPU implementation in this header.
 // The Rust crates in rust/ are the same wrapper in the reference's own language.
 #pragma once
+#include <array>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -411,5 +412,82 @@ CsVecI<I> operator*(const CsVecI<I>& v, const CsMatI<I, Iptr>& a) {
     auto c = (row * a).to_csr();
     return CsVecI<I>(a.cols(), c.indices(), c.data());
 }
+
+// ------------------------------------------------------------------------------------
+// sprs::linalg::bicgstab::BiCGSTAB<f64> (linalg/bicgstab.rs:95-300) with every vector
+// resident on the device between iterations.  Vectors cross this API as dense Array1
+// (the reference's CsVec arithmetic is dense arithmetic on the union pattern).
+namespace linalg {
+namespace bicgstab {
+template <class I, class Iptr>
+class BiCGSTAB {
+   public:
+    // BiCGSTAB::new (bicgstab.rs:120-146); borrows `a` like the reference's view does
+    BiCGSTAB(const CsMatI<I, Iptr>& a, const Array1& x0, const Array1& b) : a_(&a) {
+        if (a.cols() != x0.size() || a.rows() != b.size()) throw Panic("Dimension mismatch");
+        Context& ctx = Context::thread_default();
+        ctx.check(sprs_b200_bicgstab_new(ctx.handle(), a.device(), x0.data(), b.data(),
+                                         b.size(), &h_));
+    }
+    BiCGSTAB(const BiCGSTAB&) = delete;
+    BiCGSTAB& operator=(const BiCGSTAB&) = delete;
+    ~BiCGSTAB() { sprs_b200_bicgstab_free(h_); }
+
+    // BiCGSTAB::solve (bicgstab.rs:151-175): first = true for Ok, false for Err; the
+    // solver comes back either way, as in Result<Box<Self>, Box<Self>>
+    static std::pair<bool, std::unique_ptr<BiCGSTAB>> solve(const CsMatI<I, Iptr>& a,
+                                                            const Array1& x0, const Array1& b,
+                                                            double tol, size_t max_iter) {
+        auto s = std::make_unique<BiCGSTAB>(a, x0, b);
+        int converged = 0;
+        check(sprs_b200_bicgstab_solve(s->h_, tol, max_iter, &converged));
+        return {converged != 0, std::move(s)};
+    }
+    double step() {
+        double err = 0.0;
+        check(sprs_b200_bicgstab_step(h_, &err));
+        return err;
+    }
+    void soft_restart() { check(sprs_b200_bicgstab_soft_restart(h_)); }
+    void hard_restart() { check(sprs_b200_bicgstab_hard_restart(h_)); }
+    BiCGSTAB& with_restart_threshold(double thresh) {
+        check(sprs_b200_bicgstab_set_restart_threshold(h_, thresh));
+        return *this;
+    }
+    size_t iteration_count() const { return (size_t)counts()[0]; }
+    size_t soft_restart_count() const { return (size_t)counts()[1]; }
+    size_t hard_restart_count() const { return (size_t)counts()[2]; }
+    double err() const { return scalars()[0]; }
+    double rho() const { return scalars()[1]; }
+    double soft_restart_threshold() const { return scalars()[2]; }
+    const CsMatI<I, Iptr>& a() const { return *a_; }
+    Array1 x() const { return vec(SPRS_B200_BICGSTAB_X); }
+    Array1 b() const { return vec(SPRS_B200_BICGSTAB_B); }
+    Array1 r() const { return vec(SPRS_B200_BICGSTAB_R); }
+    Array1 rhat() const { return vec(SPRS_B200_BICGSTAB_RHAT); }
+    Array1 p() const { return vec(SPRS_B200_BICGSTAB_P); }
+
+   private:
+    static void check(int st) { Context::thread_default().check(st); }
+    std::array<uint64_t, 3> counts() const {
+        std::array<uint64_t, 3> c{};
+        check(sprs_b200_bicgstab_stats(h_, c.data(), nullptr));
+        return c;
+    }
+    std::array<double, 3> scalars() const {
+        std::array<double, 3> v{};
+        check(sprs_b200_bicgstab_stats(h_, nullptr, v.data()));
+        return v;
+    }
+    Array1 vec(int which) const {
+        Array1 out(a_->rows());
+        check(sprs_b200_bicgstab_get(h_, which, out.data(), out.size()));
+        return out;
+    }
+    const CsMatI<I, Iptr>* a_;
+    sprs_b200_bicgstab* h_ = nullptr;
+};
+}  // namespace bicgstab
+}  // namespace linalg
 
 }  // namespace sprs

@@ -210,6 +210,95 @@ def numeric(a_rows, b_cols, a, b, c_indptr, c_indices):
     return cd
 
 
+class BiCGSTAB:
+    """linalg/bicgstab.rs:95-300 on dense f64 vectors (see the restatement's header comment).
+    The matrix is CSR (indptr, indices, data); a CSC matrix goes through
+    convert_mat_storage first -- A*v sums in ascending column order either way."""
+
+    def __init__(self, csr, x0, b):
+        self._csr = _csx(*csr)  # borrowed by the C side: keep alive
+        ip, ind, d = self._csr
+        self.n = len(ip) - 1
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        assert x0.shape == (self.n,) and b.shape == (self.n,)
+        L = lib()
+        f = getattr(L, "oracle_bicgstab_new_" + _suffix(ip, ind))
+        f.restype = C.c_void_p
+        self._h = C.c_void_p(f(C.c_size_t(self.n), _p(ip), _p(ind), _p(d), _p(x0), _p(b)))
+        L.oracle_bicgstab_step.restype = C.c_double
+        L.oracle_bicgstab_solve.restype = C.c_int
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().oracle_bicgstab_free(self._h)
+            self._h = None
+
+    @classmethod
+    def solve(cls, csr, x0, b, tol, max_iter):
+        """Returns (ok, solver): Ok(solver) / Err(solver) of bicgstab.rs:151-175."""
+        s = cls(csr, x0, b)
+        ok = lib().oracle_bicgstab_solve(s._h, C.c_double(tol), C.c_size_t(max_iter))
+        return bool(ok), s
+
+    def step(self):
+        return float(lib().oracle_bicgstab_step(self._h))
+
+    def soft_restart(self):
+        lib().oracle_bicgstab_soft_restart(self._h)
+
+    def hard_restart(self):
+        lib().oracle_bicgstab_hard_restart(self._h)
+
+    def with_restart_threshold(self, thresh):
+        lib().oracle_bicgstab_set_threshold(self._h, C.c_double(thresh))
+        return self
+
+    def _vec(self, which):
+        out = np.empty(self.n, dtype=np.float64)
+        lib().oracle_bicgstab_get(self._h, C.c_int(which), _p(out))
+        return out
+
+    def _stats(self):
+        counts = (C.c_size_t * 3)()
+        scal = (C.c_double * 3)()
+        lib().oracle_bicgstab_stats(self._h, counts, scal)
+        return list(counts), list(scal)
+
+    def x(self):
+        return self._vec(0)
+
+    def r(self):
+        return self._vec(1)
+
+    def rhat(self):
+        return self._vec(2)
+
+    def p(self):
+        return self._vec(3)
+
+    def b(self):
+        return self._vec(4)
+
+    def iteration_count(self):
+        return self._stats()[0][0]
+
+    def soft_restart_count(self):
+        return self._stats()[0][1]
+
+    def hard_restart_count(self):
+        return self._stats()[0][2]
+
+    def err(self):
+        return self._stats()[1][0]
+
+    def rho(self):
+        return self._stats()[1][1]
+
+    def soft_restart_threshold(self):
+        return self._stats()[1][2]
+
+
 def ext_spmv_csr_omp(indptr, indices, data, x, y, threads):
     """EXTENSION (not in the reference): all-cores row-chunked SpMV, u32 only."""
     indptr, indices, data = _csx(indptr, indices, data)

@@ -23,6 +23,8 @@
 // sprs, every access subtracts indptr[0].
 
 #include <algorithm>
+#include <cmath>
+#include <functional>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
@@ -417,6 +419,128 @@ SpgemmResult<I, P>* mul_csr_csr(size_t a_rows, size_t a_cols, size_t b_cols,
     return res;
 }
 
+// ---------------------------------------------------------------------------
+// linalg/bicgstab.rs:95-300  BiCGSTAB (the iterative caller of SpMV).
+//
+// The reference keeps every vector as a CsVec and builds the iteration from sparse ops:
+// `&A * &v` (vec.rs:1104-1131 -> prod.rs:162-184 for CSR, csmat_mul_csmat for CSC),
+// csvec_binop (binop.rs:442-470: a missing entry takes part as an explicit 0.0),
+// `map` (vec.rs:989-997), `dot` (vec.rs:846-881: sequential mul_acc over the matching
+// entries) and `squared_l2_norm` (vec.rs:907-913: sequential sum of x*x).  On vectors whose
+// stored pattern is full that is exactly dense arithmetic in index order, which is what is
+// restated here (a dropped exact zero contributes +0.0 to every sum, so the value is the
+// same; only NaN/Inf-times-zero and the sign of zero could differ).  Both storages give the
+// same summation order for A*v: ascending column within each row.
+struct Bicgstab {
+    size_t n = 0;
+    std::function<void(const double*, double*)> matvec;  // y = A x (y zeroed first)
+    std::vector<double> b, x, r, rhat, p;
+    double rho = 0, err = 0, soft_restart_threshold = 0.1;
+    size_t iteration_count = 0, soft_restart_count = 0, hard_restart_count = 0;
+
+    static double dot(const std::vector<double>& a, const std::vector<double>& c) {
+        double sum = 0.0;
+        for (size_t i = 0; i < a.size(); ++i) {
+            const double prod = a[i] * c[i];
+            sum = sum + prod;
+        }
+        return sum;
+    }
+    // bicgstab.rs:120-146  new
+    void init(const double* x0, const double* b_) {
+        b.assign(b_, b_ + n);
+        x.assign(x0, x0 + n);
+        std::vector<double> ax(n, 0.0);
+        matvec(x.data(), ax.data());
+        r.resize(n);
+        for (size_t i = 0; i < n; ++i) r[i] = b[i] - ax[i];
+        rhat = r;
+        p = r;
+        err = std::sqrt(dot(r, r));
+        rho = err * err;
+    }
+    // bicgstab.rs:177-184
+    void soft_restart() {
+        soft_restart_count += 1;
+        rhat = r;
+        rho = err * err;
+        p = r;
+    }
+    // bicgstab.rs:186-196
+    void hard_restart() {
+        hard_restart_count += 1;
+        std::vector<double> ax(n, 0.0);
+        matvec(x.data(), ax.data());
+        for (size_t i = 0; i < n; ++i) r[i] = b[i] - ax[i];
+        err = std::sqrt(dot(r, r));
+        soft_restart();
+        soft_restart_count -= 1;
+    }
+    // bicgstab.rs:198-234
+    double step() {
+        iteration_count += 1;
+        std::vector<double> v(n, 0.0), s(n), t(n, 0.0), h(n);
+        matvec(p.data(), v.data());
+        const double alpha = rho / dot(rhat, v);
+        for (size_t i = 0; i < n; ++i) {
+            const double pa = p[i] * alpha;
+            h[i] = x[i] + pa;
+        }
+        for (size_t i = 0; i < n; ++i) {
+            const double va = v[i] * alpha;
+            s[i] = r[i] - va;
+        }
+        matvec(s.data(), t.data());
+        const double omega = dot(t, s) / dot(t, t);
+        for (size_t i = 0; i < n; ++i) {
+            const double os = omega * s[i];
+            x[i] = h[i] + os;
+        }
+        for (size_t i = 0; i < n; ++i) {
+            const double to = t[i] * omega;
+            r[i] = s[i] - to;
+        }
+        err = std::sqrt(dot(r, r));
+        const double rho_prev = rho;
+        rho = dot(rhat, r);
+        if (std::fabs(rho) / (err * err) < soft_restart_threshold) {
+            soft_restart();
+        } else {
+            const double beta = (rho / rho_prev) * (alpha / omega);
+            for (size_t i = 0; i < n; ++i) {
+                const double vo = v[i] * omega;
+                const double d = p[i] - vo;
+                const double db = d * beta;
+                p[i] = r[i] + db;
+            }
+        }
+        return err;
+    }
+    // bicgstab.rs:151-175: 1 = Ok, 0 = Err (the solver state is returned either way)
+    int solve(double tol, size_t max_iter) {
+        for (size_t it = 0; it < max_iter; ++it) {
+            step();
+            if (err < tol) {
+                hard_restart();
+                if (err < tol) return 1;
+            }
+        }
+        return 0;
+    }
+};
+
+template <class I, class P>
+Bicgstab* bicgstab_new(size_t rows, const P* ip, const I* ind, const double* d, const double* x0,
+                       const double* b) {
+    auto* s = new Bicgstab;
+    s->n = rows;
+    s->matvec = [=](const double* x, double* y) {
+        mul_acc_mat_vec_csr<I, P>(rows, ip, ind, d, x, y);
+    };
+    s->init(x0, b);
+    return s;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -466,6 +590,11 @@ SpgemmResult<I, P>* mul_csr_csr(size_t a_rows, size_t a_cols, size_t b_cols,
                                                    const I* ci, const double* v, P* ip, I* ind,  \
                                                    double* d) {                                  \
         return triplets_to_csr<I, P>(rows, n, ri, ci, v, ip, ind, d);                            \
+    }                                                                                           \
+    extern "C" void* oracle_bicgstab_new_##SUF(size_t rows, const P* ip, const I* ind,           \
+                                               const double* d, const double* x0,               \
+                                               const double* b) {                               \
+        return bicgstab_new<I, P>(rows, ip, ind, d, x0, b);                                     \
     }                                                                                           \
     extern "C" void* oracle_mul_csr_csr_##SUF(size_t ar, size_t ac, size_t bc, const P* aip,    \
                                               const I* aind, const double* ad, const P* bip,    \
@@ -522,6 +651,34 @@ extern "C" void oracle_ext_spmv_csr_omp_44(size_t rows, const uint32_t* ip, cons
         y[r] = tv;
     }
 }
+
+// BiCGSTAB handle API (the matrix arrays passed to oracle_bicgstab_new_* are borrowed).
+extern "C" double oracle_bicgstab_step(void* h) { return ((Bicgstab*)h)->step(); }
+extern "C" void oracle_bicgstab_soft_restart(void* h) { ((Bicgstab*)h)->soft_restart(); }
+extern "C" void oracle_bicgstab_hard_restart(void* h) { ((Bicgstab*)h)->hard_restart(); }
+extern "C" int oracle_bicgstab_solve(void* h, double tol, size_t max_iter) {
+    return ((Bicgstab*)h)->solve(tol, max_iter);
+}
+extern "C" void oracle_bicgstab_set_threshold(void* h, double t) {
+    ((Bicgstab*)h)->soft_restart_threshold = t;
+}
+// which: 0 x, 1 r, 2 rhat, 3 p, 4 b
+extern "C" void oracle_bicgstab_get(void* h, int which, double* out) {
+    Bicgstab* s = (Bicgstab*)h;
+    const std::vector<double>* v[5] = {&s->x, &s->r, &s->rhat, &s->p, &s->b};
+    std::memcpy(out, v[which]->data(), s->n * sizeof(double));
+}
+// counts = {iteration, soft restarts, hard restarts}; scalars = {err, rho, threshold}
+extern "C" void oracle_bicgstab_stats(void* h, size_t* counts, double* scalars) {
+    Bicgstab* s = (Bicgstab*)h;
+    counts[0] = s->iteration_count;
+    counts[1] = s->soft_restart_count;
+    counts[2] = s->hard_restart_count;
+    scalars[0] = s->err;
+    scalars[1] = s->rho;
+    scalars[2] = s->soft_restart_threshold;
+}
+extern "C" void oracle_bicgstab_free(void* h) { delete (Bicgstab*)h; }
 
 extern "C" int oracle_num_procs(void) {
 #ifdef _OPENMP

@@ -8,6 +8,7 @@ use std::os::raw::{c_char, c_double, c_int, c_void};
 #[repr(C)] pub struct sprs_b200_ctx { _private: [u8; 0] }
 #[repr(C)] pub struct sprs_b200_csmat { _private: [u8; 0] }
 #[repr(C)] pub struct sprs_b200_spgemm { _private: [u8; 0] }
+#[repr(C)] pub struct sprs_b200_bicgstab { _private: [u8; 0] }
 
 pub const SPRS_B200_CSR: c_int = 0;
 pub const SPRS_B200_CSC: c_int = 1;
@@ -17,6 +18,11 @@ pub const SPRS_B200_ERR_STORAGE: c_int = 2;
 pub const SPRS_B200_ERR_CUDA: c_int = 3;
 pub const SPRS_B200_ERR_NCCL: c_int = 4;
 pub const SPRS_B200_ERR_INDEX_RANGE: c_int = 5;
+pub const SPRS_B200_BICGSTAB_X: c_int = 0;
+pub const SPRS_B200_BICGSTAB_R: c_int = 1;
+pub const SPRS_B200_BICGSTAB_RHAT: c_int = 2;
+pub const SPRS_B200_BICGSTAB_P: c_int = 3;
+pub const SPRS_B200_BICGSTAB_B: c_int = 4;
 
 extern "C" {
     pub fn sprs_b200_version() -> c_int;
@@ -67,4 +73,19 @@ extern "C" {
         ctx: *mut sprs_b200_ctx, plan: *mut sprs_b200_spgemm, c_indptr: *mut c_void,
         indptr_bytes: c_int, c_indices: *mut c_void, index_bytes: c_int, c_data: *mut c_double) -> c_int;
     pub fn sprs_b200_spgemm_free(plan: *mut sprs_b200_spgemm) -> c_int;
+    // linalg::bicgstab::BiCGSTAB<f64> with device-resident vectors (bicgstab.rs:95-300)
+    pub fn sprs_b200_bicgstab_new(
+        ctx: *mut sprs_b200_ctx, mat: *const sprs_b200_csmat, x0: *const c_double,
+        b: *const c_double, n: u64, out: *mut *mut sprs_b200_bicgstab) -> c_int;
+    pub fn sprs_b200_bicgstab_free(s: *mut sprs_b200_bicgstab) -> c_int;
+    pub fn sprs_b200_bicgstab_step(s: *mut sprs_b200_bicgstab, err_out: *mut c_double) -> c_int;
+    pub fn sprs_b200_bicgstab_soft_restart(s: *mut sprs_b200_bicgstab) -> c_int;
+    pub fn sprs_b200_bicgstab_hard_restart(s: *mut sprs_b200_bicgstab) -> c_int;
+    pub fn sprs_b200_bicgstab_solve(
+        s: *mut sprs_b200_bicgstab, tol: c_double, max_iter: u64, converged: *mut c_int) -> c_int;
+    pub fn sprs_b200_bicgstab_set_restart_threshold(s: *mut sprs_b200_bicgstab, thresh: c_double) -> c_int;
+    pub fn sprs_b200_bicgstab_stats(
+        s: *const sprs_b200_bicgstab, counts: *mut u64, scalars: *mut c_double) -> c_int;
+    pub fn sprs_b200_bicgstab_get(
+        s: *const sprs_b200_bicgstab, which: c_int, out: *mut c_double, len: u64) -> c_int;
 }

@@ -11,7 +11,7 @@
 //! ```
 //! Contract violations panic with the reference's messages (Guidelines.rst:9-27);
 //! device failures are `LinalgError::ThirdPartyError(code, msg)` (errors.rs:70).
-use ndarray::{Array1, Array2, ArrayBase, Data, Ix1, Ix2, ShapeBuilder};
+use ndarray::{Array1, Array2, ArrayBase, ArrayView1, Data, Ix1, Ix2, ShapeBuilder};
 use sprs::errors::LinalgError;
 use sprs::{CsMatI, CsMatViewI, SpIndex};
 use sprs_b200_sys as ffi;
@@ -149,4 +149,72 @@ pub fn mul_csr_csr<I: SpIndex, Iptr: SpIndex>(lhs: &DeviceCsMat<I, Iptr>, rhs: &
 impl<'a, 'b, I: SpIndex, Iptr: SpIndex> Mul<&'b DeviceCsMat<I, Iptr>> for &'a DeviceCsMat<I, Iptr> {
     type Output = CsMatI<f64, I, Iptr>;
     fn mul(self, rhs: &'b DeviceCsMat<I, Iptr>) -> Self::Output { mul_csr_csr(self, rhs) }
+}
+
+/// sprs::linalg::bicgstab::BiCGSTAB<f64> (linalg/bicgstab.rs:95-300) with x, r, rhat, p
+/// resident on the device between iterations.  Same constructor, `solve`, `step`,
+/// restarts and accessors; vectors cross the API as dense `Array1<f64>`.
+pub mod bicgstab {
+    use super::*;
+    pub struct BiCGSTAB<'a, I: SpIndex, Iptr: SpIndex> { a: &'a DeviceCsMat<I, Iptr>, h: *mut ffi::sprs_b200_bicgstab }
+    impl<'a, I: SpIndex, Iptr: SpIndex> Drop for BiCGSTAB<'a, I, Iptr> {
+        fn drop(&mut self) { unsafe { ffi::sprs_b200_bicgstab_free(self.h); } }
+    }
+    impl<'a, I: SpIndex, Iptr: SpIndex> BiCGSTAB<'a, I, Iptr> {
+        /// bicgstab.rs:120-146
+        pub fn new(a: &'a DeviceCsMat<I, Iptr>, x0: ArrayView1<f64>, b: ArrayView1<f64>) -> Self {
+            assert_eq!(a.host.cols(), x0.len(), "Dimension mismatch");
+            assert_eq!(a.host.rows(), b.len(), "Dimension mismatch");
+            let (x0, b) = (x0.to_owned(), b.to_owned()); // contiguous
+            let mut h = std::ptr::null_mut();
+            CTX.with(|c| check(c.0, unsafe {
+                ffi::sprs_b200_bicgstab_new(c.0, a.dev, x0.as_ptr(), b.as_ptr(), b.len() as u64, &mut h)
+            })).expect("sprs_b200 device error");
+            Self { a, h }
+        }
+        /// bicgstab.rs:151-175
+        pub fn solve(a: &'a DeviceCsMat<I, Iptr>, x0: ArrayView1<f64>, b: ArrayView1<f64>, tol: f64,
+                     max_iter: usize) -> Result<Box<Self>, Box<Self>> {
+            let solver = Self::new(a, x0, b);
+            let mut converged = 0;
+            CTX.with(|c| check(c.0, unsafe {
+                ffi::sprs_b200_bicgstab_solve(solver.h, tol, max_iter as u64, &mut converged)
+            })).expect("sprs_b200 device error");
+            if converged != 0 { Ok(Box::new(solver)) } else { Err(Box::new(solver)) }
+        }
+        pub fn step(&mut self) -> f64 {
+            let mut err = 0.0;
+            CTX.with(|c| check(c.0, unsafe { ffi::sprs_b200_bicgstab_step(self.h, &mut err) }))
+                .expect("sprs_b200 device error");
+            err
+        }
+        pub fn soft_restart(&mut self) { unsafe { ffi::sprs_b200_bicgstab_soft_restart(self.h); } }
+        pub fn hard_restart(&mut self) { unsafe { ffi::sprs_b200_bicgstab_hard_restart(self.h); } }
+        pub fn with_restart_threshold(self, thresh: f64) -> Self {
+            unsafe { ffi::sprs_b200_bicgstab_set_restart_threshold(self.h, thresh); }
+            self
+        }
+        fn stats(&self) -> ([u64; 3], [f64; 3]) {
+            let (mut c, mut s) = ([0u64; 3], [0f64; 3]);
+            unsafe { ffi::sprs_b200_bicgstab_stats(self.h, c.as_mut_ptr(), s.as_mut_ptr()); }
+            (c, s)
+        }
+        pub fn iteration_count(&self) -> usize { self.stats().0[0] as usize }
+        pub fn soft_restart_count(&self) -> usize { self.stats().0[1] as usize }
+        pub fn hard_restart_count(&self) -> usize { self.stats().0[2] as usize }
+        pub fn err(&self) -> f64 { self.stats().1[0] }
+        pub fn rho(&self) -> f64 { self.stats().1[1] }
+        pub fn soft_restart_threshold(&self) -> f64 { self.stats().1[2] }
+        pub fn a(&self) -> &DeviceCsMat<I, Iptr> { self.a }
+        fn vec(&self, which: i32) -> Array1<f64> {
+            let mut out = Array1::zeros(self.a.host.rows());
+            unsafe { ffi::sprs_b200_bicgstab_get(self.h, which, out.as_mut_ptr(), out.len() as u64); }
+            out
+        }
+        pub fn x(&self) -> Array1<f64> { self.vec(ffi::SPRS_B200_BICGSTAB_X) }
+        pub fn b(&self) -> Array1<f64> { self.vec(ffi::SPRS_B200_BICGSTAB_B) }
+        pub fn r(&self) -> Array1<f64> { self.vec(ffi::SPRS_B200_BICGSTAB_R) }
+        pub fn rhat(&self) -> Array1<f64> { self.vec(ffi::SPRS_B200_BICGSTAB_RHAT) }
+        pub fn p(&self) -> Array1<f64> { self.vec(ffi::SPRS_B200_BICGSTAB_P) }
+    }
 }

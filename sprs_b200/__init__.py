@@ -5,11 +5,11 @@ Nothing here computes on the CPU: every product is a call into libsprs_b200.so
 (hand-written CUDA).  Importing works without a GPU (so the ABI can be inspected);
 creating a Context without one raises ThirdPartyError.
 """
-from . import _lib, io
+from . import _lib, io, linalg
 from .sparse import (CSC, CSR, Context, CsMat, CsVec, DeviceCsMat, SprsPanic, ThirdPartyError,
                      csmat_mul_csmat, prod, smmp)
 
 __all__ = ["CSC", "CSR", "Context", "CsMat", "CsVec", "DeviceCsMat", "SprsPanic",
-           "ThirdPartyError", "csmat_mul_csmat", "prod", "smmp", "_lib", "io"]
+           "ThirdPartyError", "csmat_mul_csmat", "prod", "smmp", "_lib", "io", "linalg"]
 __version__ = "0.1.0"
 SPMV_TILE = 384  # nnz per SpMV warp tile (default variant in csrc/spmv.cu); tests use it to find rows cut by a tile

@@ -63,6 +63,17 @@ PROTOTYPES = {
     "sprs_b200_spgemm_numeric_dev": (_int, [_vp, _vp, C.POINTER(_vp)]),
     "sprs_b200_spgemm_nprod": (_u64, [_vp]),
     "sprs_b200_spgemm_free": (_int, [_vp]),
+    "sprs_b200_bicgstab_new": (_int, [_vp, _vp, _dp, _dp, _u64, C.POINTER(_vp)]),
+    "sprs_b200_bicgstab_new_dev": (_int, [_vp, _vp, _dp, _dp, _u64, C.POINTER(_vp)]),
+    "sprs_b200_bicgstab_free": (_int, [_vp]),
+    "sprs_b200_bicgstab_step": (_int, [_vp, C.POINTER(C.c_double)]),
+    "sprs_b200_bicgstab_soft_restart": (_int, [_vp]),
+    "sprs_b200_bicgstab_hard_restart": (_int, [_vp]),
+    "sprs_b200_bicgstab_solve": (_int, [_vp, C.c_double, _u64, C.POINTER(_int)]),
+    "sprs_b200_bicgstab_set_restart_threshold": (_int, [_vp, C.c_double]),
+    "sprs_b200_bicgstab_stats": (_int, [_vp, C.POINTER(_u64), C.POINTER(C.c_double)]),
+    "sprs_b200_bicgstab_get": (_int, [_vp, _int, _dp, _u64]),
+    "sprs_b200_bicgstab_get_dev": (_int, [_vp, _int, C.POINTER(_vp)]),
     "sprs_b200_gen_rmat_keys": (_int, [_vp, _u64, _int, _u64, _u64, C.c_double, C.c_double,
                                        C.c_double, _u64, _u64, _vp, _vp]),
     "sprs_b200_gen_uniform_keys": (_int, [_vp, _u64, _u64, _u64, _u64, _u64, _vp, _vp]),

@@ -681,3 +681,7 @@ int sprs_b200_csc_mulacc_dense_colmaj(sprs_b200_ctx* ctx, const sprs_b200_csmat*
 }
 
 }  // extern "C"
+
+int csmat_csr_view(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const sprs_b200_csmat** out) {
+    return csr_of(ctx, m, out);
+}

@@ -100,6 +100,9 @@ int triplets_to_csr_launch(sprs_b200_ctx* ctx, uint64_t rows, uint64_t cols, uin
                            sprs_b200_csmat* out, cudaStream_t s);
 int transpose_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, sprs_b200_csmat* out,
                      cudaStream_t s);
+// CSR form of a mirror for the product kernels: the mirror itself or (CSC) its cached
+// device conversion, owned by the mirror (api.cu)
+int csmat_csr_view(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const sprs_b200_csmat** out);
 
 // ---- small device helpers -----------------------------------------------------
 #ifdef __CUDACC__

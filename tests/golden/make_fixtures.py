@@ -130,6 +130,16 @@ F["kat_triplets"] = {
     # triplet.rs:571-580 triplet_empty_lines (gh#170), first part
     "empty": {"shape": [2, 4], "rows": [], "cols": [], "data": [],
               "expected_csr_indptr": [0, 0, 0]}}
+# ---- sprs/src/sparse/linalg/bicgstab.rs:356-390 test_bicgstab_f64 (and the doc example
+# :29-68): solve() must return Ok within 50 iterations at tol 1e-60, i.e. reach an exactly
+# zero true residual, and |1 - b/b_recovered| < tol for b_recovered = A x.  `x_exact` is the
+# rational solution of the system (checked below), not something the reference states.
+F["kat_bicgstab"] = {
+    "a": csmat("CSC", (4, 4), [0, 2, 4, 6, 8], [0, 3, 1, 2, 1, 2, 0, 3],
+               [1.0, 2., 21., 6., 6., 2., 2., 8.]),
+    "b": [1.0, 1.0, 1.0, 1.0], "x0": [1.0, 1.0, 1.0, 1.0], "tol": 1e-60, "max_iter": 50,
+    "soft_restart_threshold": 0.1,  # bicgstab.rs:134
+    "x_exact": [1.5, -2.0 / 3.0, 2.5, -0.25]}
 # ---- sprs/src/sparse/prod.rs:604-605 layout-sweep tolerances
 F["assert_close"] = {"rtol": 1e-7, "atol": 1e-12}
 
@@ -164,6 +174,8 @@ def main():
             got = sp.coo_matrix((k["data"], (k["rows"], k["cols"])), shape=tuple(k["shape"])).tocsc()
             got.sum_duplicates()
             assert same(got, k["expected_csc"]), name
+    kb = F["kat_bicgstab"]
+    assert np.allclose(to_scipy(kb["a"]) @ np.array(kb["x_exact"]), kb["b"], rtol=0, atol=1e-15)
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sprs_fixtures.json")
     with open(out, "w") as f:
         json.dump(F, f, indent=1)

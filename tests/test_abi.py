@@ -57,6 +57,8 @@ def test_no_cpu_fallback_without_gpu():
     a = sprs_b200.CsMat.eye(3)
     with pytest.raises(sprs_b200.ThirdPartyError):
         a * np.ones(3)
+    with pytest.raises(sprs_b200.ThirdPartyError):  # the solver has no host path either
+        sprs_b200.linalg.BiCGSTAB.solve(a, np.ones(3), np.ones(3), 1e-9, 10)
 
 
 def test_host_structure_checks():
@@ -73,6 +75,25 @@ def test_host_structure_checks():
     assert m.transpose_view().shape == (3, 2) and m.transpose_view().is_csc()
     s = sp.CsMat.new((4, 4), [0, 1, 2, 3, 4], [0, 1, 2, 3], np.ones(4)).slice_outer(1, 3)
     assert s.shape == (2, 4) and s.indptr[0] == 1 and s.nnz() == 2
+
+
+def test_bicgstab_contract_checks_precede_device_work():
+    """`&a * &x0`, `&b - ..` and `&a * &p` panic on mismatched dimensions before anything is
+    computed (prod.rs:170, binop.rs:455): no device needed to see the panic."""
+    import numpy as np
+    import sprs_b200
+    from sprs_b200.linalg import BiCGSTAB, NotConverged, bicgstab
+    assert bicgstab.BiCGSTAB is BiCGSTAB and issubclass(NotConverged, Exception)
+    a = sprs_b200.CsMat.eye(4)
+    for x0, b in ((np.ones(3), np.ones(4)), (np.ones(4), np.ones(5)),
+                  (sprs_b200.CsVec(5, [0], [1.0]), np.ones(4))):
+        with pytest.raises(sprs_b200.SprsPanic, match="Dimension mismatch"):
+            BiCGSTAB(a, x0, b)
+    rect = sprs_b200.CsMat((3, 4), np.array([0, 1, 2, 3]), np.array([0, 1, 2]), np.ones(3))
+    with pytest.raises(sprs_b200.SprsPanic, match="Dimension mismatch"):
+        BiCGSTAB(rect, np.ones(4), np.ones(3))
+    with pytest.raises(TypeError):
+        BiCGSTAB(np.eye(4), np.ones(4), np.ones(4))
 
 
 def test_cpp_host_mirror_logic_without_gpu():

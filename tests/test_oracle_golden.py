@@ -270,3 +270,84 @@ def test_triplets_to_csr(fixtures, I):
             assert ind.tolist() == rind.tolist() and d.tolist() == rd.tolist(), name
         else:
             assert ip.tolist() == k["expected_csr_indptr"] and len(ind) == 0 and len(d) == 0
+
+
+# ---------------------------------------------------------------------------------------
+# BiCGSTAB (sprs/src/sparse/linalg/bicgstab.rs), the iterative caller of SpMV
+def _kat_bicgstab_csr(fixtures, I=np.uint64):
+    k = fixtures["kat_bicgstab"]
+    ip, ind, d = mat_arrays(k["a"], I)  # CSC
+    return k, O.convert_mat_storage(4, 4, ip, ind, d)
+
+
+def test_bicgstab_reference_kat(fixtures):
+    """bicgstab.rs:356-390 test_bicgstab_f64: Ok within max_iter at tol 1e-60 and
+    |1 - b/b_recovered| < tol.  Reaching an exactly zero residual depends on every rounding
+    of the iteration, so this pins the restatement's operation order."""
+    k, csr = _kat_bicgstab_csr(fixtures)
+    ok, s = O.BiCGSTAB.solve(csr, k["x0"], k["b"], k["tol"], k["max_iter"])
+    assert ok, "the reference's test unwraps an Ok"
+    assert s.iteration_count() <= k["max_iter"]
+    assert s.soft_restart_threshold() == k["soft_restart_threshold"]
+    b_rec = np.zeros(4)
+    O.mul_acc_mat_vec_csr(*csr, s.x(), b_rec)
+    assert np.all(np.abs(1.0 - np.array(k["b"]) / b_rec) < k["tol"])
+    assert np.allclose(s.x(), k["x_exact"], rtol=1e-15, atol=0)
+    assert s.err() < k["tol"] and s.hard_restart_count() >= 1
+
+
+def test_bicgstab_new_and_restarts(fixtures):
+    """bicgstab.rs:120-146 (new), :177-196 (restarts): state after construction and the
+    restart counters."""
+    k, csr = _kat_bicgstab_csr(fixtures, np.uint32)
+    A = np.zeros((4, 4))
+    ip, ind, d = csr
+    for r in range(4):
+        A[r, ind[ip[r]:ip[r + 1]]] = d[ip[r]:ip[r + 1]]
+    x0, b = np.array([0.5, -1.0, 2.0, 0.25]), np.array(k["b"])
+    s = O.BiCGSTAB(csr, x0, b)
+    r0 = b - A @ x0
+    assert np.allclose(s.r(), r0, rtol=1e-15) and np.array_equal(s.r(), s.rhat())
+    assert np.array_equal(s.r(), s.p()) and np.array_equal(s.x(), x0)
+    assert np.array_equal(s.b(), b)
+    assert np.isclose(s.err(), np.linalg.norm(r0), rtol=1e-15)
+    assert s.rho() == s.err() * s.err()
+    assert (s.iteration_count(), s.soft_restart_count(), s.hard_restart_count()) == (0, 0, 0)
+    e1 = s.step()
+    assert e1 == s.err() and s.iteration_count() == 1
+    assert np.isclose(np.linalg.norm(s.r()), e1, rtol=1e-14)
+    soft = s.soft_restart_count()
+    s.soft_restart()
+    assert s.soft_restart_count() == soft + 1 and np.array_equal(s.rhat(), s.r())
+    assert np.array_equal(s.p(), s.r()) and s.rho() == s.err() * s.err()
+    s.hard_restart()  # counts as a hard restart only (bicgstab.rs:195)
+    assert s.hard_restart_count() == 1 and s.soft_restart_count() == soft + 1
+    assert np.allclose(s.r(), b - A @ s.x(), rtol=1e-13, atol=1e-15)
+    # a threshold of 0 never soft-restarts, a huge one always does
+    s0 = O.BiCGSTAB(csr, x0, b).with_restart_threshold(0.0)
+    s1 = O.BiCGSTAB(csr, x0, b).with_restart_threshold(1e300)
+    for _ in range(3):
+        s0.step()
+        s1.step()
+    assert s0.soft_restart_count() == 0 and s1.soft_restart_count() == 3
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_bicgstab_random_dominant_systems(seed):
+    """Diagonally dominant non-symmetric systems: converges to the direct solution, the
+    accepted error is the true residual, and an unreachable tolerance returns Err with the
+    state (bicgstab.rs:151-175)."""
+    rng = np.random.default_rng(1000 + seed)
+    n = 300
+    A = sp.random(n, n, density=0.03, random_state=rng, format="csr")
+    A = (A + sp.diags(np.asarray(abs(A).sum(axis=1)).ravel() + 1.0)).tocsr()
+    A.sort_indices()
+    csr = (A.indptr.astype(np.uint32), A.indices.astype(np.uint32), A.data.copy())
+    b = rng.standard_normal(n)
+    ok, s = O.BiCGSTAB.solve(csr, np.zeros(n), b, 1e-10, 200)
+    assert ok
+    x_direct = np.linalg.solve(A.toarray(), b)
+    assert np.allclose(s.x(), x_direct, rtol=1e-8, atol=1e-10)
+    assert np.isclose(np.linalg.norm(b - A @ s.x()), s.err(), rtol=1e-6, atol=1e-16)
+    ok, s = O.BiCGSTAB.solve(csr, np.zeros(n), b, 0.0, 4)
+    assert not ok and s.iteration_count() == 4
