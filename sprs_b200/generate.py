@@ -24,8 +24,16 @@ from .sparse import DeviceCsMat
 SENTINEL = -1  # UINT64_MAX read as int64
 
 
+def _device(ctx):
+    return torch.device("cuda", ctx.device)
+
+
 def _stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _sync():
+    torch.cuda.current_stream().synchronize()
 
 
 def _dptr(t):
@@ -73,7 +81,7 @@ def _keys_to_csr(ctx, keys, rows, cols, seed):
                                                _stream_ptr()))
         ctx.check(lib.sprs_b200_gen_normal_from_keys(ctx.h, seed ^ 0xDA7A, _dptr(keys), n,
                                                      _dptr(data), _stream_ptr()))
-    torch.cuda.current_stream().synchronize()
+    _sync()
     return DeviceCsr(ctx, rows, cols, indptr, indices, data)
 
 
@@ -98,7 +106,7 @@ def _collect(ctx, gen, n_candidates, chunk=1 << 27):
     """Generate candidates in chunks, drop rejected, return sorted unique keys."""
     parts = []
     first = 0
-    dev = torch.device("cuda", ctx.device)
+    dev = _device(ctx)
     while first < n_candidates:
         cnt = min(chunk, n_candidates - first)
         k = torch.empty(cnt, device=dev, dtype=torch.int64)
@@ -154,7 +162,7 @@ def make_matrix(ctx, gen, n, nnz_per_row, seed):
 
 
 def normal_vector(ctx, n, seed=0x5EED1002):
-    x = torch.empty(n, device=torch.device("cuda", ctx.device), dtype=torch.float64)
+    x = torch.empty(n, device=_device(ctx), dtype=torch.float64)
     ctx.check(ctx.lib.sprs_b200_gen_normal_from_keys(ctx.h, seed, None, n, _dptr(x),
                                                      _stream_ptr()))
     return x

@@ -10,8 +10,32 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+def emu_library():
+    """tests/emu: the library's kernels compiled for the CPU against a CUDA-subset emulator.
+    TEST INFRASTRUCTURE (kernel-logic pre-flight where no GPU is attached); never loaded by
+    the package itself."""
+    import subprocess
+    d = os.path.join(ROOT, "tests", "emu")
+    asan = os.environ.get("SPRS_B200_EMU_ASAN") == "1"  # needs LD_PRELOAD=libasan.so
+    subprocess.check_call(["make", "-C", d, "-s"] + (["asan"] if asan else []),
+                          stdout=subprocess.DEVNULL)
+    return os.path.join(d, "build/asan/libsprs_b200_emu.so" if asan else "libsprs_b200_emu.so")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    if os.environ.get("SPRS_B200_EMU") == "1":
+        # developer switch: run `-m gpu` tests against the emulator (those that only need the
+        # C ABI and numpy work; the ones that allocate through torch.cuda do not)
+        import sprs_b200
+        import torch
+        from sprs_b200 import generate
+        sprs_b200._lib.LIB_PATH = emu_library()
+        # "device" memory of the emulator is host memory: the bench/test plumbing that
+        # allocates through torch uses CPU tensors there
+        generate._device = lambda ctx: torch.device("cpu")
+        generate._stream_ptr = lambda: None
+        generate._sync = lambda: None
 
 
 @pytest.fixture(scope="session")

@@ -62,18 +62,18 @@ def _sampled_rows_vs_oracle(a, x_host, y_dev, rows, O):
         assert abs(float(y_dev[r]) - ref[0]) <= RTOL * bound + 1e-300, r
 
 
-def test_spmv_rmat_10m_full_size(sp, O):
-    """BASELINE config 5 at full size (10M x 10M R-MAT, ~1e9 nnz, generated on the device):
-    linearity A(ax+by) = a Ax + b Ay within rounding, y = A 0 = 0 exactly, and sampled rows
-    (the 40 heaviest, the first non-empty ones and 300 random ones) against the oracle."""
+def check_spmv_rmat(sp, O, n, per_row, nnz_range, n_heavy, n_rnd):
+    """R-MAT SpMV properties: linearity A(ax+by) = a Ax + b Ay within rounding, A 0 = 0
+    exactly, the structure check, and sampled rows (the heaviest, the first ones and random
+    ones) against the oracle."""
+    import ctypes
     import torch
     from sprs_b200 import generate as G
     ctx = sp.Context.default()
-    n = 10_000_000
-    a = G.rmat_csr(ctx, n, 100, seed=0x5EED0005)
-    assert 0.98e9 < a.nnz < 1.02e9
-    bad = __import__("ctypes").c_uint64(1)
-    ctx.check(ctx.lib.sprs_b200_csmat_check_structure(ctx.h, a.mirror.h, __import__("ctypes").byref(bad)))
+    a = G.rmat_csr(ctx, n, per_row, seed=0x5EED0005)
+    assert nnz_range[0] < a.nnz < nnz_range[1]
+    bad = ctypes.c_uint64(1)
+    ctx.check(ctx.lib.sprs_b200_csmat_check_structure(ctx.h, a.mirror.h, ctypes.byref(bad)))
     assert bad.value == 0
     x1, x2 = G.normal_vector(ctx, n, 1), G.normal_vector(ctx, n, 2)
     y1, y2, y3 = (torch.empty(n, device=x1.device, dtype=torch.float64) for _ in range(3))
@@ -83,31 +83,42 @@ def test_spmv_rmat_10m_full_size(sp, O):
     absrow = torch.empty_like(y1)
     absa = G.DeviceCsr(ctx, n, n, a.indptr, a.indices, a.data.abs())
     G.spmv(ctx, absa, (2.0 * x1).abs() + (3.0 * x2).abs(), absrow)
-    torch.cuda.synchronize()
+    G._sync()
     assert bool(((y3 - (2.0 * y1 - 3.0 * y2)).abs() <= 1e-12 * absrow + 1e-300).all())
     G.spmv(ctx, a, torch.zeros_like(x1), y3)
+    G._sync()
     assert bool((y3 == 0).all())
     lens = (a.indptr[1:] - a.indptr[:-1]).to(torch.int64)
-    heavy = torch.topk(lens, 40).indices.tolist()
-    rnd = torch.randint(0, n, (300,), generator=torch.Generator().manual_seed(1)).tolist()
+    heavy = torch.topk(lens, n_heavy).indices.tolist()
+    rnd = torch.randint(0, n, (n_rnd,), generator=torch.Generator().manual_seed(1)).tolist()
     _sampled_rows_vs_oracle(a, x1.cpu().numpy(), y1, heavy + list(range(20)) + rnd, O)
 
 
-def test_spmm_1m_k64_full_size(sp, O):
-    """BASELINE config 3 at full size (1M x 1M sprs-rand times 1M x 64, C-order): sampled
-    output rows are bit-identical to the oracle's csr_mulacc_dense_rowmaj."""
+def test_spmv_rmat_10m_full_size(sp, O):
+    """BASELINE config 5 at full size: 10M x 10M R-MAT, ~1e9 nnz, generated on the device."""
+    check_spmv_rmat(sp, O, 10_000_000, 100, (0.98e9, 1.02e9), 40, 300)
+
+
+def test_spmv_rmat_small(sp, O):
+    """The same properties on a 30k x 30k R-MAT (also what the CPU emulator pre-flight runs)."""
+    check_spmv_rmat(sp, O, 30_000, 20, (0.58e6, 0.62e6), 10, 60)
+
+
+def check_spmm_rand(sp, O, n, k, n_rows):
+    """sprs-rand A (32 nnz/row) times an n x k C-order B: sampled output rows are
+    bit-identical to the oracle's csr_mulacc_dense_rowmaj."""
     import torch
     from sprs_b200 import generate as G
     ctx = sp.Context.default()
-    n, k = 1_000_000, 64
     a = G.rand_csr(ctx, n, n, 32, seed=0x5EED0002)
+    assert a.nnz == 32 * n
     b = torch.randn(n, k, device=a.data.device, dtype=torch.float64,
                     generator=torch.Generator(device=a.data.device).manual_seed(3))
     c = torch.empty(n, k, device=b.device, dtype=torch.float64)
     G.spmm_rowmaj(ctx, a, b, c)
-    torch.cuda.synchronize()
+    G._sync()
     hip = a.indptr.cpu().numpy()
-    rows = torch.randint(0, n, (200,), generator=torch.Generator().manual_seed(2)).tolist()
+    rows = torch.randint(0, n, (n_rows,), generator=torch.Generator().manual_seed(2)).tolist()
     for r in rows:
         s, e = int(hip[r]), int(hip[r + 1])
         ci = a.indices[s:e].to(torch.int64)
@@ -117,6 +128,15 @@ def test_spmm_1m_k64_full_size(sp, O):
         O.csr_mulacc_dense_rowmaj(np.array([0, e - s], np.uint32), np.arange(e - s, dtype=np.uint32),
                                   cv, bsub, ref)
         assert np.array_equal(c[r].cpu().numpy(), ref[0]), r
+
+
+def test_spmm_1m_k64_full_size(sp, O):
+    """BASELINE config 3 at full size (1M x 1M sprs-rand times 1M x 64, C-order)."""
+    check_spmm_rand(sp, O, 1_000_000, 64, 200)
+
+
+def test_spmm_small(sp, O):
+    check_spmm_rand(sp, O, 4000, 64, 100)
 
 
 def test_matrix_market_to_device(sp):
