@@ -185,6 +185,17 @@ int sprs_b200_peer_push_dev(sprs_b200_ctx* ctx, const double* d_y_own, uint64_t 
 int sprs_b200_spmv_allgather_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
                                  const double* d_x, uint64_t row_offset, int n_targets,
                                  double* const* d_y_bufs, int accumulate, void* stream);
+/* Pipelined variant of the same contract: the SpMV writes only this rank's buffer
+ * (d_y_bufs[0]) and publishes its progress; a put kernel of `put_ctas` CTAs (0 = default)
+ * on a side stream of the ctx copies each finished chunk of rows into d_y_bufs[1..) while the
+ * SpMV is still running, and the carry fix-up that follows writes the rows cut by a tile
+ * boundary to all buffers.  `stream` is joined with the side stream before the call
+ * returns control to it, so the caller's barrier goes on `stream` as for the fused form.
+ * The mirror keeps the progress counters: not const.  Do not run under a tool that
+ * serialises kernels (ncu): the put kernel waits for the SpMV and traps after ~3 s.    */
+int sprs_b200_spmv_stream_push_dev(sprs_b200_ctx* ctx, sprs_b200_csmat* mat, const double* d_x,
+                                   uint64_t row_offset, int n_targets, double* const* d_y_bufs,
+                                   int accumulate, int put_ctas, void* stream);
 
 /* ---- sparse x sparse: smmp::mul_csr_csr (smmp.rs:196-237), two calls so the
  * CALLER allocates the output Vecs, like symbolic -> numeric (smmp.rs:81,151).

@@ -189,6 +189,9 @@ int sprs_b200_ctx_destroy(sprs_b200_ctx* ctx) {
     for (int i = 0; i < 4; ++i)
         if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SPRS_B200_OK;
@@ -322,6 +325,7 @@ int sprs_b200_csmat_free(sprs_b200_csmat* m) {
     }
     if (m->d_tile_row) cudaFree(m->d_tile_row);
     if (m->d_carry) cudaFree(m->d_carry);
+    if (m->d_progress) cudaFree(m->d_progress);
     if (m->csr_cache) sprs_b200_csmat_free(m->csr_cache);
     delete m;
     return SPRS_B200_OK;

@@ -22,6 +22,10 @@ struct sprs_b200_ctx {
     size_t h_stage_bytes = 0;
     void* d_scratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t d_scratch_bytes[4] = {0, 0, 0, 0};
+    // pipelined all-gather (spmv_launch_stream_push): high-priority side stream of the put
+    // kernel and the fork/join events that tie it to the caller's stream; created on first use
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 struct sprs_b200_csmat {
@@ -42,6 +46,12 @@ struct sprs_b200_csmat {
     // CSC mirrors only: the CSR conversion the product kernels run on, built on first use
     // by the host-buffer entry points and kept until the mirror is freed.
     mutable sprs_b200_csmat* csr_cache = nullptr;
+    // pipelined all-gather only: tiles finished per chunk of 2^chunk_shift tiles, summed over
+    // all calls (call number e expects e * tiles_in_chunk); allocated on first use
+    unsigned long long* d_progress = nullptr;
+    int chunk_shift = 0;
+    uint32_t n_chunks = 0;
+    uint64_t push_epoch = 0;
 };
 
 #define SPRS_FAIL(ctx, code, ...)                                  \
@@ -92,6 +102,10 @@ int spmv_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
                 int accumulate, cudaStream_t s);
 int spmv_launch_targets(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
                         const SpmvTargets& yt, int accumulate, cudaStream_t s);
+// Single-target SpMV into targets.p[0] whose finished row chunks are copied into
+// targets.p[1..n) by a concurrent put kernel while the SpMV still runs (spmv.cu)
+int spmv_launch_stream_push(sprs_b200_ctx* ctx, sprs_b200_csmat* m, const double* d_x,
+                            const SpmvTargets& yt, int accumulate, int put_ctas, cudaStream_t s);
 int spmm_rowmaj_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_b,
                        uint64_t ldb, uint64_t k, double* d_c, uint64_t ldc, int accumulate,
                        cudaStream_t s);

@@ -111,4 +111,18 @@ int sprs_b200_spmv_allgather_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
     return spmv_launch_targets(ctx, mat, d_x, yt, accumulate, (cudaStream_t)stream);
 }
 
+int sprs_b200_spmv_stream_push_dev(sprs_b200_ctx* ctx, sprs_b200_csmat* mat, const double* d_x,
+                                   uint64_t row_offset, int n_targets, double* const* d_y_bufs,
+                                   int accumulate, int put_ctas, void* stream) {
+    if (!ctx || !mat || !d_y_bufs) return SPRS_B200_ERR_ARGUMENT;
+    if (n_targets < 1 || n_targets > SPMV_MAX_TARGETS)
+        SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "n_targets must be 1..%d", SPMV_MAX_TARGETS);
+    SpmvTargets yt;
+    yt.n = n_targets;
+    for (int q = 0; q < SPMV_MAX_TARGETS; ++q)
+        yt.p[q] = q < n_targets ? d_y_bufs[q] + row_offset : nullptr;
+    return spmv_launch_stream_push(ctx, mat, d_x, yt, accumulate, put_ctas,
+                                   (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -293,13 +293,18 @@ __device__ __forceinline__ void reduce_rows_regs(const TileCtx& tc, const double
     if ((lane & 3) == 0 && row < nrows) emit_row<MULTI>(tc, (uint64_t)r0 + jbase + row, v);
 }
 
-template <typename P, int WT, int STAGES, int NWARPS, int MINB, bool MULTI>
+// SIGNAL (single-target launches only): the kernel also publishes its progress for the
+// pipelined all-gather (spmv_launch_stream_push below).  Tiles are grouped into chunks of
+// 2^chunk_shift consecutive tiles; a warp visits its tiles in increasing order, counts the
+// ones it finishes inside the current chunk and adds that count to progress[chunk] when it
+// moves on to another chunk (release: its y stores are fenced first).
+template <typename P, int WT, int STAGES, int NWARPS, int MINB, bool MULTI, bool SIGNAL>
 __global__ void __launch_bounds__(NWARPS * 32, MINB)
     spmv_warp_kernel(const P* __restrict__ indptr, const uint32_t* __restrict__ indices,
                      const double* __restrict__ data, const uint32_t* __restrict__ tile_row,
                      const double* __restrict__ x, SpmvTargets yt,
                      double* __restrict__ carry, uint64_t nnz, uint32_t rows, uint64_t n_tiles,
-                     int accumulate) {
+                     int accumulate, unsigned long long* progress, int chunk_shift) {
     constexpr int EPL = WT / 32;               // non-zeros per lane per tile
     constexpr bool DIRECT = STAGES == 0;       // no TMA ring: stream through registers
     constexpr int STAGE_BYTES = DIRECT ? WT * 8 : WT * 12;
@@ -338,6 +343,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
     }
     uint32_t phases = 0;
     int s = 0;
+    unsigned long long sig_count = 0;  // SIGNAL: tiles finished in the current chunk
     // Row range and the first 32 row boundaries of a tile are fetched ONE TILE AHEAD, so the
     // two dependent global loads (tile_row -> indptr) never stall the in-order issue in
     // front of the gathers.
@@ -461,6 +467,15 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
             fence_proxy_async();
             SPMV_ISSUE(tn, s);
         }
+        if (SIGNAL) {
+            ++sig_count;
+            if (tnext >= n_tiles || (tnext >> chunk_shift) != (t >> chunk_shift)) {
+                __threadfence();  // every lane: its y stores are visible device-wide ...
+                __syncwarp();     // ... before lane 0 publishes the count
+                if (lane == 0) atomicAdd(&progress[t >> chunk_shift], sig_count);
+                sig_count = 0;
+            }
+        }
         s = (s + 1 == NST) ? 0 : s + 1;
         r0 = r0n;
         r1 = r1n;
@@ -525,17 +540,25 @@ SpmvVariant spmv_variant() {
     return v;
 }
 
+struct SpmvSignal {  // progress counters of the pipelined all-gather; null = no signalling
+    unsigned long long* progress = nullptr;
+    int chunk_shift = 0;
+};
+
 template <typename P, int WT, int STAGES, int NWARPS, int CTAS>
 int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
-                   const SpmvTargets& yt, int accumulate, cudaStream_t s) {
+                   const SpmvTargets& yt, int accumulate, const SpmvSignal& sig,
+                   cudaStream_t s) {
     // CTAS resident CTAs per SM is also the kernel's __launch_bounds__ minBlocks: it sets the
     // register budget (ptxas otherwise picks ~40 registers and spills the gather buffers).
-    auto kern = yt.n > 1 ? spmv_warp_kernel<P, WT, STAGES, NWARPS, CTAS, true>
-                         : spmv_warp_kernel<P, WT, STAGES, NWARPS, CTAS, false>;
+    const int flavour = sig.progress ? 2 : (yt.n > 1 ? 1 : 0);
+    auto kern = flavour == 2   ? spmv_warp_kernel<P, WT, STAGES, NWARPS, CTAS, false, true>
+                : flavour == 1 ? spmv_warp_kernel<P, WT, STAGES, NWARPS, CTAS, true, false>
+                               : spmv_warp_kernel<P, WT, STAGES, NWARPS, CTAS, false, false>;
     const size_t smem = STAGES == 0 ? (size_t)NWARPS * WT * 8 : (size_t)NWARPS * STAGES * WT * 12;
     // function attributes are per device: remember them per (device, kernel flavour)
-    static bool configured_flags[64][2] = {};
-    bool& configured = configured_flags[ctx->device & 63][yt.n > 1 ? 1 : 0];
+    static bool configured_flags[64][3] = {};
+    bool& configured = configured_flags[ctx->device & 63][flavour];
     if (!configured) {
         SPRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)smem));
@@ -555,17 +578,19 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
     if (grid > need) grid = need;
     kern<<<(unsigned)grid, NWARPS * 32, smem, s>>>((const P*)m->d_indptr, m->d_indices, m->d_data,
                                                    m->d_tile_row, d_x, yt, m->d_carry, m->nnz,
-                                                   (uint32_t)m->rows, m->n_tiles, accumulate);
+                                                   (uint32_t)m->rows, m->n_tiles, accumulate,
+                                                   sig.progress, sig.chunk_shift);
     return SPRS_B200_OK;
 }
 
 template <typename P>
 int launch_dispatch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
-                    const SpmvTargets& yt, int accumulate, cudaStream_t s) {
+                    const SpmvTargets& yt, int accumulate, const SpmvSignal& sig,
+                    cudaStream_t s) {
     const SpmvVariant v = spmv_variant();
 #define SPMV_CASE(WT, ST, NW, CT)                                                         \
     if (v.wt == WT && v.stages == ST && v.nwarps == NW && v.ctas_per_sm == CT)            \
-        return launch_variant<P, WT, ST, NW, CT>(ctx, m, d_x, yt, accumulate, s);
+        return launch_variant<P, WT, ST, NW, CT>(ctx, m, d_x, yt, accumulate, sig, s);
     SPMV_CASE(256, 0, 8, 3)
     SPMV_CASE(256, 2, 8, 3)
     SPMV_CASE(256, 2, 8, 2)
@@ -613,10 +638,154 @@ int spmv_launch_targets(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const doub
     if (m->rows == 0) return SPRS_B200_OK;
     if (!m->d_tile_row) SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "csmat has no SpMV partition");
     if (m->indptr_bytes == 4)
-        SPRS_TRY(launch_dispatch<uint32_t>(ctx, m, d_x, yt, accumulate, s));
+        SPRS_TRY(launch_dispatch<uint32_t>(ctx, m, d_x, yt, accumulate, SpmvSignal(), s));
     else
-        SPRS_TRY(launch_dispatch<uint64_t>(ctx, m, d_x, yt, accumulate, s));
+        SPRS_TRY(launch_dispatch<uint64_t>(ctx, m, d_x, yt, accumulate, SpmvSignal(), s));
     ctx->launches += 1;
+    if (m->n_tiles > 1) {
+        const unsigned fgrid = (unsigned)((m->n_tiles - 1 + 255) / 256);
+        spmv_fixup_kernel<<<fgrid, 256, 0, s>>>(m->d_tile_row, m->d_carry, yt, m->n_tiles);
+        ctx->launches += 1;
+    }
+    SPRS_CUDA(ctx, cudaGetLastError());
+    return SPRS_B200_OK;
+}
+
+// ---- pipelined all-gather: SpMV + concurrent put kernel ------------------------------
+// The put kernel (a few CTAs on a high-priority side stream, resident BEFORE the SpMV
+// starts) follows the SpMV's progress counters chunk by chunk: once every tile of chunk c
+// has been reduced, rows [tile_row[c << shift], tile_row[(c+1) << shift]) of the local y are
+// final up to the carries and are copied into every peer buffer (coalesced 8-byte stores
+// over NVLink) while the SpMV works on the later chunks.  Rows cut by a tile boundary are
+// corrected afterwards by the fix-up kernel, which writes them to all targets.  Unlike the
+// fused variant (peer stores from the SpMV's own epilogue) the remote traffic never sits in
+// the LSU queues of the warps that gather x.
+namespace {
+
+constexpr int PUT_THREADS = 512;
+constexpr long long PUT_TIMEOUT_CYCLES = 6000000000ll;  // ~3 s: trap instead of hanging
+
+__global__ void __launch_bounds__(PUT_THREADS)
+    stream_put_kernel(const double* __restrict__ y_own, SpmvTargets peers,
+                      const uint32_t* __restrict__ tile_row,
+                      const unsigned long long* progress, unsigned long long epoch,
+                      uint64_t n_tiles, int chunk_shift, uint32_t n_chunks, uint32_t rows) {
+    const uint64_t tpc = 1ull << chunk_shift;
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        const uint64_t t0 = (uint64_t)c << chunk_shift;
+        const uint64_t t1 = t0 + tpc < n_tiles ? t0 + tpc : n_tiles;
+        if (threadIdx.x == 0) {
+            const unsigned long long want = epoch * (unsigned long long)(t1 - t0);
+            const volatile unsigned long long* p = progress + c;
+            const long long start = clock64();
+            unsigned backoff = 64;
+            while (*p < want) {
+                __nanosleep(backoff);
+                if (backoff < 2048) backoff <<= 1;
+                if (clock64() - start > PUT_TIMEOUT_CYCLES) __trap();  // the SpMV never ran
+            }
+            __threadfence();  // acquire: the rows counted above are visible
+        }
+        __syncthreads();
+        const uint64_t lo = c == 0 ? 0 : tile_row[t0];
+        const uint64_t hi = c + 1 == n_chunks ? rows : tile_row[t1];
+        const uint64_t stride = (uint64_t)gridDim.x * PUT_THREADS;
+        for (uint64_t i = lo + (uint64_t)blockIdx.x * PUT_THREADS + threadIdx.x; i < hi;
+             i += 4 * stride) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (i + u * stride < hi) ? __ldcg(y_own + i + u * stride) : 0.0;
+#pragma unroll
+            for (int q = 1; q < SPMV_MAX_TARGETS; ++q)
+                if (q < peers.n) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (i + u * stride < hi) peers.p[q][i + u * stride] = v[u];
+                }
+        }
+    }
+}
+
+int stream_push_prepare(sprs_b200_ctx* ctx, sprs_b200_csmat* m, cudaStream_t s) {
+    if (!ctx->side_stream) {
+        int lo = 0, hi = 0;  // numerically lower = higher priority
+        SPRS_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        SPRS_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
+        SPRS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        SPRS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    if (!m->d_progress) {
+        // about 12 chunks: the last chunk's push is what cannot overlap
+        int shift = 0;
+        while ((m->n_tiles >> shift) > 12) ++shift;
+        if (const char* e = getenv("SPRS_B200_PUSH_CHUNK_SHIFT")) shift = atoi(e);
+        if (shift < 0) shift = 0;
+        if (shift > 40) shift = 40;
+        m->chunk_shift = shift;
+        m->n_chunks = (uint32_t)((m->n_tiles + (1ull << shift) - 1) >> shift);
+        SPRS_CUDA(ctx, cudaMalloc((void**)&m->d_progress, (size_t)m->n_chunks * 8));
+        // on the caller's stream: ordered before the fork event both kernels wait behind
+        SPRS_CUDA(ctx, cudaMemsetAsync(m->d_progress, 0, (size_t)m->n_chunks * 8, s));
+        m->push_epoch = 0;
+    }
+    return SPRS_B200_OK;
+}
+
+}  // namespace
+
+int spmv_launch_stream_push(sprs_b200_ctx* ctx, sprs_b200_csmat* m, const double* d_x,
+                            const SpmvTargets& yt, int accumulate, int put_ctas,
+                            cudaStream_t s) {
+    if (m->storage != SPRS_B200_CSR)
+        SPRS_FAIL(ctx, SPRS_B200_ERR_STORAGE, "Storage mismatch: spmv needs a CSR mirror");
+    if (m->rows == 0) return SPRS_B200_OK;
+    if (!m->d_tile_row) SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "csmat has no SpMV partition");
+    if (yt.n <= 1) return spmv_launch_targets(ctx, m, d_x, yt, accumulate, s);
+    SPRS_TRY(stream_push_prepare(ctx, m, s));
+    m->push_epoch += 1;
+    SpmvTargets own;
+    own.n = 1;
+    own.p[0] = yt.p[0];
+    for (int q = 1; q < SPMV_MAX_TARGETS; ++q) own.p[q] = nullptr;
+    SpmvSignal sig;
+    sig.progress = m->d_progress;
+    sig.chunk_shift = m->chunk_shift;
+    if (put_ctas <= 0) put_ctas = 16;
+    if (const char* e = getenv("SPRS_B200_PUSH_CTAS")) put_ctas = atoi(e) > 0 ? atoi(e) : put_ctas;
+    if (put_ctas > ctx->sm_count) put_ctas = ctx->sm_count;
+    auto launch_put = [&]() -> int {
+        stream_put_kernel<<<(unsigned)put_ctas, PUT_THREADS, 0, ctx->side_stream>>>(
+            yt.p[0], yt, m->d_tile_row, m->d_progress, (unsigned long long)m->push_epoch,
+            m->n_tiles, m->chunk_shift, m->n_chunks, (uint32_t)m->rows);
+        ctx->launches += 1;
+        SPRS_CUDA(ctx, cudaGetLastError());
+        return SPRS_B200_OK;
+    };
+    auto launch_spmv = [&]() -> int {
+        if (m->indptr_bytes == 4)
+            SPRS_TRY(launch_dispatch<uint32_t>(ctx, m, d_x, own, accumulate, sig, s));
+        else
+            SPRS_TRY(launch_dispatch<uint64_t>(ctx, m, d_x, own, accumulate, sig, s));
+        ctx->launches += 1;
+        SPRS_CUDA(ctx, cudaGetLastError());
+        return SPRS_B200_OK;
+    };
+    // fork: the put kernel starts once the caller's stream has reached this point (y and the
+    // peers' buffers are free to be overwritten) -- and it must be RESIDENT before the SpMV
+    // fills every SM, hence put first.  (The CPU emulator of tests/emu runs kernels one after
+    // the other, so there the order is swapped: the counters are complete when the put runs.)
+    SPRS_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));
+    SPRS_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+#ifdef CUEMU
+    SPRS_TRY(launch_spmv());
+    SPRS_TRY(launch_put());
+#else
+    SPRS_TRY(launch_put());
+    SPRS_TRY(launch_spmv());
+#endif
+    // join: the carries are applied (to every target) after the last chunk has been pushed
+    SPRS_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
+    SPRS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
     if (m->n_tiles > 1) {
         const unsigned fgrid = (unsigned)((m->n_tiles - 1 + 255) / 256);
         spmv_fixup_kernel<<<fgrid, 256, 0, s>>>(m->d_tile_row, m->d_carry, yt, m->n_tiles);

@@ -257,6 +257,26 @@ class PushAllGatherSpMV(FusedAllGatherSpMV):
         return self.y
 
 
+class StreamAllGatherSpMV(FusedAllGatherSpMV):
+    """Row-partitioned y = A x with a pipelined all-gather: the SpMV writes only this rank's
+    slice and publishes its progress; a small put kernel on a side stream copies every
+    finished chunk of rows into the peer buffers WHILE the SpMV is still running
+    (sprs_b200_spmv_stream_push_dev), and the carry fix-up writes the rows cut by a tile
+    boundary to all buffers.  The exchange overlaps the compute like the fused form, without
+    its remote stores in the SpMV warps' own LSU queues.  Same peer buffers and barrier."""
+
+    put_ctas = 0  # 0 = library default
+
+    def compute(self, x):
+        import ctypes as C
+        import torch
+        ctx = self.ctx
+        ctx.check(ctx.lib.sprs_b200_spmv_stream_push_dev(
+            ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()), self.bounds[self.rank],
+            len(self._targets), self._targets, 0, int(self.put_ctas),
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
 class OverlappedAllGatherSpMV:
     """Row-partitioned y = A x with the all-gather of y overlapped with the compute.
 

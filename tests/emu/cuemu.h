@@ -58,6 +58,8 @@ static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) {
 typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801 };
 typedef struct cuemu_stream* cudaStream_t;
+typedef struct cuemu_event* cudaEvent_t;
+enum { cudaEventDisableTiming = 2 };
 enum cudaMemcpyKind {
     cudaMemcpyHostToHost = 0,
     cudaMemcpyHostToDevice = 1,
@@ -99,7 +101,14 @@ cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind 
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind,
                             cudaStream_t s = nullptr);
 cudaError_t cudaMemsetAsync(void* dst, int value, size_t bytes, cudaStream_t s = nullptr);
+cudaError_t cudaMemset(void* dst, int value, size_t bytes);
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags);
+cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned flags, int priority);
+cudaError_t cudaDeviceGetStreamPriorityRange(int* least, int* greatest);
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned flags);
+cudaError_t cudaEventDestroy(cudaEvent_t e);
+cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s);
+cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned flags);
 cudaError_t cudaStreamDestroy(cudaStream_t s);
 cudaError_t cudaStreamSynchronize(cudaStream_t s);
 cudaError_t cudaSetDevice(int d);
@@ -159,6 +168,12 @@ static inline void __syncthreads() { cuemu::block_barrier(); }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { cuemu::warp_barrier(mask); }
 static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
 static inline void __threadfence() {}
+static inline void __nanosleep(unsigned) { cuemu::yield(); }
+static inline void __trap() {
+    fprintf(stderr, "cuemu: __trap()\n");
+    abort();
+}
+long long clock64();
 static inline void __threadfence_block() {}
 
 namespace cuemu {

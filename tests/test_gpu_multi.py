@@ -1,7 +1,7 @@
 """2-GPU test of the row-partitioned SpMV (needs >= 2 GPUs; skipped on a 1-GPU box): all
 exchange modes -- NCCL all_gather, the all-gather fused into the kernel through CUDA IPC peer
-stores, and the chunked compute / peer-copy overlap -- must reproduce the single-GPU result
-on every rank."""
+stores, the chunked compute / peer-copy overlap, the own put kernel and the pipelined put
+(stream) -- must reproduce the single-GPU result on every rank."""
 import os
 import socket
 import sys
@@ -20,7 +20,7 @@ def _worker(rank, world, port, q):
     import sprs_b200 as sp
     from sprs_b200 import generate as G
     from sprs_b200.dist import (FusedAllGatherSpMV, OverlappedAllGatherSpMV, PushAllGatherSpMV,
-                                RowPartitionedSpMV, nnz_balanced_bounds)
+                                RowPartitionedSpMV, StreamAllGatherSpMV, nnz_balanced_bounds)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -71,6 +71,16 @@ def _worker(rank, world, port, q):
             oks.append(bool(((g4 - ref).abs() <= 1e-9 * scale).all()))
             dist.barrier()
         pop.close()
+        sop = StreamAllGatherSpMV(ctx, a.mirror, bounds, rank, world, n, dist, dev)
+        for _ in range(3):
+            sop.y.fill_(float("nan"))
+            torch.cuda.synchronize()
+            dist.barrier()
+            g5 = sop.step(x)
+            torch.cuda.synchronize()
+            oks.append(bool(((g5 - ref).abs() <= 1e-9 * scale).all()))
+            dist.barrier()
+        sop.close()
         q.put((rank, ok_nccl, all(oks)))
     finally:
         dist.destroy_process_group()
