@@ -4,13 +4,21 @@ the "peer" buffers are ordinary device allocations, which exercises the whole me
 (progress counters, epochs, chunk row ranges, put/SpMV concurrency, carry fix-up to all
 targets) on one GPU.  Written after the round's last GPU session (sorts last on purpose)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
 
 from conftest import rand_csr
 
-pytestmark = pytest.mark.gpu
+# The put kernel spins on counters the SpMV fills: if the two kernels were ever serialised it
+# traps after ~3 s and the CUDA context is lost.  Until the mechanism has had its first run
+# on hardware these tests are opt-in there (they always run on the CPU emulator pre-flight).
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("SPRS_B200_TEST_STREAM_PUSH") != "1" and
+                                 os.environ.get("SPRS_B200_EMU") != "1",
+                                 reason="opt-in until first hardware run: "
+                                        "SPRS_B200_TEST_STREAM_PUSH=1")]
 
 
 @pytest.fixture(scope="module")

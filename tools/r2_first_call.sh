@@ -1,0 +1,27 @@
+#!/bin/bash
+# First GPU call of round 2 (one box, ~12-15 GPU-minutes): everything written after round 1's
+# GPU budget ran out gets its first hardware run, then the numbers the round-2 plan needs.
+#   gpurun --timeout 1500 -- 'bash tools/r2_first_call.sh'
+# Results land in gpurun_out/r2_first/.
+set -u
+out=gpurun_out/r2_first
+mkdir -p $out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $out/gpu.txt 2>&1
+# 1. the whole GPU suite, then the opt-in pipelined-push tests in their own process (a trap
+#    there loses the CUDA context)
+timeout 900 python -m pytest tests -m gpu -q -x > $out/pytest_gpu.txt 2>&1; echo "pytest_gpu exit $?" >> $out/summary.txt
+SPRS_B200_TEST_STREAM_PUSH=1 timeout 300 python -m pytest tests/test_gpu_zzz_stream_push.py -m gpu -q > $out/pytest_stream_push.txt 2>&1; echo "stream_push exit $?" >> $out/summary.txt
+# 2. headline bench (N=1) and the secondary workloads (SpGEMM with the panel kernel: first timing)
+timeout 600 python bench.py --steps 20 --warmup 5 > $out/bench_n1.json 2> $out/bench_n1.err; echo "bench exit $?" >> $out/summary.txt
+timeout 600 python bench.py --workload spgemm_rmat_500k --steps 3 --warmup 1 > $out/bench_spgemm.json 2> $out/bench_spgemm.err; echo "spgemm exit $?" >> $out/summary.txt
+timeout 300 python bench.py --workload spmm_rand_1m_k64 --steps 10 --warmup 3 > $out/bench_spmm.json 2> $out/bench_spmm.err; echo "spmm exit $?" >> $out/summary.txt
+# 3. BiCGSTAB: cost of a step next to its two SpMVs (config 5 matrix)
+timeout 600 python tools/time_bicgstab.py > $out/bicgstab.json 2> $out/bicgstab.err; echo "bicgstab exit $?" >> $out/summary.txt
+# 4. per-kernel launch list of the SpGEMM (where does the time go now?)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+  --log-file $out/launches_spgemm.csv python bench.py --workload spgemm_rmat_500k --steps 1 --warmup 1 --no-cpu-baseline \
+  > $out/ncu_spgemm.log 2>&1; echo "ncu spgemm exit $?" >> $out/summary.txt
+python tools/agg_launches.py $out/launches_spgemm.csv > $out/launches_spgemm_agg.txt 2>&1
+cat $out/summary.txt
+tail -3 $out/pytest_gpu.txt $out/pytest_stream_push.txt
+tail -c 600 $out/bench_n1.json; echo; tail -c 400 $out/bench_spgemm.json; echo; cat $out/bicgstab.json
