@@ -62,6 +62,7 @@ unsigned long long g_progress = 0;
 std::vector<unsigned char> g_smem;
 void* g_smem_aligned = nullptr;
 cudaError_t g_last_error = cudaSuccess;
+unsigned long long g_rng = 0x9E3779B97F4A7C15ull;
 
 void release_block_barrier_if_complete() {
     if (g_live > 0 && g_barrier_arrived == g_live) {
@@ -146,10 +147,33 @@ void run_block(unsigned nthreads) {
         g_warps[f.warp].alive |= 1u << f.lane;
         prepare_fiber(f);
     }
+    // Order in which the runnable threads get the CPU in each round.  Any order is a legal
+    // CUDA schedule, so results must not depend on it: CUEMU_SCHEDULE=reverse | random[:seed]
+    // (default: forward) lets the test-suite look for missing barriers under other schedules.
+    static const int mode = [] {
+        const char* e = getenv("CUEMU_SCHEDULE");
+        if (!e || !*e || !strncmp(e, "forward", 7)) return 0;
+        if (!strncmp(e, "reverse", 7)) return 1;
+        if (!strncmp(e, "random", 6)) {
+            if (e[6] == ':') g_rng = strtoull(e + 7, nullptr, 10) * 2654435761ull + 1;
+            return 2;
+        }
+        fprintf(stderr, "cuemu: unknown CUEMU_SCHEDULE '%s'\n", e);
+        abort();
+    }();
+    static std::vector<unsigned> order;
+    order.resize(nthreads);
+    for (unsigned t = 0; t < nthreads; ++t) order[t] = mode == 1 ? nthreads - 1 - t : t;
     unsigned idle_rounds = 0;
     while (g_live) {
         const unsigned long long before = g_progress;
-        for (unsigned t = 0; t < nthreads; ++t) {
+        if (mode == 2)
+            for (unsigned t = nthreads; t > 1; --t) {  // Fisher-Yates with a 64-bit LCG
+                g_rng = g_rng * 6364136223846793005ull + 1442695040888963407ull;
+                std::swap(order[t - 1], order[(g_rng >> 33) % t]);
+            }
+        for (unsigned k = 0; k < nthreads; ++k) {
+            const unsigned t = order[k];
             Fiber& f = g_fibers[t];
             if (f.done) continue;
             g_cur = &f;

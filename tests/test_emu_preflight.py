@@ -34,9 +34,11 @@ def _link_and_run(emu_lib, src, name):
     return r.stdout
 
 
-def test_emu_cpp_reference_kats(emu):
+def test_emu_cpp_reference_kats(emu, monkeypatch):
     """tests/cpp/test_reference_kats.cpp (the reference's product tests through the C++ host
-    mirror) linked against the emulated library."""
+    mirror) linked against the emulated library; forward and reverse thread schedules."""
+    _link_and_run(emu, "test_reference_kats.cpp", "kats_emu")
+    monkeypatch.setenv("CUEMU_SCHEDULE", "reverse")
     _link_and_run(emu, "test_reference_kats.cpp", "kats_emu")
 
 
@@ -47,10 +49,13 @@ def test_emu_cpp_bicgstab(emu):
     assert "Iteration count 45" in out and "Hard restart count 3" in out
 
 
-def test_emu_gpu_suite(emu):
+@pytest.mark.parametrize("schedule", ["forward", "random:7"])
+def test_emu_gpu_suite(emu, schedule):
     """Every `-m gpu` test that needs only the C ABI (all but the full-size ones, the
-    multi-GPU ones and the natively linked C++ drivers) passes on the emulator."""
-    env = dict(os.environ, SPRS_B200_EMU="1")
+    multi-GPU ones and the natively linked C++ drivers) passes on the emulator -- under the
+    default thread schedule and under a shuffled one (any order is a legal CUDA schedule, so a
+    result that depends on it means a missing barrier)."""
+    env = dict(os.environ, SPRS_B200_EMU="1", CUEMU_SCHEDULE=schedule)
     r = subprocess.run(
         [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "-q", "-x",
          "-p", "no:cacheprovider", "-k", "not full_size and not test_cpp",
