@@ -15,6 +15,8 @@
 // Compulsory bytes: 12*nnz + 8*k*(cols + rows); the B-row gathers (8*k per nnz) are
 // served by L2 / HBM depending on B's size (DESIGN.md "SpMM").
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -65,6 +67,55 @@ __global__ void __launch_bounds__(SPMM_NT)
     }
 }
 
+// L2-blocked variant (opt-in, SPRS_B200_SPMM_PANEL=4|8|16|32; default off until it has been
+// measured): B is consumed in column panels of G columns so that the panel (B.rows x G
+// doubles, 64 MB for 1M rows at G = 8) stays resident in the 126 MB L2 while A is re-streamed
+// once per panel -- at k = 64 the one-pass kernel above gathers a 512-byte B row per
+// non-zero and 89 % of those gathers miss L2 (14.35 GB of DRAM traffic for 1.4 GB of
+// compulsory bytes).  A group of G lanes owns one row: lane g keeps the
+// accumulator of column c0 + g, the row's (index, value) pairs are loaded G at a time and
+// broadcast inside the group.  Same sequential unfused sums: bit-identical results.
+template <typename P, int G>
+__global__ void __launch_bounds__(SPMM_NT)
+    spmm_panel_kernel(const P* __restrict__ indptr, const uint32_t* __restrict__ indices,
+                      const double* __restrict__ data, const double* __restrict__ B,
+                      uint64_t ldb, uint32_t c0, uint32_t k, double* __restrict__ C,
+                      uint64_t ldc, uint32_t rows, int accumulate) {
+    constexpr int GROUPS = 32 / G;
+    const int lane = threadIdx.x & 31, gl = lane % G, gid = lane / G;
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (gid * G);
+    const uint64_t group0 = ((blockIdx.x * (uint64_t)SPMM_NT + threadIdx.x) >> 5) * GROUPS + gid;
+    const uint64_t ngroups = (((uint64_t)gridDim.x * SPMM_NT) >> 5) * GROUPS;
+    const uint32_t c = c0 + gl;
+    const bool live = c < k;
+    for (uint64_t row = group0; row < rows; row += ngroups) {
+        const uint64_t s = (uint64_t)indptr[row], e = (uint64_t)indptr[row + 1];
+        double* crow = C + row * ldc;
+        double acc = (accumulate && live) ? crow[c] : 0.0;
+        for (uint64_t kk = s; kk < e; kk += G) {
+            const bool in = kk + gl < e;
+            const uint32_t my_idx = in ? indices[kk + gl] : 0u;
+            const double my_val = in ? data[kk + gl] : 0.0;
+            const int n = (e - kk) < (uint64_t)G ? (int)(e - kk) : G;
+            for (int j = 0; j < n; ++j) {
+                const uint32_t col = __shfl_sync(gmask, my_idx, j, G);
+                const double v = __shfl_sync(gmask, my_val, j, G);
+                if (live) acc = __dadd_rn(acc, __dmul_rn(v, __ldg(B + (uint64_t)col * ldb + c)));
+            }
+        }
+        if (live) crow[c] = acc;
+    }
+}
+
+int spmm_panel_width() {
+    static const int w = [] {
+        const char* e = getenv("SPRS_B200_SPMM_PANEL");
+        const int v = e ? atoi(e) : 0;
+        return (v == 4 || v == 8 || v == 16 || v == 32) ? v : 0;
+    }();
+    return w;
+}
+
 }  // namespace
 
 int spmm_rowmaj_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_b,
@@ -74,6 +125,33 @@ int spmm_rowmaj_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const doubl
         SPRS_FAIL(ctx, SPRS_B200_ERR_STORAGE, "Storage mismatch: spmm needs a CSR mirror");
     if (m->rows == 0 || k == 0) return SPRS_B200_OK;
     if (k > 0xffffffffull) SPRS_FAIL(ctx, SPRS_B200_ERR_UNSUPPORTED, "k too large");
+    if (const int pw = spmm_panel_width()) {
+        const uint64_t groups_per_block = (uint64_t)SPMM_NT / pw;
+        uint64_t pblocks = (m->rows + groups_per_block - 1) / groups_per_block;
+        const uint64_t pcap = (uint64_t)ctx->sm_count * 64;
+        if (pblocks > pcap) pblocks = pcap;
+        for (uint64_t c0 = 0; c0 < k; c0 += pw) {
+#define SPMM_PANEL(P, G)                                                                        \
+    spmm_panel_kernel<P, G><<<(unsigned)pblocks, SPMM_NT, 0, s>>>(                              \
+        (const P*)m->d_indptr, m->d_indices, m->d_data, d_b, ldb, (uint32_t)c0, (uint32_t)k,    \
+        d_c, ldc, (uint32_t)m->rows, accumulate)
+            if (m->indptr_bytes == 4) {
+                if (pw == 4) SPMM_PANEL(uint32_t, 4);
+                else if (pw == 8) SPMM_PANEL(uint32_t, 8);
+                else if (pw == 16) SPMM_PANEL(uint32_t, 16);
+                else SPMM_PANEL(uint32_t, 32);
+            } else {
+                if (pw == 4) SPMM_PANEL(uint64_t, 4);
+                else if (pw == 8) SPMM_PANEL(uint64_t, 8);
+                else if (pw == 16) SPMM_PANEL(uint64_t, 16);
+                else SPMM_PANEL(uint64_t, 32);
+            }
+#undef SPMM_PANEL
+            ctx->launches += 1;
+        }
+        SPRS_CUDA(ctx, cudaGetLastError());
+        return SPRS_B200_OK;
+    }
     const uint64_t warps_needed = m->rows;
     uint64_t blocks = (warps_needed * 32 + SPMM_NT - 1) / SPMM_NT;
     const uint64_t cap = (uint64_t)ctx->sm_count * 64;

@@ -153,3 +153,23 @@ def test_matrix_market_to_device(sp):
     assert csr.nnz() == 8 and csr.indptr.tolist() == [0, 2, 3, 4, 7, 8]
     assert csr.indices.tolist() == [0, 3, 1, 2, 1, 3, 4, 4]
     assert csr.data.tolist() == [1., 6., 10.5, 1.5e-2, 2.505e2, -2.8e2, 3.332e1, 1.2e1]
+
+
+@pytest.mark.parametrize("panel", [8, 32])
+def test_spmm_l2_blocked_variant(panel):
+    """The opt-in column-panel SpMM (SPRS_B200_SPMM_PANEL, read once per process) gives the
+    same bits as the oracle: the dense-product tests again in a child process with it on."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SPRS_B200_SPMM_PANEL=str(panel))
+    r = subprocess.run(
+        [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+         os.path.join(root, "tests", "test_gpu_spmv_spmm.py"),
+         os.path.join(root, "tests", "test_gpu_zz_late.py"),
+         "-k", "dense or wide_operator or spmm_small"],
+        capture_output=True, text=True, timeout=900, env=env, cwd=root)
+    tail = "\n".join(r.stdout.splitlines()[-15:])
+    assert r.returncode == 0, tail + r.stderr[-1500:]
+    assert " passed" in tail
