@@ -58,9 +58,19 @@ def test_emu_gpu_suite(emu, schedule):
     env = dict(os.environ, SPRS_B200_EMU="1", CUEMU_SCHEDULE=schedule)
     r = subprocess.run(
         [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "-q", "-x",
-         "-p", "no:cacheprovider", "-k", "not full_size and not test_cpp",
+         "-p", "no:cacheprovider", "-k", "not full_size and not test_cpp and not l2_blocked",
          "--deselect", os.path.join(ROOT, "tests", "test_gpu_multi.py")],
         capture_output=True, text=True, timeout=1500, env=env, cwd=ROOT)
     tail = "\n".join(r.stdout.splitlines()[-25:])
     assert r.returncode == 0, tail + r.stderr[-2000:]
     assert " passed" in tail and "failed" not in tail
+
+
+def test_emu_spmm_panel_variant(emu):
+    """The opt-in L2-blocked SpMM kernel (its own child processes with SPRS_B200_SPMM_PANEL)."""
+    env = dict(os.environ, SPRS_B200_EMU="1")
+    r = subprocess.run(
+        [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_zz_late.py"), "-m", "gpu",
+         "-q", "-x", "-p", "no:cacheprovider", "-k", "l2_blocked"],
+        capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
