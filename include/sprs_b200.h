@@ -187,9 +187,10 @@ int sprs_b200_spmv_allgather_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
                                  double* const* d_y_bufs, int accumulate, void* stream);
 /* Pipelined variant of the same contract: the SpMV writes only this rank's buffer
  * (d_y_bufs[0]) and publishes its progress; a put kernel of `put_ctas` CTAs (0 = default)
- * on a side stream of the ctx copies each finished chunk of rows into d_y_bufs[1..) while the
- * SpMV is still running, and the carry fix-up that follows writes the rows cut by a tile
- * boundary to all buffers.  `stream` is joined with the side stream before the call
+ * on a side stream of the ctx follows it chunk by chunk, applies the carries of the rows
+ * that end in the chunk (rows cut by a tile boundary) and copies the now final rows into
+ * d_y_bufs[1..) while the SpMV is still running.  The other buffers may be peer GPUs' memory
+ * or mapped pinned host memory.  `stream` is joined with the side stream before the call
  * returns control to it, so the caller's barrier goes on `stream` as for the fused form.
  * The mirror keeps the progress counters: not const.  Do not run under a tool that
  * serialises kernels (ncu): the put kernel waits for the SpMV and traps after ~3 s.    */

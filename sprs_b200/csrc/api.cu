@@ -8,6 +8,8 @@
 #include <mutex>
 #include <vector>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -540,11 +542,42 @@ static int spmv_host(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, int want_st
             st = SPRS_B200_ERR_CUDA;
             break;
         }
-        if ((st = spmv_launch(ctx, csr, (const double*)d_x, (double*)d_y, accumulate, s)) !=
-            SPRS_B200_OK)
-            break;
-        if (y_len) e = cudaMemcpyAsync(y, d_y, y_len * sizeof(double), cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        // Opt-in (SPRS_B200_E2E_PIPELINE=1, until it has been measured): when the caller's y
+        // is pinned host memory the device can address, the result leaves for the host WHILE
+        // the SpMV runs -- the pipelined put of spmv.cu with the host buffer as the second
+        // target -- instead of one D2H copy after it.
+        double* y_mapped = nullptr;
+        static const bool pipeline = [] {
+            const char* v = getenv("SPRS_B200_E2E_PIPELINE");
+            return v && atoi(v) != 0;
+        }();
+        if (pipeline && y_len >= 4096) {
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, y) == cudaSuccess &&
+                attr.type == cudaMemoryTypeHost && attr.devicePointer)
+                y_mapped = (double*)attr.devicePointer;
+            else
+                cudaGetLastError();  // pageable memory: not an error, just the plain path
+        }
+        if (y_mapped) {
+            SpmvTargets yt;
+            yt.n = 2;
+            for (int q = 0; q < SPMV_MAX_TARGETS; ++q) yt.p[q] = nullptr;
+            yt.p[0] = (double*)d_y;
+            yt.p[1] = y_mapped;
+            if ((st = spmv_launch_stream_push(ctx, const_cast<sprs_b200_csmat*>(csr),
+                                              (const double*)d_x, yt, accumulate, 24, s)) !=
+                SPRS_B200_OK)
+                break;
+            e = cudaStreamSynchronize(s);  // joined with the put kernel: y is complete
+        } else {
+            if ((st = spmv_launch(ctx, csr, (const double*)d_x, (double*)d_y, accumulate, s)) !=
+                SPRS_B200_OK)
+                break;
+            if (y_len)
+                e = cudaMemcpyAsync(y, d_y, y_len * sizeof(double), cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        }
         if (e != cudaSuccess) {
             sprs_b200_set_error(ctx, cudaGetErrorString(e));
             st = SPRS_B200_ERR_CUDA;

@@ -653,23 +653,54 @@ int spmv_launch_targets(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const doub
 
 // ---- pipelined all-gather: SpMV + concurrent put kernel ------------------------------
 // The put kernel (a few CTAs on a high-priority side stream, resident BEFORE the SpMV
-// starts) follows the SpMV's progress counters chunk by chunk: once every tile of chunk c
-// has been reduced, rows [tile_row[c << shift], tile_row[(c+1) << shift]) of the local y are
-// final up to the carries and are copied into every peer buffer (coalesced 8-byte stores
-// over NVLink) while the SpMV works on the later chunks.  Rows cut by a tile boundary are
-// corrected afterwards by the fix-up kernel, which writes them to all targets.  Unlike the
-// fused variant (peer stores from the SpMV's own epilogue) the remote traffic never sits in
-// the LSU queues of the warps that gather x.
+// starts) follows the SpMV's progress counters chunk by chunk.  Once every tile of chunks
+// 0..c has been reduced, each put CTA takes a contiguous share [u_lo, u_hi) of the chunk's
+// tiles, applies the carries of the rows that END in those tiles (so rows
+// [tile_row[u_lo], tile_row[u_hi]) of the local y are final), and copies those rows into
+// every other target buffer -- peer GPUs' y over NVLink, or a pinned host buffer over PCIe --
+// with coalesced 8-byte stores, while the SpMV works on the later chunks.  Unlike the fused
+// variant (peer stores from the SpMV's own epilogue) the remote traffic never sits in the LSU
+// queues of the warps that gather x, and nothing is left to do after the SpMV but the last
+// chunk.
 namespace {
 
 constexpr int PUT_THREADS = 512;
 constexpr long long PUT_TIMEOUT_CYCLES = 6000000000ll;  // ~3 s: trap instead of hanging
 
+// Carries of the row that ends in tile u (u >= 1): the run of tiles [t, u-1] whose carry
+// row is tile_row[u] left partial sums in carry[]; they are added in tile order, exactly
+// like spmv_fixup_kernel does from the head of the run (same bits).
+__device__ __forceinline__ void apply_carries_ending_in(const uint32_t* __restrict__ tile_row,
+                                                        const double* carry, double* y,
+                                                        uint64_t u) {
+    const uint32_t row = tile_row[u];
+    if (tile_row[u + 1] == row) return;  // the row continues past tile u: not final yet
+    // head of the run: first index f in [1, u] with tile_row[f] >= row, t = f - 1
+    uint64_t hi = u, lo = 1;
+    for (uint64_t step = 1; step < hi; step <<= 1) {  // gallop down: most runs are 1 tile
+        if (tile_row[hi - step] < row) {
+            lo = hi - step + 1;
+            break;
+        }
+        hi -= step;
+    }
+    while (lo < hi) {
+        const uint64_t mid = lo + (hi - lo) / 2;
+        if (tile_row[mid] >= row)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    double sum = __ldcg(carry + lo - 1);
+    for (uint64_t v = lo; v < u; ++v) sum = __dadd_rn(sum, __ldcg(carry + v));
+    y[row] = __dadd_rn(__ldcg(y + row), sum);
+}
+
 __global__ void __launch_bounds__(PUT_THREADS)
-    stream_put_kernel(const double* __restrict__ y_own, SpmvTargets peers,
-                      const uint32_t* __restrict__ tile_row,
-                      const unsigned long long* progress, unsigned long long epoch,
-                      uint64_t n_tiles, int chunk_shift, uint32_t n_chunks, uint32_t rows) {
+    stream_put_kernel(double* y_own, SpmvTargets targets, const uint32_t* __restrict__ tile_row,
+                      const double* carry, const unsigned long long* progress,
+                      unsigned long long epoch, uint64_t n_tiles, int chunk_shift,
+                      uint32_t n_chunks, uint32_t rows) {
     const uint64_t tpc = 1ull << chunk_shift;
     for (uint32_t c = 0; c < n_chunks; ++c) {
         const uint64_t t0 = (uint64_t)c << chunk_shift;
@@ -684,26 +715,37 @@ __global__ void __launch_bounds__(PUT_THREADS)
                 if (backoff < 2048) backoff <<= 1;
                 if (clock64() - start > PUT_TIMEOUT_CYCLES) __trap();  // the SpMV never ran
             }
-            __threadfence();  // acquire: the rows counted above are visible
+            __threadfence();  // acquire: the rows and carries counted above are visible
         }
         __syncthreads();
-        const uint64_t lo = c == 0 ? 0 : tile_row[t0];
-        const uint64_t hi = c + 1 == n_chunks ? rows : tile_row[t1];
-        const uint64_t stride = (uint64_t)gridDim.x * PUT_THREADS;
-        for (uint64_t i = lo + (uint64_t)blockIdx.x * PUT_THREADS + threadIdx.x; i < hi;
-             i += 4 * stride) {
-            double v[4];
+        // this CTA's share of the chunk's tiles (chunks are visited in order, so every tile
+        // before u_hi is complete)
+        const uint64_t span = t1 - t0;
+        const uint64_t u_lo = t0 + span * blockIdx.x / gridDim.x;
+        const uint64_t u_hi = t0 + span * (blockIdx.x + 1) / gridDim.x;
+        for (uint64_t u = u_lo + threadIdx.x; u < u_hi; u += PUT_THREADS)
+            if (u >= 1) apply_carries_ending_in(tile_row, carry, y_own, u);
+        __syncthreads();
+        if (targets.n > 1) {
+            const uint64_t lo = tile_row[u_lo];  // tile_row[0] == 0, tile_row[n_tiles] == rows
+            const uint64_t hi = tile_row[u_hi];
+            for (uint64_t i = lo + threadIdx.x; i < hi; i += 4 * PUT_THREADS) {
+                double v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = (i + u * stride < hi) ? __ldcg(y_own + i + u * stride) : 0.0;
+                for (int w = 0; w < 4; ++w)
+                    v[w] = (i + w * PUT_THREADS < hi) ? __ldcg(y_own + i + w * PUT_THREADS) : 0.0;
 #pragma unroll
-            for (int q = 1; q < SPMV_MAX_TARGETS; ++q)
-                if (q < peers.n) {
+                for (int q = 1; q < SPMV_MAX_TARGETS; ++q)
+                    if (q < targets.n) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (i + u * stride < hi) peers.p[q][i + u * stride] = v[u];
-                }
+                        for (int w = 0; w < 4; ++w)
+                            if (i + w * PUT_THREADS < hi) targets.p[q][i + w * PUT_THREADS] = v[w];
+                    }
+            }
         }
+        __syncthreads();
     }
+    (void)rows;
 }
 
 int stream_push_prepare(sprs_b200_ctx* ctx, sprs_b200_csmat* m, cudaStream_t s) {
@@ -740,7 +782,8 @@ int spmv_launch_stream_push(sprs_b200_ctx* ctx, sprs_b200_csmat* m, const double
         SPRS_FAIL(ctx, SPRS_B200_ERR_STORAGE, "Storage mismatch: spmv needs a CSR mirror");
     if (m->rows == 0) return SPRS_B200_OK;
     if (!m->d_tile_row) SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "csmat has no SpMV partition");
-    if (yt.n <= 1) return spmv_launch_targets(ctx, m, d_x, yt, accumulate, s);
+    if (yt.n <= 1 && !getenv("SPRS_B200_PUSH_ALWAYS"))  // nothing to push to: the plain path
+        return spmv_launch_targets(ctx, m, d_x, yt, accumulate, s);
     SPRS_TRY(stream_push_prepare(ctx, m, s));
     m->push_epoch += 1;
     SpmvTargets own;
@@ -755,8 +798,9 @@ int spmv_launch_stream_push(sprs_b200_ctx* ctx, sprs_b200_csmat* m, const double
     if (put_ctas > ctx->sm_count) put_ctas = ctx->sm_count;
     auto launch_put = [&]() -> int {
         stream_put_kernel<<<(unsigned)put_ctas, PUT_THREADS, 0, ctx->side_stream>>>(
-            yt.p[0], yt, m->d_tile_row, m->d_progress, (unsigned long long)m->push_epoch,
-            m->n_tiles, m->chunk_shift, m->n_chunks, (uint32_t)m->rows);
+            yt.p[0], yt, m->d_tile_row, m->d_carry, m->d_progress,
+            (unsigned long long)m->push_epoch, m->n_tiles, m->chunk_shift, m->n_chunks,
+            (uint32_t)m->rows);
         ctx->launches += 1;
         SPRS_CUDA(ctx, cudaGetLastError());
         return SPRS_B200_OK;
@@ -783,15 +827,9 @@ int spmv_launch_stream_push(sprs_b200_ctx* ctx, sprs_b200_csmat* m, const double
     SPRS_TRY(launch_put());
     SPRS_TRY(launch_spmv());
 #endif
-    // join: the carries are applied (to every target) after the last chunk has been pushed
+    // join: the caller's stream continues when the last chunk has been fixed up and pushed
     SPRS_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
     SPRS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
-    if (m->n_tiles > 1) {
-        const unsigned fgrid = (unsigned)((m->n_tiles - 1 + 255) / 256);
-        spmv_fixup_kernel<<<fgrid, 256, 0, s>>>(m->d_tile_row, m->d_carry, yt, m->n_tiles);
-        ctx->launches += 1;
-    }
-    SPRS_CUDA(ctx, cudaGetLastError());
     return SPRS_B200_OK;
 }
 

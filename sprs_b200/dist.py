@@ -260,9 +260,8 @@ class PushAllGatherSpMV(FusedAllGatherSpMV):
 class StreamAllGatherSpMV(FusedAllGatherSpMV):
     """Row-partitioned y = A x with a pipelined all-gather: the SpMV writes only this rank's
     slice and publishes its progress; a small put kernel on a side stream copies every
-    finished chunk of rows into the peer buffers WHILE the SpMV is still running
-    (sprs_b200_spmv_stream_push_dev), and the carry fix-up writes the rows cut by a tile
-    boundary to all buffers.  The exchange overlaps the compute like the fused form, without
+    finished chunk of rows (carries of the rows cut by tile boundaries applied first) into the
+    peer buffers WHILE the SpMV is still running (sprs_b200_spmv_stream_push_dev).  The exchange overlaps the compute like the fused form, without
     its remote stores in the SpMV warps' own LSU queues.  Same peer buffers and barrier."""
 
     put_ctas = 0  # 0 = library default

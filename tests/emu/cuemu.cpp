@@ -391,6 +391,14 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     p->minor = 0;
     return cudaSuccess;
 }
+// every host pointer is "pinned and mapped" here (device memory IS host memory)
+cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
+    a->type = cudaMemoryTypeHost;
+    a->device = 0;
+    a->devicePointer = const_cast<void*>(p);
+    a->hostPointer = const_cast<void*>(p);
+    return cudaSuccess;
+}
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
 cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) {
     return cudaErrorNotSupported;

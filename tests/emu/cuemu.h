@@ -78,6 +78,13 @@ struct cudaDeviceProp {
     size_t totalGlobalMem;
     int major, minor;
 };
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2 };
+struct cudaPointerAttributes {
+    cudaMemoryType type;
+    int device;
+    void* devicePointer;
+    void* hostPointer;
+};
 struct cudaIpcMemHandle_t {
     char reserved[64];
 };
@@ -114,6 +121,7 @@ cudaError_t cudaStreamSynchronize(cudaStream_t s);
 cudaError_t cudaSetDevice(int d);
 cudaError_t cudaGetDeviceCount(int* n);
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int d);
+cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p);
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p);
 cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned flags);
 cudaError_t cudaIpcCloseMemHandle(void* p);

@@ -92,3 +92,7 @@ def test_stream_push_degenerate_shapes(sp, monkeypatch):
     _run_case(sp, monkeypatch, empty, 50, 10, None)     # no non-zeros: y = 0 everywhere
     one_target = rand_csr(rng, 500, 400, 30)
     _run_case(sp, monkeypatch, one_target, 500, 400, 1, n_targets=1)  # world size 1: plain SpMV
+    monkeypatch.setenv("SPRS_B200_PUSH_ALWAYS", "1")  # ... or the put kernel for its carries only
+    _run_case(sp, monkeypatch, one_target, 500, 400, 1, n_targets=1)
+    hub = rand_csr(rng, 60, 5000, 900, skew=True)
+    _run_case(sp, monkeypatch, hub, 60, 5000, 0, n_targets=1)
