@@ -239,7 +239,13 @@ int sprs_b200_csmat_upload(sprs_b200_ctx* ctx, int storage, uint64_t rows, uint6
     m->nnz = nnz;
     m->outer = outer;
     m->inner = storage == SPRS_B200_CSR ? cols : rows;
-    m->indptr_bytes = nnz >= 0xffffffffull ? 8 : 4;
+    // 64-bit indptr only when nnz needs it; SPRS_B200_FORCE_INDPTR64=1 is a TEST hook that
+    // takes the uint64 instantiations of the kernels at sizes a test can afford
+    static const bool force64 = [] {
+        const char* v = getenv("SPRS_B200_FORCE_INDPTR64");
+        return v && atoi(v) != 0;
+    }();
+    m->indptr_bytes = (nnz >= 0xffffffffull || force64) ? 8 : 4;
     cudaStream_t s = ctx->stream;
     int st = SPRS_B200_OK;
     do {

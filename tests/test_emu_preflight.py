@@ -58,7 +58,7 @@ def test_emu_gpu_suite(emu, schedule):
     env = dict(os.environ, SPRS_B200_EMU="1", CUEMU_SCHEDULE=schedule)
     r = subprocess.run(
         [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "-q", "-x",
-         "-p", "no:cacheprovider", "-k", "not full_size and not test_cpp and not l2_blocked",
+         "-p", "no:cacheprovider", "-k", "not full_size and not test_cpp and not l2_blocked and not indptr64",
          "--deselect", os.path.join(ROOT, "tests", "test_gpu_multi.py")],
         capture_output=True, text=True, timeout=1500, env=env, cwd=ROOT)
     tail = "\n".join(r.stdout.splitlines()[-25:])
@@ -66,11 +66,12 @@ def test_emu_gpu_suite(emu, schedule):
     assert " passed" in tail and "failed" not in tail
 
 
-def test_emu_spmm_panel_variant(emu):
-    """The opt-in L2-blocked SpMM kernel (its own child processes with SPRS_B200_SPMM_PANEL)."""
+def test_emu_spmm_panel_and_indptr64_variants(emu):
+    """The opt-in L2-blocked SpMM kernel and the uint64-indptr kernel instantiations (each in
+    child processes with its environment switch)."""
     env = dict(os.environ, SPRS_B200_EMU="1")
     r = subprocess.run(
         [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_zz_late.py"), "-m", "gpu",
-         "-q", "-x", "-p", "no:cacheprovider", "-k", "l2_blocked"],
+         "-q", "-x", "-p", "no:cacheprovider", "-k", "l2_blocked or indptr64"],
         capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]

@@ -173,3 +173,26 @@ def test_spmm_l2_blocked_variant(panel):
     tail = "\n".join(r.stdout.splitlines()[-15:])
     assert r.returncode == 0, tail + r.stderr[-1500:]
     assert " passed" in tail
+
+
+def test_indptr64_kernels():
+    """The uint64-indptr instantiations (taken for nnz >= 2^32, far beyond test sizes) through
+    the SPRS_B200_FORCE_INDPTR64 test hook: every SpMV / SpMM / conversion / solver test again
+    in a child process (SpGEMM is 32-bit-indptr only and says so)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SPRS_B200_FORCE_INDPTR64="1")
+    files = ["test_gpu_spmv_spmm.py", "test_gpu_spgemm_csc.py", "test_gpu_zz_late.py",
+             "test_gpu_zzz_solver.py"]
+    r = subprocess.run(
+        [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider"] +
+        [os.path.join(root, "tests", f) for f in files] +
+        ["-k", "not spgemm and not csc_csc and not csc_csr and not issue_99 and not "
+               "structural_zeros and not csvec and not full_size and not test_cpp and not "
+               "l2_blocked and not indptr64"],
+        capture_output=True, text=True, timeout=1500, env=env, cwd=root)
+    tail = "\n".join(r.stdout.splitlines()[-15:])
+    assert r.returncode == 0, tail + r.stderr[-1500:]
+    assert " passed" in tail
