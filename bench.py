@@ -26,6 +26,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+import bench_other  # noqa: E402  (needs ROOT on sys.path)
+
 WORKLOADS = {
     # name: (kind, n, nnz_per_row, generator)
     "spmv_rmat_10m": ("spmv", 10_000_000, 100, "rmat"),
@@ -262,7 +264,6 @@ def main():
     ctx = sp.Context.default(local)
     kind, n, npr, gen = WORKLOADS[args.workload]
     if kind != "spmv":
-        import bench_other
         return bench_other.run(args, ctx, kind, n, npr, gen, SEEDS[args.workload])
     peaks, peak_src = measured_peaks()
     hbm_peak = float(peaks["hbm_gbs"])
@@ -510,8 +511,10 @@ def main():
                        "gen_seconds": round(t_gen, 1)},
             "achieved_hbm_frac": (alg_bytes / (ms_per_step * 1e-3) / 1e9) / (hbm_peak * world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None,
-                         "kernel": "spmv_tile_kernel (+ spmv_fixup_kernel)",
+                         "frac": achieved / hbm_peak,
+                         "traffic": bench_other.ncu_traffic(args.workload, world),
+                         "traffic_source": bench_other.ncu_traffic(args.workload, world, source=True),
+                         "kernel": "spmv_warp_kernel (+ spmv_fixup_kernel)",
                          "kernel_ms": kern_ms_avg, "peak_source": peak_src,
                          "algorithmic_bytes": "12*nnz + 8*rows of this rank's block per launch",
                          "variant": os.environ.get("SPRS_B200_SPMV_VARIANT", "default 384,1,8,3 (wt,stages,warps,ctas/SM)")},

@@ -4,10 +4,26 @@
 Single GPU (the BASELINE configs are single-B200); same JSON contract as bench.py."""
 import ctypes as C
 import json
+import os
 import statistics
 import time
 
 import numpy as np
+
+
+def ncu_traffic(workload, world, source=False):
+    """roofline.traffic: DRAM bytes (read + write) per launch of the dominant kernel as ncu
+    measured them (profiles/ncu_traffic.json names the capture each number comes from);
+    null when no capture of this workload / GPU count exists."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
+                               "ncu_traffic.json")) as f:
+            rec = json.load(f).get(workload)
+    except (OSError, ValueError):
+        return None
+    if not rec or rec.get("n_gpus") != world:
+        return None
+    return rec["source"] if source else rec["bytes"]
 
 
 def _cpu_spmm(a, b_t, budget_rows):
@@ -98,7 +114,9 @@ def run(args, ctx, kind, n, npr, gen, seed):
                            "layout": "B, C row-major (csr_mulacc_dense_rowmaj)",
                            "l2_policy": "inputs (1.4 GB) exceed L2; no flush needed"},
                 "roofline": {"bound": "hbm", "achieved": comp_bytes / ms / 1e6, "peak": hbm,
-                             "unit": "GB/s", "frac": comp_bytes / ms / 1e6 / hbm, "traffic": None,
+                             "unit": "GB/s", "frac": comp_bytes / ms / 1e6 / hbm,
+                             "traffic": (None if os.environ.get("SPRS_B200_SPMM_PANEL")
+                                         else ncu_traffic(args.workload, 1)),
                              "kernel": "spmm_rowmaj_kernel", "peak_source": peak_src,
                              "algorithmic_bytes": "compulsory 12*nnz + 8*k*(cols+rows)"},
                 "e2e": {"value": flops / e2e_ms / 1e6, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
