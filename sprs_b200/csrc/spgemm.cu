@@ -32,6 +32,7 @@
 //   reference to rounding (gate 1e-6 * sum|terms|), indices/indptr exactly.
 // Algorithmic bytes: 12*(nnzA + n_prod + nnzC) + 8*(rows+1).
 
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -59,6 +60,34 @@ constexpr uint32_t NUM_S_MAX = 128, NUM_M_MAX = 4096;
 constexpr int S_SLOTS = 256;
 constexpr uint32_t SYM_M_SLOTS = 16384, NUM_M_SLOTS = 8192;
 constexpr uint64_t BITMAP_SMEM_MAX_COLS = 200ull * 1024 * 8;  // 200 KB of bits
+
+// Round-2 candidate tuning, opt-in until it has been timed on hardware (SPRS_B200_SPGEMM_V2=1;
+// profiles/r1_launches_spgemm_breakdown.txt and tools/spgemm_rmat_stats.py are the evidence
+// behind it).  What it changes, results unchanged:
+//   * routing: the hash bins shrink to the rows they are cheap for -- with a shared-memory
+//     bitmap the symbolic phase sends rows with n_prod > B.cols/256 to the bitmap kernel, and
+//     the numeric phase sends rows with nnz(C_i) > 16 * n_panels to the panel kernel (config 4:
+//     sym_med + num_med were 20 % of the time for 2 % of the products);
+//   * short A rows: groups of G warps share one B row (the CTA-per-row kernels otherwise keep
+//     nwarps - nnz(A_i) warps idle: half of config 4's large rows have <= 8 A non-zeros);
+//   * panel kernel: 1024 threads (32 warps of latency hiding instead of 8 at one CTA per SM),
+//     two chunks of every B row in flight per warp, panels nothing landed in are skipped.
+bool spgemm_v2() {
+    static const bool v = [] {
+        const char* e = getenv("SPRS_B200_SPGEMM_V2");
+        return e && atoi(e) != 0;
+    }();
+    return v;
+}
+
+// Warps that share one B row in the CTA-per-row kernels: the largest power of two G with
+// G * na <= nwarps (1 when grouping is off or the A row has at least nwarps/2 non-zeros).
+__device__ __forceinline__ int warps_per_brow(uint32_t na, int nwarps, int grouping) {
+    int g = 1;
+    if (grouping)
+        while (2 * g <= nwarps && (uint32_t)(2 * g) * na <= (uint32_t)nwarps) g *= 2;
+    return g;
+}
 
 __device__ __forceinline__ uint32_t hash_col(uint32_t c, uint32_t mask) {
     return (c * 2654435761u) & mask;
@@ -154,7 +183,7 @@ __global__ void __launch_bounds__(NT)
     sym_med_kernel(const uint32_t* __restrict__ a_ip, const uint32_t* __restrict__ a_idx,
                    const uint32_t* __restrict__ b_ip, const uint32_t* __restrict__ b_idx,
                    const uint64_t* __restrict__ nprod, const uint32_t* __restrict__ list,
-                   uint32_t n_list, uint32_t* __restrict__ cnt) {
+                   uint32_t n_list, uint32_t* __restrict__ cnt, int grouping) {
     extern __shared__ uint32_t dyn_u32[];
     uint32_t* t = dyn_u32;
     __shared__ uint32_t total;
@@ -167,9 +196,12 @@ __global__ void __launch_bounds__(NT)
         if (threadIdx.x == 0) total = 0;
         __syncthreads();
         uint32_t mine = 0;
-        for (uint32_t k = a_ip[r] + warp, e = a_ip[r + 1]; k < e; k += WARPS) {
+        const uint32_t a0 = a_ip[r], a1 = a_ip[r + 1];
+        const int G = warps_per_brow(a1 - a0, WARPS, grouping);
+        const int grp = warp / G, wg = warp % G, ngrp = WARPS / G;
+        for (uint32_t k = a0 + grp; k < a1; k += ngrp) {
             const uint32_t br = a_idx[k];
-            for (uint32_t p = b_ip[br] + lane, pe = b_ip[br + 1]; p < pe; p += 32) {
+            for (uint32_t p = b_ip[br] + wg * 32 + lane, pe = b_ip[br + 1]; p < pe; p += 32 * G) {
                 bool fresh;
                 table_insert(t, slots - 1, b_idx[p], &fresh);
                 mine += fresh;
@@ -185,14 +217,18 @@ __global__ void __launch_bounds__(NT)
 }
 
 // ---- symbolic, large rows: CTA per row, dense bitmap (shared or global slot) -------
+// SMEM_BM: the bitmap's address space is a template parameter, not a run-time pointer choice
+// (with the choice at run time the compiler has to emit generic ATOM.E.OR instead of ATOMS.OR
+// for the shared-memory bitmap; cuobjdump of the first version).
+template <bool SMEM_BM>
 __global__ void __launch_bounds__(NT)
     sym_large_kernel(const uint32_t* __restrict__ a_ip, const uint32_t* __restrict__ a_idx,
                      const uint32_t* __restrict__ b_ip, const uint32_t* __restrict__ b_idx,
                      const uint32_t* __restrict__ list, uint32_t n_list, uint32_t words,
-                     uint32_t* __restrict__ g_bitmaps /* null -> shared */,
-                     uint32_t* __restrict__ cnt) {
+                     uint32_t* __restrict__ g_bitmaps /* used when !SMEM_BM */,
+                     uint32_t* __restrict__ cnt, int grouping) {
     extern __shared__ uint32_t dyn_u32[];
-    uint32_t* bm = g_bitmaps ? g_bitmaps + (uint64_t)blockIdx.x * words : dyn_u32;
+    uint32_t* bm = SMEM_BM ? dyn_u32 : g_bitmaps + (uint64_t)blockIdx.x * words;
     __shared__ uint32_t total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t li = blockIdx.x; li < n_list; li += gridDim.x) {
@@ -200,9 +236,12 @@ __global__ void __launch_bounds__(NT)
         for (uint32_t i = threadIdx.x; i < words; i += NT) bm[i] = 0;
         if (threadIdx.x == 0) total = 0;
         __syncthreads();
-        for (uint32_t k = a_ip[r] + warp, e = a_ip[r + 1]; k < e; k += WARPS) {
+        const uint32_t a0 = a_ip[r], a1 = a_ip[r + 1];
+        const int G = warps_per_brow(a1 - a0, WARPS, grouping);
+        const int grp = warp / G, wg = warp % G, ngrp = WARPS / G;
+        for (uint32_t k = a0 + grp; k < a1; k += ngrp) {
             const uint32_t br = a_idx[k];
-            for (uint32_t p = b_ip[br] + lane, pe = b_ip[br + 1]; p < pe; p += 32) {
+            for (uint32_t p = b_ip[br] + wg * 32 + lane, pe = b_ip[br + 1]; p < pe; p += 32 * G) {
                 const uint32_t c = b_idx[p];
                 atomicOr(&bm[c >> 5], 1u << (c & 31));
             }
@@ -284,7 +323,7 @@ __global__ void __launch_bounds__(NT)
                    const uint32_t* __restrict__ b_idx, const double* __restrict__ b_val,
                    const uint64_t* __restrict__ c_ip, const uint32_t* __restrict__ cnt,
                    const uint32_t* __restrict__ list, uint32_t n_list,
-                   uint32_t* __restrict__ c_idx, double* __restrict__ c_val) {
+                   uint32_t* __restrict__ c_idx, double* __restrict__ c_val, int grouping) {
     extern __shared__ __align__(16) unsigned char dyn_raw[];
     double* tv = (double*)dyn_raw;                               // NUM_M_SLOTS doubles
     uint32_t* tk = (uint32_t*)(dyn_raw + NUM_M_SLOTS * sizeof(double));
@@ -299,10 +338,13 @@ __global__ void __launch_bounds__(NT)
             tv[i] = 0.0;
         }
         __syncthreads();
-        for (uint32_t k = a_ip[r] + warp, e = a_ip[r + 1]; k < e; k += WARPS) {
+        const uint32_t a0 = a_ip[r], a1 = a_ip[r + 1];
+        const int G = warps_per_brow(a1 - a0, WARPS, grouping);
+        const int grp = warp / G, wg = warp % G, ngrp = WARPS / G;
+        for (uint32_t k = a0 + grp; k < a1; k += ngrp) {
             const uint32_t br = a_idx[k];
             const double av = a_val[k];
-            for (uint32_t p = b_ip[br] + lane, pe = b_ip[br + 1]; p < pe; p += 32) {
+            for (uint32_t p = b_ip[br] + wg * 32 + lane, pe = b_ip[br + 1]; p < pe; p += 32 * G) {
                 bool fresh;
                 const uint32_t slot = table_insert(tk, slots - 1, b_idx[p], &fresh);
                 atomicAdd(&tv[slot], __dmul_rn(av, b_val[p]));
@@ -338,17 +380,18 @@ __global__ void __launch_bounds__(NT)
 }
 
 // ---- numeric, large rows: dense accumulator slot in global memory + bitmap --------
+template <bool SMEM_BM>
 __global__ void __launch_bounds__(1024)
     num_large_kernel(const uint32_t* __restrict__ a_ip, const uint32_t* __restrict__ a_idx,
                      const double* __restrict__ a_val, const uint32_t* __restrict__ b_ip,
                      const uint32_t* __restrict__ b_idx, const double* __restrict__ b_val,
                      const uint64_t* __restrict__ c_ip, const uint32_t* __restrict__ list,
                      uint32_t n_list, uint32_t words, uint64_t cols,
-                     uint32_t* __restrict__ g_bitmaps /* null -> shared */,
+                     uint32_t* __restrict__ g_bitmaps /* used when !SMEM_BM */,
                      double* __restrict__ g_acc /* gridDim.x * cols, zero on entry */,
                      uint32_t* __restrict__ c_idx, double* __restrict__ c_val) {
     extern __shared__ uint32_t dyn_u32[];
-    uint32_t* bm = g_bitmaps ? g_bitmaps + (uint64_t)blockIdx.x * words : dyn_u32;
+    uint32_t* bm = SMEM_BM ? dyn_u32 : g_bitmaps + (uint64_t)blockIdx.x * words;
     double* acc = g_acc + (uint64_t)blockIdx.x * cols;
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t chunk_total;
@@ -421,54 +464,103 @@ constexpr uint32_t PANEL_W = 20480;       // columns per panel: 160 KB of f64 ac
 constexpr uint32_t PANEL_MAX_A = 4096;    // cursors: 16 KB
 constexpr size_t PANEL_SMEM = PANEL_W * 8 + PANEL_W / 8 + PANEL_MAX_A * 4;
 
-__global__ void __launch_bounds__(NT)
+// NTH threads per CTA (one CTA per SM: the panel takes the shared memory).  TUNED = the
+// round-2 candidate (spgemm_v2): warp groups for short A rows, two chunks of a B row in flight
+// per warp, untouched panels skipped; <256, false> is the kernel validated in round 1.
+template <int NTH, bool TUNED>
+__global__ void __launch_bounds__(NTH)
     num_panel_kernel(const uint32_t* __restrict__ a_ip, const uint32_t* __restrict__ a_idx,
                      const double* __restrict__ a_val, const uint32_t* __restrict__ b_ip,
                      const uint32_t* __restrict__ b_idx, const double* __restrict__ b_val,
                      const uint64_t* __restrict__ c_ip, const uint32_t* __restrict__ list,
                      uint32_t n_list, uint32_t cols, uint32_t* __restrict__ c_idx,
                      double* __restrict__ c_val) {
+    constexpr int NWARPS = NTH / 32;
     extern __shared__ __align__(16) unsigned char dyn_raw[];
     double* acc = (double*)dyn_raw;                                  // PANEL_W
     uint32_t* bm = (uint32_t*)(dyn_raw + (size_t)PANEL_W * 8);        // PANEL_W / 32 words
     uint32_t* cursor = bm + PANEL_W / 32;                             // PANEL_MAX_A
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t chunk_total;
+    __shared__ uint32_t panel_mark;  // TUNED: sequence number of the last panel something landed in
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t i = threadIdx.x; i < PANEL_W; i += NT) acc[i] = 0.0;   // stays zero between rows
-    for (uint32_t i = threadIdx.x; i < PANEL_W / 32; i += NT) bm[i] = 0;
+    for (uint32_t i = threadIdx.x; i < PANEL_W; i += NTH) acc[i] = 0.0;   // stays zero between rows
+    for (uint32_t i = threadIdx.x; i < PANEL_W / 32; i += NTH) bm[i] = 0;
+    if (threadIdx.x == 0) panel_mark = 0;
     __syncthreads();
+    uint32_t seq = 0;  // panels visited by this CTA so far (uniform)
     for (uint32_t li = blockIdx.x; li < n_list; li += gridDim.x) {
         const uint32_t r = list[li];
         const uint32_t a0 = a_ip[r], na = a_ip[r + 1] - a0;
-        for (uint32_t kk = threadIdx.x; kk < na; kk += NT) cursor[kk] = b_ip[a_idx[a0 + kk]];
+        for (uint32_t kk = threadIdx.x; kk < na; kk += NTH) cursor[kk] = b_ip[a_idx[a0 + kk]];
         __syncthreads();
+        // G warps share one B row when the A row is short (G > 1 implies na <= NWARPS / 2, so
+        // every group then sees exactly one A non-zero per panel)
+        const int G = warps_per_brow(na, NWARPS, TUNED ? 1 : 0);
+        const int grp = warp / G, wg = warp % G, ngrp = NWARPS / G;
         uint64_t out = c_ip[r];
         for (uint32_t p0 = 0; p0 < cols; p0 += PANEL_W) {
             const uint32_t p1 = (cols - p0 > PANEL_W) ? p0 + PANEL_W : cols;
-            for (uint32_t kk = warp; kk < na; kk += WARPS) {
+            ++seq;
+            uint32_t grp_taken = 0;  // G > 1: entries of the group's B row this warp consumed
+            for (uint32_t kk = grp; kk < na; kk += ngrp) {
                 const uint32_t br = a_idx[a0 + kk];
                 const double av = a_val[a0 + kk];
                 const uint32_t end = b_ip[br + 1];
-                uint32_t pos = cursor[kk];
+                const uint32_t base = cursor[kk];
+                uint32_t pos = base + (uint32_t)wg * 32;  // this warp's chunks: pos, pos + 32 G, ...
+                uint32_t taken = 0;
+                // columns ascend, so the entries below p1 are a prefix of [base, end): a chunk
+                // inside the prefix is taken whole, the chunk holding its end partly, later
+                // chunks not at all -- the warps' counts add up to the prefix length
                 while (pos < end) {
-                    const uint32_t p = pos + lane;
-                    const uint32_t c = p < end ? b_idx[p] : 0xffffffffu;
-                    const bool take = c < p1;  // columns ascend: takers are a prefix of the lanes
-                    if (take) {
-                        atomicAdd(&acc[c - p0], __dmul_rn(av, b_val[p]));
-                        atomicOr(&bm[(c - p0) >> 5], 1u << ((c - p0) & 31));
+                    const uint32_t pa = pos + lane;
+                    const uint32_t ca = pa < end ? b_idx[pa] : 0xffffffffu;
+                    uint32_t cb = 0xffffffffu;
+                    double va = 0.0, vb = 0.0;
+                    if (TUNED) {  // second chunk and both value loads in flight with the first
+                        const uint32_t pb = pos + 32u * G + lane;
+                        cb = pb < end ? b_idx[pb] : 0xffffffffu;
+                        if (pa < end) va = b_val[pa];
+                        if (pb < end) vb = b_val[pb];
                     }
-                    const uint32_t nt = __popc(__ballot_sync(0xffffffffu, take));
-                    pos += nt;
-                    if (nt < 32) break;
+                    const bool take_a = ca < p1;
+                    if (take_a) {
+                        if (!TUNED) va = b_val[pa];
+                        atomicAdd(&acc[ca - p0], __dmul_rn(av, va));
+                        atomicOr(&bm[(ca - p0) >> 5], 1u << ((ca - p0) & 31));
+                    }
+                    const uint32_t na_t = __popc(__ballot_sync(0xffffffffu, take_a));
+                    taken += na_t;
+                    if (na_t < 32) break;
+                    if (TUNED) {
+                        const bool take_b = cb < p1;
+                        if (take_b) {
+                            atomicAdd(&acc[cb - p0], __dmul_rn(av, vb));
+                            atomicOr(&bm[(cb - p0) >> 5], 1u << ((cb - p0) & 31));
+                        }
+                        const uint32_t nb_t = __popc(__ballot_sync(0xffffffffu, take_b));
+                        taken += nb_t;
+                        if (nb_t < 32) break;
+                        pos += 64u * G;
+                    } else {
+                        pos += 32;
+                    }
                 }
-                if (lane == 0) cursor[kk] = pos;
+                if (TUNED && taken && lane == 0) panel_mark = seq;  // same value from every writer
+                if (G == 1) {
+                    if (lane == 0) cursor[kk] = base + taken;
+                } else {
+                    grp_taken = taken;  // added after the barrier: the group's other warps read `base`
+                }
             }
             __syncthreads();
+            if (G > 1 && grp < (int)na && grp_taken && lane == 0) atomicAdd(&cursor[grp], grp_taken);
+            if (TUNED && panel_mark != seq) continue;  // nothing landed here (uniform: read after the barrier;
+                                                       // the next write to panel_mark is behind the next barrier)
             // ordered extraction of this panel (also re-zeroes what it touched)
             const uint32_t words = (p1 - p0 + 31) / 32;
-            for (uint32_t w0 = 0; w0 < words; w0 += NT) {
+            for (uint32_t w0 = 0; w0 < words; w0 += NTH) {
                 const uint32_t w = w0 + threadIdx.x;
                 uint32_t bits = w < words ? bm[w] : 0u;
                 if (w < words) bm[w] = 0;
@@ -482,7 +574,7 @@ __global__ void __launch_bounds__(NT)
                 if (lane == 31) wsum[warp] = inc;
                 __syncthreads();
                 if (warp == 0) {
-                    uint32_t v = lane < WARPS ? wsum[lane] : 0u, vi = v;
+                    uint32_t v = lane < NWARPS ? wsum[lane] : 0u, vi = v;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const uint32_t u = __shfl_up_sync(0xffffffffu, vi, o);
@@ -587,7 +679,15 @@ int run_numeric(sprs_b200_ctx* ctx, sprs_b200_spgemm* p, uint32_t* d_cidx, doubl
     const auto* b = p->b;
     const uint32_t *a_ip = (const uint32_t*)a->d_indptr, *b_ip = (const uint32_t*)b->d_indptr;
     SPRS_CUDA(ctx, cudaMemsetAsync(p->d_counters, 0, 8 * sizeof(uint32_t), s));
-    bin_rows_kernel<uint32_t><<<grid_for(rows), 256, 0, s>>>(p->d_cnt, rows, NUM_S_MAX, NUM_M_MAX,
+    const bool v2 = spgemm_v2();
+    // v2: rows with more than 16 entries per column panel are cheaper in the panel kernel (no
+    // probing, no sort; fixed cost ~ n_panels) than in the CTA hash map
+    uint32_t num_m_max = NUM_M_MAX;
+    if (v2) {
+        const uint64_t n_panels = (p->cols + PANEL_W - 1) / PANEL_W;
+        num_m_max = (uint32_t)std::min<uint64_t>(NUM_M_MAX, std::max<uint64_t>(NUM_S_MAX, 16 * n_panels));
+    }
+    bin_rows_kernel<uint32_t><<<grid_for(rows), 256, 0, s>>>(p->d_cnt, rows, NUM_S_MAX, num_m_max,
                                                             p->d_lists, p->d_counters, nullptr);
     ctx->launches += 1;
     uint32_t h_cnt[8];
@@ -608,7 +708,7 @@ int run_numeric(sprs_b200_ctx* ctx, sprs_b200_spgemm* p, uint32_t* d_cidx, doubl
         const unsigned g = std::min<unsigned>(h_cnt[1], cap);
         num_med_kernel<<<g, NT, smem, s>>>(a_ip, a->d_indices, a->d_data, b_ip, b->d_indices,
                                            b->d_data, p->d_cptr, p->d_cnt, l1, h_cnt[1], d_cidx,
-                                           d_cval);
+                                           d_cval, v2 ? 1 : 0);
         ctx->launches += 1;
     }
     if (h_cnt[2]) {
@@ -625,12 +725,13 @@ int run_numeric(sprs_b200_ctx* ctx, sprs_b200_spgemm* p, uint32_t* d_cidx, doubl
         int st = cudaStreamSynchronize(s) == cudaSuccess ? SPRS_B200_OK : SPRS_B200_ERR_CUDA;
         const uint32_t n_panel = h2[3], n_hub = h2[4];
         if (st == SPRS_B200_OK && n_panel) {
-            if (cudaFuncSetAttribute(num_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            auto kern = v2 ? num_panel_kernel<1024, true> : num_panel_kernel<NT, false>;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)PANEL_SMEM) != cudaSuccess)
                 st = SPRS_B200_ERR_CUDA;
             else {
                 const unsigned g = std::min<unsigned>(n_panel, (unsigned)ctx->sm_count);
-                num_panel_kernel<<<g, NT, PANEL_SMEM, s>>>(a_ip, a->d_indices, a->d_data, b_ip,
+                kern<<<g, v2 ? 1024 : NT, PANEL_SMEM, s>>>(a_ip, a->d_indices, a->d_data, b_ip,
                                                            b->d_indices, b->d_data, p->d_cptr,
                                                            panel_list, n_panel, (uint32_t)p->cols,
                                                            d_cidx, d_cval);
@@ -640,14 +741,14 @@ int run_numeric(sprs_b200_ctx* ctx, sprs_b200_spgemm* p, uint32_t* d_cidx, doubl
         if (st == SPRS_B200_OK && n_hub) {
             LargeWorkspace w;
             st = plan_large(ctx, p->cols, n_hub, true, &w, s);
+            auto kern = w.smem ? num_large_kernel<true> : num_large_kernel<false>;
             if (st == SPRS_B200_OK && w.smem)
-                if (cudaFuncSetAttribute(num_large_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)w.smem) != cudaSuccess)
                     st = SPRS_B200_ERR_CUDA;
             if (st == SPRS_B200_OK) {
                 const unsigned big_nt = w.grid < (unsigned)ctx->sm_count ? 1024 : NT;
-                num_large_kernel<<<w.grid, big_nt, w.smem, s>>>(
+                kern<<<w.grid, big_nt, w.smem, s>>>(
                     a_ip, a->d_indices, a->d_data, b_ip, b->d_indices, b->d_data, p->d_cptr,
                     hub_list, n_hub, w.words, p->cols, w.bitmaps, w.acc, d_cidx, d_cval);
                 ctx->launches += 1;
@@ -701,8 +802,14 @@ int sprs_b200_spgemm_symbolic(sprs_b200_ctx* ctx, const sprs_b200_csmat* a,
         nprod_kernel<<<std::min<unsigned>((rows + WARPS - 1) / WARPS, cap * 4), NT, 0, s>>>(
             a_ip, a->d_indices, b_ip, rows, p->d_nprod);
         cudaMemsetAsync(p->d_counters, 0, 8 * sizeof(uint32_t), s);
+        const bool v2 = spgemm_v2();
+        // v2: with the bitmap in shared memory (no probing, fixed cost ~ cols / 32 words) the
+        // hash set only pays below ~cols/256 products
+        uint32_t sym_m_max = SYM_M_MAX;
+        if (v2 && p->cols <= BITMAP_SMEM_MAX_COLS)
+            sym_m_max = (uint32_t)std::min<uint64_t>(SYM_M_MAX, std::max<uint64_t>(SYM_S_MAX, p->cols / 256));
         bin_rows_kernel<uint64_t><<<grid_for(rows), 256, 0, s>>>(
-            p->d_nprod, rows, SYM_S_MAX, SYM_M_MAX, p->d_lists, p->d_counters, p->d_cnt);
+            p->d_nprod, rows, SYM_S_MAX, sym_m_max, p->d_lists, p->d_counters, p->d_cnt);
         ctx->launches += 2;
         uint32_t h_cnt[8];
         if (cudaMemcpyAsync(h_cnt, p->d_counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, s) !=
@@ -724,17 +831,19 @@ int sprs_b200_spgemm_symbolic(sprs_b200_ctx* ctx, const sprs_b200_csmat* a,
             cudaFuncSetAttribute(sym_med_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem);
             sym_med_kernel<<<std::min<unsigned>(h_cnt[1], cap), NT, smem, s>>>(
-                a_ip, a->d_indices, b_ip, b->d_indices, p->d_nprod, l1, h_cnt[1], p->d_cnt);
+                a_ip, a->d_indices, b_ip, b->d_indices, p->d_nprod, l1, h_cnt[1], p->d_cnt,
+                v2 ? 1 : 0);
             ctx->launches += 1;
         }
         if (h_cnt[2]) {
             LargeWorkspace w;
             if ((st = plan_large(ctx, p->cols, h_cnt[2], false, &w, s)) != SPRS_B200_OK) break;
+            auto kern = w.smem ? sym_large_kernel<true> : sym_large_kernel<false>;
             if (w.smem)
-                cudaFuncSetAttribute(sym_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)w.smem);
-            sym_large_kernel<<<w.grid, NT, w.smem, s>>>(a_ip, a->d_indices, b_ip, b->d_indices, l2,
-                                                        h_cnt[2], w.words, w.bitmaps, p->d_cnt);
+            kern<<<w.grid, NT, w.smem, s>>>(a_ip, a->d_indices, b_ip, b->d_indices, l2, h_cnt[2],
+                                            w.words, w.bitmaps, p->d_cnt, v2 ? 1 : 0);
             ctx->launches += 1;
             cudaStreamSynchronize(s);
             free_large(w);

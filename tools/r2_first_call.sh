@@ -11,11 +11,13 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $out/gpu.txt 
 #    there loses the CUDA context)
 timeout 900 python -m pytest tests -m gpu -q -x > $out/pytest_gpu.txt 2>&1; echo "pytest_gpu exit $?" >> $out/summary.txt
 SPRS_B200_TEST_STREAM_PUSH=1 timeout 300 python -m pytest tests/test_gpu_zzz_stream_push.py -m gpu -q > $out/pytest_stream_push.txt 2>&1; echo "stream_push exit $?" >> $out/summary.txt
+SPRS_B200_TEST_SPGEMM_V2=1 timeout 600 python -m pytest tests/test_gpu_zzz_spgemm_v2.py -m gpu -q > $out/pytest_spgemm_v2.txt 2>&1; echo "spgemm_v2 tests exit $?" >> $out/summary.txt
 # 2. headline bench (N=1) and the secondary workloads (SpGEMM with the panel kernel: first timing)
 timeout 600 python bench.py --steps 20 --warmup 5 > $out/bench_n1.json 2> $out/bench_n1.err; echo "bench exit $?" >> $out/summary.txt
 SPRS_B200_E2E_PIPELINE=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extra > $out/bench_n1_e2e_pipeline.json 2> $out/bench_n1_e2e_pipeline.err; echo "bench e2e pipeline exit $?" >> $out/summary.txt
 for pw in 8 4; do SPRS_B200_SPMM_PANEL=$pw timeout 300 python bench.py --workload spmm_rand_1m_k64 --steps 10 --warmup 3 --no-cpu-baseline > $out/bench_spmm_panel$pw.json 2> $out/bench_spmm_panel$pw.err; done
 timeout 600 python bench.py --workload spgemm_rmat_500k --steps 3 --warmup 1 > $out/bench_spgemm.json 2> $out/bench_spgemm.err; echo "spgemm exit $?" >> $out/summary.txt
+SPRS_B200_SPGEMM_V2=1 timeout 600 python bench.py --workload spgemm_rmat_500k --steps 3 --warmup 1 --no-cpu-baseline > $out/bench_spgemm_v2.json 2> $out/bench_spgemm_v2.err; echo "spgemm v2 exit $?" >> $out/summary.txt
 timeout 300 python bench.py --workload spmm_rand_1m_k64 --steps 10 --warmup 3 > $out/bench_spmm.json 2> $out/bench_spmm.err; echo "spmm exit $?" >> $out/summary.txt
 # 3. BiCGSTAB: cost of a step next to its two SpMVs (config 5 matrix)
 timeout 600 python tools/time_bicgstab.py > $out/bicgstab.json 2> $out/bicgstab.err; echo "bicgstab exit $?" >> $out/summary.txt
@@ -24,6 +26,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   --log-file $out/launches_spgemm.csv python bench.py --workload spgemm_rmat_500k --steps 1 --warmup 1 --no-cpu-baseline \
   > $out/ncu_spgemm.log 2>&1; echo "ncu spgemm exit $?" >> $out/summary.txt
 python tools/agg_launches.py $out/launches_spgemm.csv > $out/launches_spgemm_agg.txt 2>&1
+SPRS_B200_SPGEMM_V2=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+  --log-file $out/launches_spgemm_v2.csv python bench.py --workload spgemm_rmat_500k --steps 1 --warmup 1 --no-cpu-baseline \
+  > $out/ncu_spgemm_v2.log 2>&1; echo "ncu spgemm v2 exit $?" >> $out/summary.txt
+python tools/agg_launches.py $out/launches_spgemm_v2.csv > $out/launches_spgemm_v2_agg.txt 2>&1
 cat $out/summary.txt
 tail -3 $out/pytest_gpu.txt $out/pytest_stream_push.txt
 tail -c 600 $out/bench_n1.json; echo; python - <<'PY'
@@ -35,4 +41,4 @@ for f in ("bench_n1", "bench_n1_e2e_pipeline", "bench_spmm", "bench_spmm_panel8"
     except Exception as e:
         print(f, "FAILED", e)
 PY
-tail -c 400 $out/bench_spgemm.json; echo; cat $out/bicgstab.json
+tail -c 400 $out/bench_spgemm.json; echo; tail -c 400 $out/bench_spgemm_v2.json; echo; cat $out/bicgstab.json
