@@ -194,6 +194,10 @@ int sprs_b200_ctx_destroy(sprs_b200_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    for (int i = 0; i < SPRS_E2E_MAX_CHUNKS; ++i)
+        if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
+    if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SPRS_B200_OK;
@@ -521,6 +525,58 @@ int sprs_b200_spmm_rowmaj_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, co
 // ---------------------------------------------------------------------------------
 // host-buffer entry points.  x / y travel through cudaMemcpyAsync on the ctx stream
 // (true DMA when the caller's buffers are pinned); the call blocks until y is visible.
+
+// Chunked variant of the host path (opt-in: SPRS_B200_E2E_PIPELINE=2, until it has been timed):
+// the tile stream is cut into a few chunks; each chunk's SpMV + carry kernel is followed by an
+// event, and a second stream copies the rows that chunk completed to the host while the next
+// chunk computes -- plain stream/event ordering, no kernel waits on another.  Only the last
+// chunk's copy is left after the SpMV.
+static int spmv_host_chunked(sprs_b200_ctx* ctx, const sprs_b200_csmat* csr, const double* d_x,
+                             double* d_y, double* y, int accumulate, cudaStream_t s) {
+    if (!ctx->copy_stream) {
+        SPRS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < SPRS_E2E_MAX_CHUNKS; ++i)
+            SPRS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
+        SPRS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
+    }
+    if (csr->e2e_tiles.empty()) {
+        // chunks of at least ~64 tiles per resident warp (tail effects of a launch stay small)
+        const uint64_t per_chunk = (uint64_t)ctx->sm_count * 24 * 64;
+        uint64_t n_chunks = csr->n_tiles / per_chunk;
+        if (const char* e = getenv("SPRS_B200_E2E_CHUNKS")) n_chunks = (uint64_t)atoi(e);
+        n_chunks = std::max<uint64_t>(1, std::min<uint64_t>(n_chunks, SPRS_E2E_MAX_CHUNKS));
+        n_chunks = std::min<uint64_t>(n_chunks, csr->n_tiles);
+        std::vector<uint64_t> tiles(n_chunks + 1), rows(n_chunks + 1);
+        for (uint64_t c = 0; c <= n_chunks; ++c) tiles[c] = csr->n_tiles * c / n_chunks;
+        for (uint64_t c = 0; c <= n_chunks; ++c) {
+            uint32_t r = 0;  // tile_row[0] == 0, tile_row[n_tiles] == rows
+            SPRS_CUDA(ctx, cudaMemcpyAsync(&r, csr->d_tile_row + tiles[c], sizeof(r),
+                                           cudaMemcpyDeviceToHost, s));
+            SPRS_CUDA(ctx, cudaStreamSynchronize(s));
+            rows[c] = r;
+        }
+        csr->e2e_rows = rows;
+        csr->e2e_tiles = tiles;
+    }
+    const size_t n_chunks = csr->e2e_tiles.size() - 1;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        SPRS_TRY(spmv_launch_tile_range(ctx, csr, d_x, d_y, accumulate, csr->e2e_tiles[c],
+                                        csr->e2e_tiles[c + 1], s));
+        SPRS_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[c], s));
+    }
+    for (size_t c = 0; c < n_chunks; ++c) {
+        const uint64_t r0 = csr->e2e_rows[c], r1 = csr->e2e_rows[c + 1];
+        SPRS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[c], 0));
+        if (r1 > r0)
+            SPRS_CUDA(ctx, cudaMemcpyAsync(y + r0, d_y + r0, (r1 - r0) * sizeof(double),
+                                           cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+    // join: the ctx stream (and the caller, who synchronises it) waits for the last copy
+    SPRS_CUDA(ctx, cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+    SPRS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_copied, 0));
+    return SPRS_B200_OK;
+}
+
 static int spmv_host(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, int want_storage,
                      const double* x, uint64_t x_len, double* y, uint64_t y_len,
                      int accumulate) {
@@ -553,11 +609,22 @@ static int spmv_host(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, int want_st
         // the SpMV runs -- the pipelined put of spmv.cu with the host buffer as the second
         // target -- instead of one D2H copy after it.
         double* y_mapped = nullptr;
-        static const bool pipeline = [] {
+        static const int pipeline = [] {
             const char* v = getenv("SPRS_B200_E2E_PIPELINE");
-            return v && atoi(v) != 0;
+            return v ? atoi(v) : 0;
         }();
-        if (pipeline && y_len >= 4096) {
+        if (pipeline == 2 && y_len >= 4096 && csr->nnz) {
+            if ((st = spmv_host_chunked(ctx, csr, (const double*)d_x, (double*)d_y, y, accumulate,
+                                        s)) != SPRS_B200_OK)
+                break;
+            e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) {
+                sprs_b200_set_error(ctx, cudaGetErrorString(e));
+                st = SPRS_B200_ERR_CUDA;
+            }
+            break;
+        }
+        if (pipeline == 1 && y_len >= 4096) {
             cudaPointerAttributes attr;
             if (cudaPointerGetAttributes(&attr, y) == cudaSuccess &&
                 attr.type == cudaMemoryTypeHost && attr.devicePointer)

@@ -6,8 +6,11 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/sprs_b200.h"
+
+constexpr int SPRS_E2E_MAX_CHUNKS = 8;
 
 // ---- error plumbing: C functions return int, never throw/abort ----
 struct sprs_b200_ctx {
@@ -26,6 +29,10 @@ struct sprs_b200_ctx {
     // kernel and the fork/join events that tie it to the caller's stream; created on first use
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // chunked host path (api.cu, SPRS_B200_E2E_PIPELINE=2): copy stream + one event per chunk
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_chunk[SPRS_E2E_MAX_CHUNKS] = {};
+    cudaEvent_t ev_copied = nullptr;
 };
 
 struct sprs_b200_csmat {
@@ -52,6 +59,10 @@ struct sprs_b200_csmat {
     int chunk_shift = 0;
     uint32_t n_chunks = 0;
     uint64_t push_epoch = 0;
+    // chunked host path only: tile and row boundaries of the chunks (host copies, built on
+    // first use: chunk c covers tiles [e2e_tiles[c], e2e_tiles[c+1]) and completes rows
+    // [e2e_rows[c], e2e_rows[c+1]))
+    mutable std::vector<uint64_t> e2e_tiles, e2e_rows;
 };
 
 #define SPRS_FAIL(ctx, code, ...)                                  \
@@ -106,6 +117,10 @@ int spmv_launch_targets(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const doub
 // targets.p[1..n) by a concurrent put kernel while the SpMV still runs (spmv.cu)
 int spmv_launch_stream_push(sprs_b200_ctx* ctx, sprs_b200_csmat* m, const double* d_x,
                             const SpmvTargets& yt, int accumulate, int put_ctas, cudaStream_t s);
+// One chunk of the tile stream: tiles [t0, t1) + the carries of the rows ending in them; after
+// chunks 0..c (in order, one stream) rows [0, tile_row[t1_c]) of y are final (spmv.cu)
+int spmv_launch_tile_range(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
+                           double* d_y, int accumulate, uint64_t t0, uint64_t t1, cudaStream_t s);
 int spmm_rowmaj_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_b,
                        uint64_t ldb, uint64_t k, double* d_c, uint64_t ldc, int accumulate,
                        cudaStream_t s);

@@ -303,8 +303,9 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
     spmv_warp_kernel(const P* __restrict__ indptr, const uint32_t* __restrict__ indices,
                      const double* __restrict__ data, const uint32_t* __restrict__ tile_row,
                      const double* __restrict__ x, SpmvTargets yt,
-                     double* __restrict__ carry, uint64_t nnz, uint32_t rows, uint64_t n_tiles,
-                     int accumulate, unsigned long long* progress, int chunk_shift) {
+                     double* __restrict__ carry, uint64_t nnz, uint32_t rows, uint64_t t_begin,
+                     uint64_t n_tiles /* end of this launch's tile range */, int accumulate,
+                     unsigned long long* progress, int chunk_shift) {
     constexpr int EPL = WT / 32;               // non-zeros per lane per tile
     constexpr bool DIRECT = STAGES == 0;       // no TMA ring: stream through registers
     constexpr int STAGE_BYTES = DIRECT ? WT * 8 : WT * 12;
@@ -313,7 +314,9 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
     __shared__ __align__(8) uint64_t bars[NWARPS][NST];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wsm = smem_raw + (size_t)warp * NST * STAGE_BYTES;
-    const uint64_t gw = (uint64_t)blockIdx.x * NWARPS + warp;
+    // this launch covers tiles [t_begin, n_tiles): the whole matrix, or one chunk of it when the
+    // caller pipelines something behind finished row ranges (spmv_launch_tile_range)
+    const uint64_t gw = t_begin + (uint64_t)blockIdx.x * NWARPS + warp;
     const uint64_t GW = (uint64_t)gridDim.x * NWARPS;
     const uint64_t pol_stream = policy_evict_first();
     const uint64_t polx = policy_evict_last();
@@ -543,6 +546,7 @@ SpmvVariant spmv_variant() {
 struct SpmvSignal {  // progress counters of the pipelined all-gather; null = no signalling
     unsigned long long* progress = nullptr;
     int chunk_shift = 0;
+    uint64_t t0 = 0, t1 = 0;  // tile range of this launch; t1 == 0: the whole matrix
 };
 
 template <typename P, int WT, int STAGES, int NWARPS, int CTAS>
@@ -573,12 +577,13 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
                                             carve));
         configured = true;
     }
+    const uint64_t t0 = sig.t1 ? sig.t0 : 0, t1 = sig.t1 ? sig.t1 : m->n_tiles;
     uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
-    const uint64_t need = (m->n_tiles + NWARPS - 1) / NWARPS;
+    const uint64_t need = (t1 - t0 + NWARPS - 1) / NWARPS;
     if (grid > need) grid = need;
     kern<<<(unsigned)grid, NWARPS * 32, smem, s>>>((const P*)m->d_indptr, m->d_indices, m->d_data,
                                                    m->d_tile_row, d_x, yt, m->d_carry, m->nnz,
-                                                   (uint32_t)m->rows, m->n_tiles, accumulate,
+                                                   (uint32_t)m->rows, t0, t1, accumulate,
                                                    sig.progress, sig.chunk_shift);
     return SPRS_B200_OK;
 }
@@ -830,6 +835,45 @@ int spmv_launch_stream_push(sprs_b200_ctx* ctx, sprs_b200_csmat* m, const double
     // join: the caller's stream continues when the last chunk has been fixed up and pushed
     SPRS_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
     SPRS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    return SPRS_B200_OK;
+}
+
+// ---- one chunk of the tile stream (pipelined host path of api.cu) ---------------------
+namespace {
+__global__ void spmv_fixup_range_kernel(const uint32_t* __restrict__ tile_row, const double* carry,
+                                        double* y, uint64_t u_lo, uint64_t u_hi) {
+    const uint64_t u = u_lo + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (u >= 1 && u < u_hi) apply_carries_ending_in(tile_row, carry, y, u);
+}
+}  // namespace
+
+// SpMV over tiles [t0, t1) followed by the carries of the rows that END in those tiles: once
+// this has run for every tile below t1 (chunks in increasing order on one stream), rows
+// [0, tile_row[t1]) of y are final -- the same sums in the same order as the one-shot
+// spmv_launch (apply_carries_ending_in adds a run's carries in tile order from its head, like
+// spmv_fixup_kernel).
+int spmv_launch_tile_range(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
+                           double* d_y, int accumulate, uint64_t t0, uint64_t t1,
+                           cudaStream_t s) {
+    if (m->storage != SPRS_B200_CSR)
+        SPRS_FAIL(ctx, SPRS_B200_ERR_STORAGE, "Storage mismatch: spmv needs a CSR mirror");
+    if (!m->d_tile_row) SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "csmat has no SpMV partition");
+    if (t1 > m->n_tiles || t0 >= t1) SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "bad tile range");
+    SpmvTargets yt;
+    yt.n = 1;
+    yt.p[0] = d_y;
+    for (int q = 1; q < SPMV_MAX_TARGETS; ++q) yt.p[q] = nullptr;
+    SpmvSignal sig;
+    sig.t0 = t0;
+    sig.t1 = t1;
+    if (m->indptr_bytes == 4)
+        SPRS_TRY(launch_dispatch<uint32_t>(ctx, m, d_x, yt, accumulate, sig, s));
+    else
+        SPRS_TRY(launch_dispatch<uint64_t>(ctx, m, d_x, yt, accumulate, sig, s));
+    spmv_fixup_range_kernel<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, s>>>(
+        m->d_tile_row, m->d_carry, d_y, t0, t1);
+    ctx->launches += 2;
+    SPRS_CUDA(ctx, cudaGetLastError());
     return SPRS_B200_OK;
 }
 
