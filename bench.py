@@ -233,7 +233,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "overlap", "fused", "push", "stream", "nccl"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "overlap", "fused", "push", "stream", "chunked", "nccl"],
                     help="N>1 all-gather of y: 'overlap' = row block cut into chunks, each "
                          "chunk's y slice pushed to the peers by DMA copies on a second stream "
                          "while the next chunk computes; 'fused' = the SpMV kernel itself stores "
@@ -249,7 +249,7 @@ def main():
     import sprs_b200 as sp
     from sprs_b200 import generate as G
     from sprs_b200.dist import (FusedAllGatherSpMV, OverlappedAllGatherSpMV, PushAllGatherSpMV,
-                                StreamAllGatherSpMV,
+                                StreamAllGatherSpMV, ChunkedPushAllGatherSpMV,
                                 RowPartitionedSpMV, fit_row_cost, nnz_balanced_bounds)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -313,14 +313,15 @@ def main():
         # with the bytes pushed (~0.14 ms at 40 MB, ~0.22 ms at 60 MB), while at 8 GPUs the
         # fused kernel measured 0.82 ms against 0.61 ms of pure compute -> fused from 6 GPUs up
         args.exchange = "fused" if world >= 6 else "push"
-    fused = world > 1 and args.exchange in ("fused", "overlap", "push", "stream")
+    fused = world > 1 and args.exchange in ("fused", "overlap", "push", "stream", "chunked")
 
     def make_op(a_blk, bnds):
         if world > 1 and args.exchange == "overlap":
             o = OverlappedAllGatherSpMV(ctx, a_blk, bnds, rank, world, n, dist, dev,
                                         chunks=args.chunks, row_cost=row_cost)
         elif fused:
-            cls = {"push": PushAllGatherSpMV, "stream": StreamAllGatherSpMV}.get(
+            cls = {"push": PushAllGatherSpMV, "stream": StreamAllGatherSpMV,
+                   "chunked": ChunkedPushAllGatherSpMV}.get(
                 args.exchange, FusedAllGatherSpMV)
             o = cls(ctx, a_blk.mirror, bnds, rank, world, n, dist, dev)
         else:
@@ -505,6 +506,10 @@ def main():
                                      "copying finished row chunks into the peer buffers "
                                      "(pipelined all-gather over NVLink) + 1-element NCCL "
                                      "all_reduce barrier",
+                           "chunked": "SpMV launched in 4 chunks of decreasing size; behind each "
+                                      "chunk's event a side stream pushes the rows it completed "
+                                      "into the peer buffers (own put kernel over NVLink) + "
+                                      "1-element NCCL all_reduce barrier",
                            "nccl": "NCCL all_gather(y), unequal slices"}[args.exchange]),
                        "l2_policy": "inputs (%.1f GB) exceed L2 (126 MB); no flush needed" %
                                     (alg_bytes / 1e9),

@@ -197,6 +197,16 @@ int sprs_b200_spmv_allgather_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
 int sprs_b200_spmv_stream_push_dev(sprs_b200_ctx* ctx, sprs_b200_csmat* mat, const double* d_x,
                                    uint64_t row_offset, int n_targets, double* const* d_y_bufs,
                                    int accumulate, int put_ctas, void* stream);
+/* The same all-gather without any kernel waiting on another: the tile stream of the block is
+ * launched in `n_chunks` chunks of decreasing size (0 = default 4, at most 8); behind each
+ * chunk's event a side stream of the ctx copies the rows that chunk completed (carries
+ * applied) into d_y_bufs[1..) with a put kernel while the next chunk computes; `stream` is
+ * joined with the side stream before the call returns control to it.  Bit-identical to
+ * sprs_b200_spmv_dev.  Safe under tools that serialise kernels.                          */
+int sprs_b200_spmv_chunked_push_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
+                                    const double* d_x, uint64_t row_offset, int n_targets,
+                                    double* const* d_y_bufs, int accumulate, int n_chunks,
+                                    void* stream);
 
 /* ---- sparse x sparse: smmp::mul_csr_csr (smmp.rs:196-237), two calls so the
  * CALLER allocates the output Vecs, like symbolic -> numeric (smmp.rs:81,151).

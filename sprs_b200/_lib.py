@@ -60,6 +60,8 @@ PROTOTYPES = {
     "sprs_b200_spmv_allgather_dev": (_int, [_vp, _vp, _dp, _u64, _int, C.POINTER(_vp), _int, _vp]),
     "sprs_b200_spmv_stream_push_dev": (_int, [_vp, _vp, _dp, _u64, _int, C.POINTER(_vp), _int,
                                               _int, _vp]),
+    "sprs_b200_spmv_chunked_push_dev": (_int, [_vp, _vp, _dp, _u64, _int, C.POINTER(_vp), _int,
+                                               _int, _vp]),
     "sprs_b200_spgemm_symbolic": (_int, [_vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_u64)]),
     "sprs_b200_spgemm_numeric": (_int, [_vp, _vp, _vp, _int, _vp, _int, _dp]),
     "sprs_b200_spgemm_numeric_dev": (_int, [_vp, _vp, C.POINTER(_vp)]),

@@ -128,6 +128,42 @@ int ctx_scratch(sprs_b200_ctx* ctx, int i, size_t bytes, void** out) {
     return SPRS_B200_OK;
 }
 
+int ctx_side_stream(sprs_b200_ctx* ctx) {
+    if (ctx->side_stream) return SPRS_B200_OK;
+    int lo = 0, hi = 0;  // numerically lower = higher priority
+    SPRS_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    SPRS_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
+    SPRS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    SPRS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    return SPRS_B200_OK;
+}
+
+int csmat_chunk_table(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, uint64_t n_chunks, bool taper,
+                      cudaStream_t s, std::vector<uint64_t>* tiles, std::vector<uint64_t>* rows) {
+    n_chunks = std::max<uint64_t>(1, std::min<uint64_t>(n_chunks, SPRS_E2E_MAX_CHUNKS));
+    n_chunks = std::min<uint64_t>(n_chunks, m->n_tiles);
+    tiles->assign(n_chunks + 1, 0);
+    rows->assign(n_chunks + 1, 0);
+    const uint64_t wsum = taper ? n_chunks * (n_chunks + 1) / 2 : n_chunks;
+    uint64_t acc = 0;
+    for (uint64_t c = 0; c < n_chunks; ++c) {
+        (*tiles)[c] = m->n_tiles * acc / wsum;
+        acc += taper ? n_chunks - c : 1;
+    }
+    (*tiles)[n_chunks] = m->n_tiles;
+    for (uint64_t c = 1; c <= n_chunks; ++c)  // never an empty chunk
+        if ((*tiles)[c] <= (*tiles)[c - 1]) (*tiles)[c] = (*tiles)[c - 1] + 1;
+    (*tiles)[n_chunks] = m->n_tiles;
+    for (uint64_t c = 0; c <= n_chunks; ++c) {
+        uint32_t r = 0;  // tile_row[0] == 0, tile_row[n_tiles] == rows
+        SPRS_CUDA(ctx, cudaMemcpyAsync(&r, m->d_tile_row + (*tiles)[c], sizeof(r),
+                                       cudaMemcpyDeviceToHost, s));
+        SPRS_CUDA(ctx, cudaStreamSynchronize(s));
+        (*rows)[c] = r;
+    }
+    return SPRS_B200_OK;
+}
+
 int ctx_stage(sprs_b200_ctx* ctx, size_t bytes, void** out) {
     if (bytes < 256) bytes = 256;
     if (ctx->h_stage_bytes < bytes) {
@@ -535,26 +571,18 @@ static int spmv_host_chunked(sprs_b200_ctx* ctx, const sprs_b200_csmat* csr, con
                              double* d_y, double* y, int accumulate, cudaStream_t s) {
     if (!ctx->copy_stream) {
         SPRS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < SPRS_E2E_MAX_CHUNKS; ++i)
-            SPRS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
         SPRS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
     }
+    if (!ctx->ev_chunk[0])
+        for (int i = 0; i < SPRS_E2E_MAX_CHUNKS; ++i)
+            SPRS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
     if (csr->e2e_tiles.empty()) {
         // chunks of at least ~64 tiles per resident warp (tail effects of a launch stay small)
         const uint64_t per_chunk = (uint64_t)ctx->sm_count * 24 * 64;
         uint64_t n_chunks = csr->n_tiles / per_chunk;
         if (const char* e = getenv("SPRS_B200_E2E_CHUNKS")) n_chunks = (uint64_t)atoi(e);
-        n_chunks = std::max<uint64_t>(1, std::min<uint64_t>(n_chunks, SPRS_E2E_MAX_CHUNKS));
-        n_chunks = std::min<uint64_t>(n_chunks, csr->n_tiles);
-        std::vector<uint64_t> tiles(n_chunks + 1), rows(n_chunks + 1);
-        for (uint64_t c = 0; c <= n_chunks; ++c) tiles[c] = csr->n_tiles * c / n_chunks;
-        for (uint64_t c = 0; c <= n_chunks; ++c) {
-            uint32_t r = 0;  // tile_row[0] == 0, tile_row[n_tiles] == rows
-            SPRS_CUDA(ctx, cudaMemcpyAsync(&r, csr->d_tile_row + tiles[c], sizeof(r),
-                                           cudaMemcpyDeviceToHost, s));
-            SPRS_CUDA(ctx, cudaStreamSynchronize(s));
-            rows[c] = r;
-        }
+        std::vector<uint64_t> tiles, rows;
+        SPRS_TRY(csmat_chunk_table(ctx, csr, n_chunks, false, s, &tiles, &rows));
         csr->e2e_rows = rows;
         csr->e2e_tiles = tiles;
     }

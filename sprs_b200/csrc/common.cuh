@@ -63,6 +63,8 @@ struct sprs_b200_csmat {
     // first use: chunk c covers tiles [e2e_tiles[c], e2e_tiles[c+1]) and completes rows
     // [e2e_rows[c], e2e_rows[c+1]))
     mutable std::vector<uint64_t> e2e_tiles, e2e_rows;
+    // chunked push (peer.cu): the same kind of table with front-loaded chunk sizes
+    mutable std::vector<uint64_t> push_tiles, push_rows;
 };
 
 #define SPRS_FAIL(ctx, code, ...)                                  \
@@ -121,6 +123,14 @@ int spmv_launch_stream_push(sprs_b200_ctx* ctx, sprs_b200_csmat* m, const double
 // chunks 0..c (in order, one stream) rows [0, tile_row[t1_c]) of y are final (spmv.cu)
 int spmv_launch_tile_range(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
                            double* d_y, int accumulate, uint64_t t0, uint64_t t1, cudaStream_t s);
+// Chunk table of a mirror's tile stream: tiles[c] .. tiles[c+1] is chunk c, rows[c] =
+// tile_row[tiles[c]] (rows [rows[c], rows[c+1]) are final once chunk c and its carries ran).
+// `taper`: chunk sizes proportional to n, n-1, .., 1 (small last chunk: what follows the last
+// chunk cannot overlap with compute) instead of equal.  Synchronises `s` (api.cu).
+int csmat_chunk_table(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, uint64_t n_chunks, bool taper,
+                      cudaStream_t s, std::vector<uint64_t>* tiles, std::vector<uint64_t>* rows);
+// high-priority side stream + fork/join events of the ctx, created on first use (api.cu)
+int ctx_side_stream(sprs_b200_ctx* ctx);
 int spmm_rowmaj_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_b,
                        uint64_t ldb, uint64_t k, double* d_c, uint64_t ldc, int accumulate,
                        cudaStream_t s);

@@ -6,6 +6,9 @@
 // FUSED into the SpMV kernel: every rank maps the other ranks' y buffers through CUDA IPC
 // (NVLink/NVSwitch peer access) and the kernel stores each finished row into all of them,
 // so the transfer overlaps the rest of the compute; only a stream-ordered barrier remains.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -123,6 +126,62 @@ int sprs_b200_spmv_stream_push_dev(sprs_b200_ctx* ctx, sprs_b200_csmat* mat, con
         yt.p[q] = q < n_targets ? d_y_bufs[q] + row_offset : nullptr;
     return spmv_launch_stream_push(ctx, mat, d_x, yt, accumulate, put_ctas,
                                    (cudaStream_t)stream);
+}
+
+// Pipelined all-gather without any kernel waiting on another (plan B of the stream push): the
+// rank's tile stream is launched in a few chunks of decreasing size; behind each chunk's event
+// the side stream runs a put kernel that copies the rows that chunk completed into the peer
+// buffers while the next chunk computes.  Only the put of the (small) last chunk is exposed.
+int sprs_b200_spmv_chunked_push_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
+                                    const double* d_x, uint64_t row_offset, int n_targets,
+                                    double* const* d_y_bufs, int accumulate, int n_chunks,
+                                    void* stream) {
+    if (!ctx || !mat || !d_y_bufs) return SPRS_B200_ERR_ARGUMENT;
+    if (n_targets < 1 || n_targets > SPMV_MAX_TARGETS)
+        SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "n_targets must be 1..%d", SPMV_MAX_TARGETS);
+    if (mat->storage != SPRS_B200_CSR)
+        SPRS_FAIL(ctx, SPRS_B200_ERR_STORAGE, "Storage mismatch: spmv needs a CSR mirror");
+    if (mat->rows == 0) return SPRS_B200_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    double* y_own = d_y_bufs[0] + row_offset;
+    if (n_chunks <= 0) n_chunks = 4;
+    if (const char* e = getenv("SPRS_B200_PUSH_CHUNKS")) n_chunks = atoi(e) > 0 ? atoi(e) : n_chunks;
+    if (n_chunks > SPRS_E2E_MAX_CHUNKS) n_chunks = SPRS_E2E_MAX_CHUNKS;
+    if (mat->push_tiles.empty() || (int)mat->push_tiles.size() - 1 != std::min<int>(n_chunks, (int)mat->n_tiles)) {
+        std::vector<uint64_t> tiles, rows;
+        SPRS_TRY(csmat_chunk_table(ctx, mat, (uint64_t)n_chunks, true, s, &tiles, &rows));
+        mat->push_tiles = tiles;
+        mat->push_rows = rows;
+    }
+    SPRS_TRY(ctx_side_stream(ctx));
+    if (!ctx->ev_chunk[0])
+        for (int i = 0; i < SPRS_E2E_MAX_CHUNKS; ++i)
+            SPRS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
+    SpmvTargets dst;
+    dst.n = n_targets - 1;
+    for (int q = 0; q < SPMV_MAX_TARGETS; ++q) dst.p[q] = nullptr;
+    const size_t nc = mat->push_tiles.size() - 1;
+    for (size_t c = 0; c < nc; ++c) {
+        SPRS_TRY(spmv_launch_tile_range(ctx, mat, d_x, y_own, accumulate, mat->push_tiles[c],
+                                        mat->push_tiles[c + 1], s));
+        if (n_targets == 1) continue;
+        const uint64_t r0 = mat->push_rows[c], r1 = mat->push_rows[c + 1];
+        SPRS_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[c], s));
+        SPRS_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_chunk[c], 0));
+        if (r1 == r0) continue;
+        for (int q = 0; q < dst.n; ++q) dst.p[q] = d_y_bufs[q + 1] + row_offset + r0;
+        uint64_t blocks = (r1 - r0 + 1023) / 1024;
+        const uint64_t cap = (uint64_t)ctx->sm_count / 4;  // a few SMs' worth: the next chunk computes
+        if (blocks > cap) blocks = cap;
+        peer_push_kernel<<<(unsigned)blocks, 256, 0, ctx->side_stream>>>(y_own + r0, dst, r1 - r0);
+        ctx->launches += 1;
+        SPRS_CUDA(ctx, cudaGetLastError());
+    }
+    if (n_targets > 1) {
+        SPRS_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
+        SPRS_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    }
+    return SPRS_B200_OK;
 }
 
 }  // extern "C"

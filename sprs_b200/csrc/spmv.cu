@@ -754,13 +754,7 @@ __global__ void __launch_bounds__(PUT_THREADS)
 }
 
 int stream_push_prepare(sprs_b200_ctx* ctx, sprs_b200_csmat* m, cudaStream_t s) {
-    if (!ctx->side_stream) {
-        int lo = 0, hi = 0;  // numerically lower = higher priority
-        SPRS_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        SPRS_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi));
-        SPRS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-        SPRS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-    }
+    SPRS_TRY(ctx_side_stream(ctx));
     if (!m->d_progress) {
         // about 12 chunks: the last chunk's push is what cannot overlap
         int shift = 0;

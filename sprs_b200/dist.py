@@ -276,6 +276,25 @@ class StreamAllGatherSpMV(FusedAllGatherSpMV):
             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
 
+class ChunkedPushAllGatherSpMV(FusedAllGatherSpMV):
+    """Row-partitioned y = A x with a pipelined all-gather built from plain stream ordering
+    (plan B of StreamAllGatherSpMV: no kernel waits on another).  The rank's tile stream is
+    launched in a few chunks of decreasing size; behind each chunk's event a side stream runs
+    the put kernel for the rows that chunk completed while the next chunk computes
+    (sprs_b200_spmv_chunked_push_dev).  Same peer buffers and barrier as the fused form."""
+
+    n_chunks = 0  # 0 = library default (4)
+
+    def compute(self, x):
+        import ctypes as C
+        import torch
+        ctx = self.ctx
+        ctx.check(ctx.lib.sprs_b200_spmv_chunked_push_dev(
+            ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()), self.bounds[self.rank],
+            len(self._targets), self._targets, 0, int(self.n_chunks),
+            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
 class OverlappedAllGatherSpMV:
     """Row-partitioned y = A x with the all-gather of y overlapped with the compute.
 

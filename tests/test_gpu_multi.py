@@ -20,7 +20,8 @@ def _worker(rank, world, port, q):
     import sprs_b200 as sp
     from sprs_b200 import generate as G
     from sprs_b200.dist import (FusedAllGatherSpMV, OverlappedAllGatherSpMV, PushAllGatherSpMV,
-                                RowPartitionedSpMV, StreamAllGatherSpMV, nnz_balanced_bounds)
+                                ChunkedPushAllGatherSpMV, RowPartitionedSpMV,
+                                StreamAllGatherSpMV, nnz_balanced_bounds)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -71,6 +72,16 @@ def _worker(rank, world, port, q):
             oks.append(bool(((g4 - ref).abs() <= 1e-9 * scale).all()))
             dist.barrier()
         pop.close()
+        cop = ChunkedPushAllGatherSpMV(ctx, a.mirror, bounds, rank, world, n, dist, dev)
+        for _ in range(3):
+            cop.y.fill_(float("nan"))
+            torch.cuda.synchronize()
+            dist.barrier()
+            g6 = cop.step(x)
+            torch.cuda.synchronize()
+            oks.append(bool(((g6 - ref).abs() <= 1e-9 * scale).all()))
+            dist.barrier()
+        cop.close()
         sop = StreamAllGatherSpMV(ctx, a.mirror, bounds, rank, world, n, dist, dev)
         for _ in range(3):
             sop.y.fill_(float("nan"))

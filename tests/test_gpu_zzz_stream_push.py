@@ -29,7 +29,7 @@ def sp():
 
 
 def _run_case(sp, monkeypatch, csr, rows, cols, chunk_shift, n_targets=3, offset=5, reps=3,
-              accumulate=False):
+              accumulate=False, chunked=None):
     import torch
     from sprs_b200 import generate as G
     ctx = sp.Context.default()
@@ -55,9 +55,14 @@ def _run_case(sp, monkeypatch, csr, rows, cols, chunk_shift, n_targets=3, offset
         ctx.check(ctx.lib.sprs_b200_spmv_dev(ctx.h, mirror, C.c_void_p(x.data_ptr()),
                                              C.c_void_p(ref.data_ptr()), int(accumulate),
                                              G._stream_ptr()))
-        ctx.check(ctx.lib.sprs_b200_spmv_stream_push_dev(
-            ctx.h, mirror, C.c_void_p(x.data_ptr()), offset, n_targets, ptrs, int(accumulate),
-            4, G._stream_ptr()))
+        if chunked is not None:   # plan B: chunks + events (sprs_b200_spmv_chunked_push_dev)
+            ctx.check(ctx.lib.sprs_b200_spmv_chunked_push_dev(
+                ctx.h, mirror, C.c_void_p(x.data_ptr()), offset, n_targets, ptrs, int(accumulate),
+                chunked, G._stream_ptr()))
+        else:
+            ctx.check(ctx.lib.sprs_b200_spmv_stream_push_dev(
+                ctx.h, mirror, C.c_void_p(x.data_ptr()), offset, n_targets, ptrs, int(accumulate),
+                4, G._stream_ptr()))
         G._sync()
         want = ref.cpu().numpy()
         for q, b in enumerate(bufs):
@@ -96,3 +101,25 @@ def test_stream_push_degenerate_shapes(sp, monkeypatch):
     _run_case(sp, monkeypatch, one_target, 500, 400, 1, n_targets=1)
     hub = rand_csr(rng, 60, 5000, 900, skew=True)
     _run_case(sp, monkeypatch, hub, 60, 5000, 0, n_targets=1)
+
+
+@pytest.mark.parametrize("n_chunks", [0, 1, 3, 8])
+def test_chunked_push_matches_plain_spmv(sp, monkeypatch, n_chunks):
+    """sprs_b200_spmv_chunked_push_dev: same buffers, same bits, chunk/event pipelining."""
+    rng = np.random.default_rng(177)
+    rows, cols = 3000, 2500
+    csr = rand_csr(rng, rows, cols, 40, empty_frac=0.1)
+    _run_case(sp, monkeypatch, csr, rows, cols, None, chunked=n_chunks)
+
+
+def test_chunked_push_hub_rows_degenerate_shapes(sp, monkeypatch):
+    rng = np.random.default_rng(178)
+    hub = rand_csr(rng, 400, 6000, 300, skew=True)
+    _run_case(sp, monkeypatch, hub, 400, 6000, None, chunked=4)
+    _run_case(sp, monkeypatch, hub, 400, 6000, None, chunked=5, accumulate=True, n_targets=8)
+    tiny = rand_csr(rng, 7, 9, 2)                       # one ragged tile: a single chunk
+    _run_case(sp, monkeypatch, tiny, 7, 9, None, chunked=4)
+    empty = (np.zeros(51, np.uint32), np.zeros(0, np.uint32), np.zeros(0))
+    _run_case(sp, monkeypatch, empty, 50, 10, None, chunked=4)
+    one_target = rand_csr(rng, 500, 400, 30)
+    _run_case(sp, monkeypatch, one_target, 500, 400, None, n_targets=1, chunked=3)

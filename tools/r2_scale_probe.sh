@@ -1,7 +1,7 @@
 #!/bin/bash
 # 8-GPU probe of the exchange modes incl. the pipelined put (charged 8x: keep it short).
-#   gpurun --gpus 8 --timeout 900 -- 'bash tools/r2_scale_probe.sh 8 "stream fused push"'
-n=${1:-8}; modes=${2:-"stream fused push"}
+#   gpurun --gpus 8 --timeout 900 -- 'bash tools/r2_scale_probe.sh 8 "chunked stream fused push"'
+n=${1:-8}; modes=${2:-"chunked stream fused push"}
 out=gpurun_out/r2_scale; mkdir -p $out
 for ex in $modes; do
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 \
