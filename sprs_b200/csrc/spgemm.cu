@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(NTH)
                      const uint32_t* __restrict__ b_idx, const double* __restrict__ b_val,
                      const uint64_t* __restrict__ c_ip, const uint32_t* __restrict__ list,
                      uint32_t n_list, uint32_t cols, uint32_t* __restrict__ c_idx,
-                     double* __restrict__ c_val) {
+                     double* __restrict__ c_val, uint32_t* __restrict__ row_counter) {
     constexpr int NWARPS = NTH / 32;
     extern __shared__ __align__(16) unsigned char dyn_raw[];
     double* acc = (double*)dyn_raw;                                  // PANEL_W
@@ -489,7 +489,16 @@ __global__ void __launch_bounds__(NTH)
     if (threadIdx.x == 0) panel_mark = 0;
     __syncthreads();
     uint32_t seq = 0;  // panels visited by this CTA so far (uniform)
-    for (uint32_t li = blockIdx.x; li < n_list; li += gridDim.x) {
+    __shared__ uint32_t next_li;
+    // TUNED: rows are handed out dynamically (work per row spans three orders of magnitude and
+    // the list starts with the heaviest rows of an R-MAT matrix); otherwise round-robin
+    for (uint32_t li = blockIdx.x;; li += gridDim.x) {
+        if (TUNED) {
+            if (threadIdx.x == 0) next_li = atomicAdd(row_counter, 1u);
+            __syncthreads();
+            li = next_li;  // the next write is behind the barrier after the cursor set-up
+        }
+        if (li >= n_list) break;
         const uint32_t r = list[li];
         const uint32_t a0 = a_ip[r], na = a_ip[r + 1] - a0;
         for (uint32_t kk = threadIdx.x; kk < na; kk += NTH) cursor[kk] = b_ip[a_idx[a0 + kk]];
@@ -734,7 +743,7 @@ int run_numeric(sprs_b200_ctx* ctx, sprs_b200_spgemm* p, uint32_t* d_cidx, doubl
                 kern<<<g, v2 ? 1024 : NT, PANEL_SMEM, s>>>(a_ip, a->d_indices, a->d_data, b_ip,
                                                            b->d_indices, b->d_data, p->d_cptr,
                                                            panel_list, n_panel, (uint32_t)p->cols,
-                                                           d_cidx, d_cval);
+                                                           d_cidx, d_cval, p->d_counters + 5);
                 ctx->launches += 1;
             }
         }
