@@ -67,6 +67,69 @@ __global__ void __launch_bounds__(SPMM_NT)
     }
 }
 
+// U = non-zeros whose B-row loads are issued together before their products are added (in
+// storage order, so the sums are the same bits).  The kernel above, measured in round 1,
+// stalls on every B load before the next one is issued: 2 loads in flight per warp -- 64 warps
+// x 2 x 256 B per ~1 us of loaded DRAM latency is the 5.0 TB/s it reached
+// (profiles/r1_ncu_spmm_v1.csv).  This variant (opt-in, SPRS_B200_SPMM_UNROLL=4, until timed)
+// puts 8 loads per warp in flight.
+template <typename P, int KV, int U>
+__global__ void __launch_bounds__(SPMM_NT)
+    spmm_rowmaj_unrolled_kernel(const P* __restrict__ indptr, const uint32_t* __restrict__ indices,
+                       const double* __restrict__ data, const double* __restrict__ B,
+                       uint64_t ldb, uint32_t k, double* __restrict__ C, uint64_t ldc,
+                       uint32_t rows, int accumulate) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp0 = (blockIdx.x * (uint64_t)SPMM_NT + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * SPMM_NT) >> 5;
+    for (uint64_t row = warp0; row < rows; row += nwarps) {
+        const uint64_t s = (uint64_t)indptr[row], e = (uint64_t)indptr[row + 1];
+        double* crow = C + row * ldc;
+        for (uint32_t c0 = 0; c0 < k; c0 += 32 * KV) {
+            double acc[KV];
+#pragma unroll
+            for (int q = 0; q < KV; ++q) {
+                const uint32_t c = c0 + lane + 32 * q;
+                acc[q] = (accumulate && c < k) ? crow[c] : 0.0;
+            }
+            for (uint64_t kk = s; kk < e; kk += 32) {
+                const bool in = kk + lane < e;
+                const uint32_t my_idx = in ? indices[kk + lane] : 0u;
+                const double my_val = in ? data[kk + lane] : 0.0;
+                const int n = (e - kk) < 32 ? (int)(e - kk) : 32;
+                for (int j = 0; j < n; j += U) {
+                    double v[U], b[U][KV];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {  // all loads of U non-zeros first
+                        const uint32_t col = __shfl_sync(0xffffffffu, my_idx, (j + u) & 31);
+                        v[u] = __shfl_sync(0xffffffffu, my_val, (j + u) & 31);
+                        const double* brow = B + (uint64_t)col * ldb;
+#pragma unroll
+                        for (int q = 0; q < KV; ++q) {
+                            const uint32_t c = c0 + lane + 32 * q;
+                            b[u][q] = (j + u < n && c < k) ? __ldg(brow + c) : 0.0;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)  // then the sums, in storage order
+                        if (j + u < n) {
+#pragma unroll
+                            for (int q = 0; q < KV; ++q) {
+                                const uint32_t c = c0 + lane + 32 * q;
+                                if (c < k) acc[q] = __dadd_rn(acc[q], __dmul_rn(v[u], b[u][q]));
+                            }
+                        }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < KV; ++q) {
+                const uint32_t c = c0 + lane + 32 * q;
+                if (c < k) crow[c] = acc[q];
+            }
+        }
+    }
+}
+
 // L2-blocked variant (opt-in, SPRS_B200_SPMM_PANEL=4|8|16|32; default off until it has been
 // measured): B is consumed in column panels of G columns so that the panel (B.rows x G
 // doubles, 64 MB for 1M rows at G = 8) stays resident in the 126 MB L2 while A is re-streamed
@@ -105,6 +168,14 @@ __global__ void __launch_bounds__(SPMM_NT)
         }
         if (live) crow[c] = acc;
     }
+}
+
+int spmm_unroll() {
+    static const int u = [] {
+        const char* e = getenv("SPRS_B200_SPMM_UNROLL");
+        return (e && atoi(e) == 4) ? 4 : 1;
+    }();
+    return u;
 }
 
 int spmm_panel_width() {
@@ -158,9 +229,16 @@ int spmm_rowmaj_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const doubl
     if (blocks > cap) blocks = cap;
     const unsigned grid = (unsigned)blocks;
 #define SPMM_LAUNCH(P, KV)                                                                    \
-    spmm_rowmaj_kernel<P, KV><<<grid, SPMM_NT, 0, s>>>(                                       \
-        (const P*)m->d_indptr, m->d_indices, m->d_data, d_b, ldb, (uint32_t)k, d_c, ldc,      \
-        (uint32_t)m->rows, accumulate)
+    do {                                                                                      \
+        if (spmm_unroll() == 4)                                                               \
+            spmm_rowmaj_unrolled_kernel<P, KV, 4><<<grid, SPMM_NT, 0, s>>>(                            \
+                (const P*)m->d_indptr, m->d_indices, m->d_data, d_b, ldb, (uint32_t)k, d_c,   \
+                ldc, (uint32_t)m->rows, accumulate);                                          \
+        else                                                                                  \
+            spmm_rowmaj_kernel<P, KV><<<grid, SPMM_NT, 0, s>>>(                            \
+                (const P*)m->d_indptr, m->d_indices, m->d_data, d_b, ldb, (uint32_t)k, d_c,   \
+                ldc, (uint32_t)m->rows, accumulate);                                          \
+    } while (0)
     if (m->indptr_bytes == 4) {
         if (k <= 32) SPMM_LAUNCH(uint32_t, 1);
         else if (k <= 64) SPMM_LAUNCH(uint32_t, 2);

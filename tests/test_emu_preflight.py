@@ -58,7 +58,7 @@ def test_emu_gpu_suite(emu, schedule):
     env = dict(os.environ, SPRS_B200_EMU="1", CUEMU_SCHEDULE=schedule)
     r = subprocess.run(
         [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "-q", "-x",
-         "-p", "no:cacheprovider", "-k", "not full_size and not test_cpp and not l2_blocked and not indptr64",
+         "-p", "no:cacheprovider", "-k", "not full_size and not test_cpp and not l2_blocked and not indptr64 and not unrolled_variant",
          "--deselect", os.path.join(ROOT, "tests", "test_gpu_multi.py")],
         capture_output=True, text=True, timeout=1500, env=env, cwd=ROOT)
     tail = "\n".join(r.stdout.splitlines()[-25:])
@@ -72,6 +72,6 @@ def test_emu_spmm_panel_and_indptr64_variants(emu):
     env = dict(os.environ, SPRS_B200_EMU="1")
     r = subprocess.run(
         [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_zz_late.py"), "-m", "gpu",
-         "-q", "-x", "-p", "no:cacheprovider", "-k", "l2_blocked or indptr64"],
+         "-q", "-x", "-p", "no:cacheprovider", "-k", "l2_blocked or indptr64 or unrolled_variant"],
         capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]

@@ -175,6 +175,26 @@ def test_spmm_l2_blocked_variant(panel):
     assert " passed" in tail
 
 
+def test_spmm_unrolled_variant():
+    """The opt-in SpMM variant with the B-row loads of four non-zeros in flight
+    (SPRS_B200_SPMM_UNROLL=4, read once per process): same bits as the oracle -- the
+    dense-product tests again in a child process with it on."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SPRS_B200_SPMM_UNROLL="4")
+    r = subprocess.run(
+        [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+         os.path.join(root, "tests", "test_gpu_spmv_spmm.py"),
+         os.path.join(root, "tests", "test_gpu_zz_late.py"),
+         "-k", "dense or wide_operator or spmm_small"],
+        capture_output=True, text=True, timeout=900, env=env, cwd=root)
+    tail = "\n".join(r.stdout.splitlines()[-15:])
+    assert r.returncode == 0, tail + r.stderr[-1500:]
+    assert " passed" in tail
+
+
 def test_indptr64_kernels():
     """The uint64-indptr instantiations (taken for nnz >= 2^32, far beyond test sizes) through
     the SPRS_B200_FORCE_INDPTR64 test hook: every SpMV / SpMM / conversion / solver test again
@@ -191,7 +211,7 @@ def test_indptr64_kernels():
         [os.path.join(root, "tests", f) for f in files] +
         ["-k", "not spgemm and not csc_csc and not csc_csr and not issue_99 and not "
                "structural_zeros and not csvec and not full_size and not test_cpp and not "
-               "l2_blocked and not indptr64"],
+               "l2_blocked and not indptr64 and not unrolled_variant"],
         capture_output=True, text=True, timeout=1500, env=env, cwd=root)
     tail = "\n".join(r.stdout.splitlines()[-15:])
     assert r.returncode == 0, tail + r.stderr[-1500:]

@@ -20,6 +20,7 @@ SPRS_B200_E2E_PIPELINE=2 timeout 600 python bench.py --steps 20 --warmup 5 --no-
 for pw in 8 4; do SPRS_B200_SPMM_PANEL=$pw timeout 300 python bench.py --workload spmm_rand_1m_k64 --steps 10 --warmup 3 --no-cpu-baseline > $out/bench_spmm_panel$pw.json 2> $out/bench_spmm_panel$pw.err; done
 timeout 600 python bench.py --workload spgemm_rmat_500k --steps 3 --warmup 1 > $out/bench_spgemm.json 2> $out/bench_spgemm.err; echo "spgemm exit $?" >> $out/summary.txt
 SPRS_B200_SPGEMM_V2=1 timeout 600 python bench.py --workload spgemm_rmat_500k --steps 3 --warmup 1 --no-cpu-baseline > $out/bench_spgemm_v2.json 2> $out/bench_spgemm_v2.err; echo "spgemm v2 exit $?" >> $out/summary.txt
+SPRS_B200_SPMM_UNROLL=4 timeout 300 python bench.py --workload spmm_rand_1m_k64 --steps 10 --warmup 3 --no-cpu-baseline > $out/bench_spmm_unroll4.json 2> $out/bench_spmm_unroll4.err
 timeout 300 python bench.py --workload spmm_rand_1m_k64 --steps 10 --warmup 3 > $out/bench_spmm.json 2> $out/bench_spmm.err; echo "spmm exit $?" >> $out/summary.txt
 # 3. BiCGSTAB: cost of a step next to its two SpMVs (config 5 matrix)
 timeout 600 python tools/time_bicgstab.py > $out/bicgstab.json 2> $out/bicgstab.err; echo "bicgstab exit $?" >> $out/summary.txt
@@ -36,7 +37,7 @@ cat $out/summary.txt
 tail -3 $out/pytest_gpu.txt $out/pytest_stream_push.txt
 tail -c 600 $out/bench_n1.json; echo; python - <<'PY'
 import json
-for f in ("bench_n1", "bench_n1_e2e_pipeline", "bench_n1_e2e_chunked", "bench_spmm", "bench_spmm_panel8", "bench_spmm_panel4"):
+for f in ("bench_n1", "bench_n1_e2e_pipeline", "bench_n1_e2e_chunked", "bench_spmm", "bench_spmm_unroll4", "bench_spmm_panel8", "bench_spmm_panel4"):
     try:
         d = json.loads(open("gpurun_out/r2_first/%s.json" % f).read().strip().splitlines()[-1])
         print(f, "ms/step %.3f" % d["ms_per_step"], "value %.1f" % d["value"], "e2e", d.get("e2e", {}).get("value"))
