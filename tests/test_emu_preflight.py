@@ -49,29 +49,39 @@ def test_emu_cpp_bicgstab(emu):
     assert "Iteration count 45" in out and "Hard restart count 3" in out
 
 
-@pytest.mark.parametrize("schedule", ["forward", "random:7"])
-def test_emu_gpu_suite(emu, schedule):
+def _pytest_child(env_extra, args, timeout):
+    env = dict(os.environ, SPRS_B200_EMU="1", **env_extra)
+    return subprocess.Popen([sys.executable, "-m", "pytest", "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"] + args,
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=ROOT), timeout
+
+
+def test_emu_gpu_suite(emu):
     """Every `-m gpu` test that needs only the C ABI (all but the full-size ones, the
     multi-GPU ones and the natively linked C++ drivers) passes on the emulator -- under the
     default thread schedule and under a shuffled one (any order is a legal CUDA schedule, so a
-    result that depends on it means a missing barrier)."""
-    env = dict(os.environ, SPRS_B200_EMU="1", CUEMU_SCHEDULE=schedule)
-    r = subprocess.run(
-        [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "-q", "-x",
-         "-p", "no:cacheprovider", "-k", "not full_size and not test_cpp and not l2_blocked and not indptr64 and not unrolled_variant",
-         "--deselect", os.path.join(ROOT, "tests", "test_gpu_multi.py")],
-        capture_output=True, text=True, timeout=1500, env=env, cwd=ROOT)
-    tail = "\n".join(r.stdout.splitlines()[-25:])
-    assert r.returncode == 0, tail + r.stderr[-2000:]
-    assert " passed" in tail and "failed" not in tail
-
-
-def test_emu_spmm_panel_and_indptr64_variants(emu):
-    """The opt-in L2-blocked SpMM kernel and the uint64-indptr kernel instantiations (each in
-    child processes with its environment switch)."""
-    env = dict(os.environ, SPRS_B200_EMU="1")
-    r = subprocess.run(
-        [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_zz_late.py"), "-m", "gpu",
-         "-q", "-x", "-p", "no:cacheprovider", "-k", "l2_blocked or indptr64 or unrolled_variant"],
-        capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
+    result that depends on it means a missing barrier) -- and so do the opt-in L2-blocked /
+    unrolled SpMM kernels and the uint64-indptr kernel instantiations (each of those in child
+    processes with its environment switch).  The three runs are independent processes and run
+    side by side to keep the CPU suite short."""
+    suite = [os.path.join(ROOT, "tests"), "-k",
+             "not full_size and not test_cpp and not l2_blocked and not indptr64 and not unrolled_variant",
+             "--deselect", os.path.join(ROOT, "tests", "test_gpu_multi.py")]
+    runs = {
+        "forward": _pytest_child({"CUEMU_SCHEDULE": "forward"}, suite, 1500),
+        "random:7": _pytest_child({"CUEMU_SCHEDULE": "random:7"}, suite, 1500),
+        "variants": _pytest_child({}, [os.path.join(ROOT, "tests", "test_gpu_zz_late.py"), "-k",
+                                       "l2_blocked or indptr64 or unrolled_variant"], 900),
+    }
+    failures = []
+    for name, (proc, timeout) in runs.items():
+        try:
+            out, err = proc.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            proc.kill()
+            out, err = proc.communicate()
+            failures.append("%s: timed out\n%s" % (name, out[-1500:]))
+            continue
+        tail = "\n".join(out.splitlines()[-25:])
+        if proc.returncode != 0 or " passed" not in tail or "failed" in tail:
+            failures.append("%s: exit %d\n%s\n%s" % (name, proc.returncode, tail, err[-2000:]))
+    assert not failures, "\n\n".join(failures)
