@@ -123,6 +123,20 @@ int sprs_b200_mul_acc_mat_vec_csc(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat
 int sprs_b200_mul_mat_vec(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, const double* x,
                           uint64_t x_len, double* y, uint64_t y_len);
 
+/* prod::csr_mul_csvec(lhs, rhs) (prod.rs:162-184): what `&A * &v` runs for a CSR matrix and a
+ * sparse vector (vec.rs:1104-1131; the README example, BASELINE config 1).  res[i] is the
+ * reference's sorted-merge dot of row i with v (CsVecBase::dot_acc, vec.rs:846-881): only
+ * entries present in BOTH patterns are multiplied, summed sequentially in ascending column
+ * order -- bit-identical to the reference, non-finite values included.  `res` is a dense host
+ * array of `rows` doubles (0.0 where no entries meet); the caller builds the CsVec by dropping
+ * exact zeros (prod.rs:178-180) and handles the dim == 0 early return (prod.rs:170-173).
+ * v_indices: ascending, unique, < dim (the CsVec invariant), 4 or 8 bytes wide.
+ * Errors: DIMENSION if dim != cols or res_len != rows, STORAGE if the mirror is not CSR,
+ * STRUCTURE for an index >= dim.                                                        */
+int sprs_b200_csr_mul_csvec(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, uint64_t dim,
+                            uint64_t v_nnz, const void* v_indices, int index_bytes,
+                            const double* v_data, double* res, uint64_t res_len);
+
 /* ---- sparse x dense matrix, HOST buffers; rhs/out are ndarray views, strides in
  * ELEMENTS (may be negative/any, like ArrayView).  out += lhs * rhs.
  * prod::csr_mulacc_dense_rowmaj prod.rs:189-214 ; csr_mulacc_dense_colmaj :274-298

@@ -388,15 +388,22 @@ Array2 operator*(const CsMatI<I, Iptr>& a, const Array2& b) {
     else prod::csc_mulacc_dense_colmaj(a, b, res);
     return res;
 }
-// `&A * &v`, v: CsVec (vec.rs:1104-1131 -> prod::csr_mul_csvec, prod.rs:162-184): the
-// sparse rhs is scattered into a dense x, one device SpMV, exact zeros dropped (:179).
+// `&A * &v`, v: CsVec (vec.rs:1104-1131).  CSR: prod::csr_mul_csvec (prod.rs:162-184), the
+// per-row sorted-merge dot on the device (csrc/csvec.cu, bit-identical), exact zeros dropped
+// (:178-180).  CSC: `self.mul(&rhs.col_view())`, the sparse-sparse product (vec.rs:1128).
 template <class I, class Iptr>
 CsVecI<I> operator*(const CsMatI<I, Iptr>& a, const CsVecI<I>& v) {
+    if (!a.is_csr()) {
+        auto col = CsMatI<I, Iptr>::new_csc({v.dim, 1}, {(Iptr)0, (Iptr)v.nnz()}, v.indices, v.data);
+        auto c = (a * col).to_csc();
+        return CsVecI<I>(a.rows(), c.indices(), c.data());
+    }
     if (v.dim == 0) return CsVecI<I>::empty(0);
     if (a.cols() != v.dim) throw Panic("Dimension mismatch");
-    Array1 x(v.dim, 0.0);
-    for (size_t k = 0; k < v.nnz(); ++k) x[(size_t)v.indices[k]] = v.data[k];
-    const Array1 y = a * x;
+    Context& ctx = Context::thread_default();
+    Array1 y(a.rows(), 0.0);
+    ctx.check(sprs_b200_csr_mul_csvec(ctx.handle(), a.device(), v.dim, v.nnz(), v.indices.data(),
+                                      (int)sizeof(I), v.data.data(), y.data(), y.size()));
     CsVecI<I> res = CsVecI<I>::empty(a.rows());
     for (size_t r = 0; r < y.size(); ++r)
         if (y[r] != 0.0) {

@@ -13,7 +13,7 @@
 //! device failures are `LinalgError::ThirdPartyError(code, msg)` (errors.rs:70).
 use ndarray::{Array1, Array2, ArrayBase, ArrayView1, Data, Ix1, Ix2, ShapeBuilder};
 use sprs::errors::LinalgError;
-use sprs::{CsMatI, CsMatViewI, SpIndex};
+use sprs::{CsMatI, CsMatViewI, CsVecI, SpIndex};
 use sprs_b200_sys as ffi;
 use std::ffi::CStr;
 use std::ops::Mul;
@@ -94,6 +94,29 @@ impl<'a, 'b, I: SpIndex, Iptr: SpIndex, DS: Data<Elem = f64>> Mul<&'b ArrayBase<
                                        y.as_mut_ptr(), y.len() as u64)
         })).expect("sprs_b200 device error");
         y
+    }
+}
+
+// `&A * &v`, v sparse (vec.rs:1104-1131 -> prod::csr_mul_csvec, prod.rs:162-184): the per-row
+// sorted-merge dot runs on the device (bit-identical); zeros are dropped here (prod.rs:178-180).
+// A CSC lhs goes through the sparse-sparse product with `rhs.col_view()` like the reference.
+impl<'a, 'b, I: SpIndex, Iptr: SpIndex> Mul<&'b CsVecI<f64, I>> for &'a DeviceCsMat<I, Iptr> {
+    type Output = CsVecI<f64, I>;
+    fn mul(self, rhs: &'b CsVecI<f64, I>) -> CsVecI<f64, I> {
+        if rhs.dim() == 0 { return CsVecI::empty(0); }
+        assert_eq!(self.host.cols(), rhs.dim(), "Dimension mismatch");
+        assert!(self.host.is_csr(), "CSC x CsVec: use &a * &DeviceCsMat::new(rhs.col_view().to_owned())");
+        let mut y = vec![0f64; self.host.rows()];
+        CTX.with(|c| check(c.0, unsafe {
+            ffi::sprs_b200_csr_mul_csvec(c.0, self.dev, rhs.dim() as u64, rhs.nnz() as u64,
+                rhs.indices().as_ptr() as *const c_void, std::mem::size_of::<I>() as i32,
+                rhs.data().as_ptr(), y.as_mut_ptr(), y.len() as u64)
+        })).expect("sprs_b200 device error");
+        let mut res = CsVecI::empty(self.host.rows());
+        for (row, val) in y.into_iter().enumerate() {
+            if val != 0.0 { res.append(row, val); }
+        }
+        res
     }
 }
 

@@ -521,16 +521,23 @@ class prod:
 
     @staticmethod
     def csr_mul_csvec(lhs, rhs):
-        """prod.rs:162-184.  On the device the sparse rhs is scattered into a dense x
-        (structural zeros contribute exact 0 terms), one SpMV, exact zeros dropped
-        (prod.rs:179).  Differs from the sorted-merge dot only for non-finite A
-        entries opposite a structural zero of rhs."""
+        """prod.rs:162-184: row i of the result is the sorted-merge dot of row i with rhs
+        (vec.rs:846-881) -- only entries present in both patterns are multiplied, summed in
+        ascending column order (csrc/csvec.cu, bit-identical) -- and exact zeros are
+        dropped (prod.rs:178-180)."""
         if rhs.dim == 0:
             return CsVec.empty(0)
         if lhs.cols() != rhs.dim:
             raise SprsPanic("Dimension mismatch")
-        y = _csmat_mul_dense_vec(lhs, rhs.to_dense())
-        nz = np.nonzero(y != 0.0)[0]
+        if not lhs.is_csr():
+            raise SprsPanic("Storage mismatch")
+        ctx = lhs.context()
+        vi = np.ascontiguousarray(rhs.indices, dtype=np.uint64)
+        vd = np.ascontiguousarray(rhs.data, dtype=np.float64)
+        y = np.empty(lhs.rows())
+        ctx.check(ctx.lib.sprs_b200_csr_mul_csvec(ctx.h, lhs.device().h, rhs.dim, vi.size,
+                                                  _ptr(vi), 8, _ptr(vd), _ptr(y), y.size))
+        nz = np.nonzero(y != 0.0)[0]  # `val != N::zero()`: NaN is kept, -0.0 is dropped
         return CsVec(lhs.rows(), nz, y[nz])
 
 

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "..", "..", "sprs_b200", "csrc")
 FILES = ["api.cu", "spmv.cu", "spmm.cu", "spgemm.cu", "transpose.cu", "gen.cu", "peer.cu",
-         "solver.cu", "common.cuh", "scan.cuh"]
+         "solver.cu", "csvec.cu", "common.cuh", "scan.cuh"]
 
 
 def match_back(s, end):

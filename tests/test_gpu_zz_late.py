@@ -216,3 +216,54 @@ def test_indptr64_kernels():
     tail = "\n".join(r.stdout.splitlines()[-15:])
     assert r.returncode == 0, tail + r.stderr[-1500:]
     assert " passed" in tail
+
+
+# ---------------------------------------------------------------- CSR x sparse vector
+def _csvec_case(rng, rows, cols, per_row, v_nnz, idx_dtype=np.uint32):
+    ip, ind, d = rand_csr(rng, rows, cols, per_row, idx_dtype, empty_frac=0.1)
+    vi = np.sort(rng.choice(cols, v_nnz, replace=False))
+    vd = rng.standard_normal(v_nnz)
+    return ip, ind, d, vi, vd
+
+
+@pytest.mark.parametrize("shape", [(300, 400, 12, 90), (2000, 700, 40, 350), (64, 5000, 300, 4000),
+                                   (50, 50, 50, 0), (1, 1, 1, 1)])
+def test_csr_mul_csvec_bit_exact_vs_oracle(sp, O, shape):
+    """prod.rs:162-184 / vec.rs:846-881: sequential sum over the pattern intersection in
+    ascending column order -- the device result is the oracle's to the last bit, and rows
+    whose dot is exactly zero (or that meet nothing) are dropped."""
+    rows, cols, per_row, v_nnz = shape
+    rng = np.random.default_rng(rows * 7 + cols)
+    ip, ind, d, vi, vd = _csvec_case(rng, rows, cols, min(per_row, cols), v_nnz)
+    for idx in (np.uint32, np.uint64):
+        a = sp.CsMat.new((rows, cols), ip.astype(idx), ind.astype(idx), d)
+        res = a * sp.CsVec(cols, vi, vd)
+        oi, od = O.csr_mul_csvec(ip, ind, d, vi, vd)
+        assert res.dim == rows
+        assert np.array_equal(res.indices, oi.astype(np.int64))
+        assert np.array_equal(res.data.view(np.uint64), od.view(np.uint64))
+    # the free function of prod.rs, and its contract checks in the reference's order
+    assert sp.prod.csr_mul_csvec(a, sp.CsVec(cols, vi, vd)) == res
+    with pytest.raises(sp.SprsPanic, match="Dimension mismatch"):
+        sp.prod.csr_mul_csvec(a, sp.CsVec(cols + 1, vi, vd))
+    assert sp.prod.csr_mul_csvec(a, sp.CsVec(0, [], [])) == sp.CsVec.empty(0)
+
+
+def test_csr_mul_csvec_structural_zeros_non_finite(sp, O):
+    """An A entry opposite a STRUCTURAL zero of v takes no part in the merge dot
+    (vec.rs:862-876): an Inf/NaN stored there leaves the row finite, where a dense x with
+    explicit zeros would give Inf*0 = NaN.  Explicitly stored zeros of v do take part; NaN
+    results are kept (`val != N::zero()`), -0.0 and cancelled sums are dropped."""
+    ip = np.array([0, 3, 5, 7, 9, 9, 10], dtype=np.uint32)
+    ind = np.array([0, 1, 3,  1, 2,  0, 3,  2, 4,  4], dtype=np.uint32)
+    d = np.array([2.0, np.inf, 5.0,  np.nan, 1.5,  1.0, -1.0,  np.inf, 7.0,  -0.0])
+    vi, vd = np.array([0, 2, 3, 4]), np.array([3.0, 0.0, 3.0, 1.0])   # v[2] is a STORED zero
+    a = sp.CsMat.new((6, 5), ip, ind, d)
+    res = a * sp.CsVec(5, vi, vd)
+    oi, od = O.csr_mul_csvec(ip, ind, d, vi, vd)
+    assert np.array_equal(res.indices, oi.astype(np.int64))
+    assert np.array_equal(res.data.view(np.uint64), od.view(np.uint64))
+    # row 0: 2*3 + 5*3 (Inf at column 1 skipped); row 1: 1.5*0 = 0 dropped (NaN at column 1
+    # skipped); row 2: 3 - 3 = 0 dropped; row 3: Inf*0 + 7 = NaN kept; row 4 empty; row 5: -0.0
+    assert res.indices.tolist() == [0, 3]
+    assert res.data[0] == 21.0 and np.isnan(res.data[1])
