@@ -233,13 +233,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "overlap", "fused", "push", "stream", "chunked", "nccl"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "overlap", "fused", "push", "stream", "chunked", "mcast", "mcast-push", "nccl"],
                     help="N>1 all-gather of y: 'overlap' = row block cut into chunks, each "
                          "chunk's y slice pushed to the peers by DMA copies on a second stream "
                          "while the next chunk computes; 'fused' = the SpMV kernel itself stores "
                          "every finished row into the peers' buffers; 'nccl' = one NCCL "
                          "all_gather after the kernel")
     ap.add_argument("--chunks", type=int, default=4)
+    ap.add_argument("--barrier", default="nccl", choices=["nccl", "symm"],
+                    help="mcast modes: barrier after the stores -- 1-element NCCL all_reduce, or "
+                         "the signal-pad barrier of the symmetric-memory handle")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -249,7 +252,7 @@ def main():
     import sprs_b200 as sp
     from sprs_b200 import generate as G
     from sprs_b200.dist import (FusedAllGatherSpMV, OverlappedAllGatherSpMV, PushAllGatherSpMV,
-                                StreamAllGatherSpMV, ChunkedPushAllGatherSpMV,
+                                StreamAllGatherSpMV, ChunkedPushAllGatherSpMV, McastAllGatherSpMV,
                                 RowPartitionedSpMV, fit_row_cost, nnz_balanced_bounds)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -313,12 +316,17 @@ def main():
         # with the bytes pushed (~0.14 ms at 40 MB, ~0.22 ms at 60 MB), while at 8 GPUs the
         # fused kernel measured 0.82 ms against 0.61 ms of pure compute -> fused from 6 GPUs up
         args.exchange = "fused" if world >= 6 else "push"
-    fused = world > 1 and args.exchange in ("fused", "overlap", "push", "stream", "chunked")
+    fused = world > 1 and args.exchange in ("fused", "overlap", "push", "stream", "chunked",
+                                            "mcast", "mcast-push")
 
     def make_op(a_blk, bnds):
         if world > 1 and args.exchange == "overlap":
             o = OverlappedAllGatherSpMV(ctx, a_blk, bnds, rank, world, n, dist, dev,
                                         chunks=args.chunks, row_cost=row_cost)
+        elif fused and args.exchange.startswith("mcast"):
+            o = McastAllGatherSpMV(ctx, a_blk.mirror, bnds, rank, world, n, dist, dev,
+                                   mode="push" if args.exchange == "mcast-push" else "fused",
+                                   barrier=args.barrier)
         elif fused:
             cls = {"push": PushAllGatherSpMV, "stream": StreamAllGatherSpMV,
                    "chunked": ChunkedPushAllGatherSpMV}.get(
@@ -510,6 +518,12 @@ def main():
                                       "chunk's event a side stream pushes the rows it completed "
                                       "into the peer buffers (own put kernel over NVLink) + "
                                       "1-element NCCL all_reduce barrier",
+                           "mcast": "all-gather of y fused into the SpMV kernel through the "
+                                    "NVSwitch multicast address of y (one store per finished row, "
+                                    "replicated by the switch) + barrier (%s)" % args.barrier,
+                           "mcast-push": "SpMV, then one push kernel storing this rank's y slice "
+                                         "to the NVSwitch multicast address of y + barrier (%s)"
+                                         % args.barrier,
                            "nccl": "NCCL all_gather(y), unequal slices"}[args.exchange]),
                        "l2_policy": "inputs (%.1f GB) exceed L2 (126 MB); no flush needed" %
                                     (alg_bytes / 1e9),

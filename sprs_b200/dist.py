@@ -295,6 +295,107 @@ class ChunkedPushAllGatherSpMV(FusedAllGatherSpMV):
             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 
 
+class McastAllGatherSpMV:
+    """Row-partitioned y = A x whose all-gather goes through the NVSwitch MULTICAST object of
+    y (NVLS): every rank's full-length y is one symmetric allocation bound to a multicast
+    address, and a store to that address is replicated by the switch into the y of ALL ranks.
+    A finished row therefore leaves the GPU ONCE instead of once per peer: at 8 GPUs the
+    NVLink egress of a rank drops from 7 x 10 MB to 10 MB per step.
+
+    Allocation, the exchange of the memory handles between the processes and the multicast
+    binding are `torch.distributed._symmetric_memory` (device-memory plumbing); the stores are
+    this library's kernels, unchanged: `multimem.st` and `st.global` on a multicast address
+    are the same SASS (STG.E.64), so the multicast pointer is simply the second y target of
+
+      * mode "fused": the SpMV kernel itself (sprs_b200_spmv_allgather_dev with targets
+        [local y, multicast y]) -- one extra store per finished row instead of world-1;
+      * mode "push": the plain SpMV into the local y, then the put kernel copying this
+        rank's slice to the multicast address (sprs_b200_peer_push_dev with one "peer").
+
+    Barrier after the stores: the 1-element NCCL all-reduce of the other modes, or
+    (barrier="symm") the signal-pad barrier of the symmetric-memory handle, a device-side
+    flag exchange in peer memory with no NCCL kernel.
+    Fails loudly when the devices have no multicast support (no silent fallback).
+    Not yet run on hardware (written after round 1's GPU budget): opt-in
+    (`bench.py --exchange mcast|mcast-push`), to be measured by tools/r2_scale_probe.sh."""
+
+    def __init__(self, ctx, mirror, bounds, rank, world, n, dist, device, mode="fused",
+                 barrier="nccl", group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        from . import generate as G
+        from .sparse import ThirdPartyError
+        if mode not in ("fused", "push") or barrier not in ("nccl", "symm"):
+            raise ValueError("mode: fused|push, barrier: nccl|symm")
+        self.ctx, self.mirror, self.bounds, self.rank, self.world = ctx, mirror, bounds, rank, world
+        self.dist, self.n, self.mode, self.barrier = dist, n, mode, barrier
+        grp = group if group is not None else dist.group.WORLD
+        buf = symm.empty(max(n, 2), dtype=torch.float64, device=device)
+        self._hdl = symm.rendezvous(buf, grp)
+        mc = int(self._hdl.multicast_ptr or 0)
+        if world > 1 and mc == 0:
+            raise ThirdPartyError(0, "NVSwitch multicast is not available for this process group "
+                                     "(symmetric-memory handle has no multicast_ptr)")
+        self._buf = buf
+        self.y = buf[:n]
+        self.y.zero_()
+        self._own = buf.data_ptr()
+        self._mc = mc
+        ptrs = [self._own] + ([mc] if world > 1 else [])
+        self._targets = (C.c_void_p * len(ptrs))(*ptrs)
+        self._mc_only = (C.c_void_p * 1)(mc)
+        self._flag = torch.zeros(1, device=device)
+        G._sync()
+        dist.barrier()
+
+    @property
+    def rows_local(self):
+        return self.bounds[self.rank + 1] - self.bounds[self.rank]
+
+    def compute(self, x):
+        import ctypes as C
+        from . import generate as G
+        ctx = self.ctx
+        s = G._stream_ptr()
+        r0 = self.bounds[self.rank]
+        if self.mode == "fused":
+            ctx.check(ctx.lib.sprs_b200_spmv_allgather_dev(
+                ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()), r0, len(self._targets),
+                self._targets, 0, s))
+        else:
+            ctx.check(ctx.lib.sprs_b200_spmv_dev(ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()),
+                                                 C.c_void_p(self._own + 8 * r0), 0, s))
+
+    def exchange(self):
+        import ctypes as C
+        from . import generate as G
+        if self.world <= 1:
+            return
+        ctx = self.ctx
+        if self.mode == "push":
+            s = G._stream_ptr()
+            ctx.check(ctx.lib.sprs_b200_peer_push_dev(ctx.h, C.c_void_p(self._own),
+                                                      self.bounds[self.rank], self.rows_local, 1,
+                                                      self._mc_only, s))
+        if self.barrier == "symm":
+            self._hdl.barrier(channel=0)   # stream-ordered, after this rank's stores
+        else:
+            self.dist.all_reduce(self._flag)
+
+    def step(self, x):
+        self.compute(x)
+        self.exchange()
+        return self.y
+
+    def close(self):
+        from . import generate as G
+        G._sync()
+        if self.world > 1:
+            self.dist.barrier()
+        self.y = self._buf = self._hdl = None
+
+
 class OverlappedAllGatherSpMV:
     """Row-partitioned y = A x with the all-gather of y overlapped with the compute.
 

@@ -123,3 +123,90 @@ def test_chunked_push_hub_rows_degenerate_shapes(sp, monkeypatch):
     _run_case(sp, monkeypatch, empty, 50, 10, None, chunked=4)
     one_target = rand_csr(rng, 500, 400, 30)
     _run_case(sp, monkeypatch, one_target, 500, 400, None, n_targets=1, chunked=3)
+
+
+# ---------------------------------------------------------------- NVSwitch multicast exchange
+class _FakeSymmHandle:
+    """Stand-in for torch's symmetric-memory handle on ONE device: the "multicast" address is
+    a second ordinary buffer (a store to a real multicast address lands in every rank's y;
+    here it lands in that buffer), which checks everything McastAllGatherSpMV does itself --
+    target order, row offsets, put-kernel arguments, barrier choice."""
+
+    def __init__(self, mc_buf):
+        self.mc_buf = mc_buf
+        self.multicast_ptr = mc_buf.data_ptr()
+        self.barriers = 0
+
+    def barrier(self, channel=0):
+        self.barriers += 1
+
+
+class _FakeDist:
+    class group:
+        WORLD = "world"
+
+    def __init__(self):
+        self.all_reduces = 0
+
+    def barrier(self):
+        pass
+
+    def all_reduce(self, t):
+        self.all_reduces += 1
+
+
+@pytest.mark.parametrize("mode,barrier", [("fused", "nccl"), ("push", "symm"), ("fused", "symm")])
+def test_mcast_allgather_host_logic(sp, monkeypatch, mode, barrier):
+    import torch
+    import torch.distributed._symmetric_memory as symm
+    from sprs_b200 import generate as G
+    from sprs_b200.dist import McastAllGatherSpMV
+    ctx = sp.Context.default()
+    tdev = G._device(ctx)
+    rng = np.random.default_rng(5)
+    n = 3000
+    csr = rand_csr(rng, n, n, 30, skew=True)
+    bounds = [0, 1100, n]                       # this process is rank 1 of 2: rows [1100, n)
+    r0, r1 = bounds[1], bounds[2]
+    ip = csr[0].astype(np.int64)
+    s0, s1 = int(ip[r0]), int(ip[r1])
+    a = sp.CsMat((r1 - r0, n), (ip[r0:r1 + 1] - s0).astype(np.uint32), csr[1][s0:s1], csr[2][s0:s1])
+    mirror = a.device()
+    handles = []
+
+    def fake_empty(size, dtype=None, device=None):
+        return torch.full((size,), -777.0, dtype=dtype, device=tdev)
+
+    def fake_rendezvous(t, group):
+        assert group == "world"
+        handles.append(_FakeSymmHandle(torch.full((t.numel(),), -777.0, dtype=t.dtype, device=tdev)))
+        return handles[-1]
+
+    monkeypatch.setattr(symm, "empty", fake_empty)
+    monkeypatch.setattr(symm, "rendezvous", fake_rendezvous)
+    fd = _FakeDist()
+    op = McastAllGatherSpMV(ctx, mirror, bounds, 1, 2, n, fd, tdev, mode=mode, barrier=barrier)
+    x = G.normal_vector(ctx, n, seed=3)
+    ref = torch.zeros(r1 - r0, device=tdev, dtype=torch.float64)
+    ctx.check(ctx.lib.sprs_b200_spmv_dev(ctx.h, mirror.h, C.c_void_p(x.data_ptr()),
+                                         C.c_void_p(ref.data_ptr()), 0, G._stream_ptr()))
+    for _ in range(2):
+        op.y.fill_(-1.0)
+        handles[0].mc_buf.fill_(-1.0)
+        y = op.step(x)
+        G._sync()
+        want = ref.cpu().numpy()
+        own, mc = y.cpu().numpy(), handles[0].mc_buf.cpu().numpy()
+        assert np.array_equal(own[r0:r1], want) and np.array_equal(mc[r0:r1], want)
+        assert np.all(own[:r0] == -1.0) and np.all(mc[:r0] == -1.0)   # other ranks' rows untouched
+    assert (handles[0].barriers, fd.all_reduces) == ((2, 0) if barrier == "symm" else (0, 2))
+    op.close()
+    # no multicast object -> loud failure, never a silent unicast fallback
+    def rendezvous_without_mc(t, group):
+        h = _FakeSymmHandle(t)
+        h.multicast_ptr = 0
+        return h
+
+    monkeypatch.setattr(symm, "rendezvous", rendezvous_without_mc)
+    with pytest.raises(sp.ThirdPartyError, match="multicast"):
+        McastAllGatherSpMV(ctx, mirror, bounds, 1, 2, n, fd, tdev)
