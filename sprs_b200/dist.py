@@ -1,4 +1,4 @@
-"""Row-partitioned multi-GPU SpMV: host-side logic (one process per GPU).
+"""Row-partitioned multi-GPU products (SpMV, SpMM, SpGEMM): host-side logic, one process per GPU.
 
 The path shards by contiguous row blocks (CsMatBase::slice_outer, sprs/src/sparse/
 slicing.rs:65-89 -- the same primitive the reference's SpGEMM driver uses to chunk rows,
@@ -103,6 +103,19 @@ def fit_row_cost(samples):
     return float(min(max(beta / alpha, 0.0), 64.0))
 
 
+def all_gather_uneven(dist, views, rank, group=None):
+    """In-place all-gather of slices with unequal lengths: views[g] is rank g's slice of one
+    buffer every rank holds; views[rank] is filled, the others are received."""
+    if dist.get_backend(group) == "nccl":
+        # torch's NCCL backend runs one grouped-broadcast kernel for unequal lengths
+        dist.all_gather(views, views[rank], group=group)
+    else:  # gloo (CPU tests) has no uneven all_gather: one broadcast per slice
+        works = [dist.broadcast(views[g], src=g, group=group, async_op=True)
+                 for g in range(len(views)) if views[g].numel()]
+        for w in works:
+            w.wait()
+
+
 class RowPartitionedSpMV:
     """y = A x with A split by rows over the ranks of a process group.
 
@@ -124,21 +137,123 @@ class RowPartitionedSpMV:
         self.local_spmv(x, self.views[self.rank])
 
     def exchange(self):
-        if self.world <= 1:
-            return
-        if self.dist.get_backend(self.group) == "nccl":
-            # unequal slice lengths: torch's NCCL backend runs one grouped-broadcast kernel
-            self.dist.all_gather(self.views, self.views[self.rank], group=self.group)
-        else:  # gloo (CPU tests) has no uneven all_gather: one broadcast per slice
-            works = [self.dist.broadcast(self.views[g], src=g, group=self.group, async_op=True)
-                     for g in range(self.world) if self.views[g].numel()]
-            for w in works:
-                w.wait()
+        if self.world > 1:
+            all_gather_uneven(self.dist, self.views, self.rank, self.group)
 
     def step(self, x):
         self.compute(x)
         self.exchange()
         return self.y
+
+
+class RowPartitionedSpMM:
+    """C = A B (csr_mulacc_dense_rowmaj, prod.rs:189-214) with A split by rows:
+    B is replicated, rank g computes rows [bounds[g], bounds[g+1]) of the row-major C into
+    its slice of the full C; with gather=True the slices (unequal row counts x k) are
+    all-gathered so that every rank holds C (what a caller feeding C into the next product
+    needs); gather=False leaves C row-distributed.  Rows are independent, so every row is
+    the same sequential sum as on one GPU: results are bit-identical to the 1-GPU product.
+
+    local_spmm(b, c_slice) computes this rank's block (c_slice: rows_local x k view)."""
+
+    def __init__(self, bounds, rank, world, c_full, local_spmm, dist=None, group=None,
+                 gather=True):
+        self.bounds, self.rank, self.world = bounds, rank, world
+        self.c = c_full
+        self.views = [c_full[bounds[g]:bounds[g + 1]] for g in range(world)]
+        self.local_spmm = local_spmm
+        self.dist, self.group, self.gather = dist, group, gather
+
+    @property
+    def rows_local(self):
+        return self.bounds[self.rank + 1] - self.bounds[self.rank]
+
+    def compute(self, b):
+        self.local_spmm(b, self.views[self.rank])
+
+    def exchange(self):
+        if self.world > 1 and self.gather:
+            # contiguous row-major C: a row slice is one contiguous piece of memory
+            flat = [v.reshape(-1) for v in self.views]
+            all_gather_uneven(self.dist, flat, self.rank, self.group)
+
+    def step(self, b):
+        self.compute(b)
+        self.exchange()
+        return self.c
+
+
+class RowPartitionedSpGEMM:
+    """C = A B (smmp::mul_csr_csr, smmp.rs:196-237) with A split by rows and B replicated --
+    the reference's own parallel decomposition (contiguous row chunks of A, smmp.rs:277-296,
+    each producing its own indptr / indices / data piece, concatenated with an indptr offset
+    by the running nnz, smmp.rs:320-331 and :384-404) with GPUs in place of threads.
+
+    local_spgemm() returns this rank's piece (indptr_local zero-based with rows_local+1
+    entries, indices_local, data_local) as torch tensors.  product() exchanges the piece
+    sizes, offsets the local indptr by the exclusive scan of nnz(C_g) and, with gather=True,
+    all-gathers the three arrays so every rank holds the full CSR of C; with gather=False it
+    returns this rank's rows with the GLOBAL indptr values (a row-distributed C).
+    Pieces are concatenated untouched: indptr / indices are bit-exact and values identical
+    to the single-GPU product."""
+
+    def __init__(self, bounds, rank, world, local_spgemm, dist=None, group=None, gather=True):
+        self.bounds, self.rank, self.world = bounds, rank, world
+        self.local_spgemm = local_spgemm
+        self.dist, self.group, self.gather = dist, group, gather
+
+    @property
+    def rows_local(self):
+        return self.bounds[self.rank + 1] - self.bounds[self.rank]
+
+    def piece_offsets(self, nnz_local, device):
+        """(offsets, total): offsets[g] = sum of nnz(C_h) for h < g, from an all-gather of the
+        piece sizes (one int64 per rank)."""
+        import torch
+        mine = torch.tensor([int(nnz_local)], dtype=torch.int64, device=device)
+        if self.world > 1:
+            allc = [torch.empty_like(mine) for _ in range(self.world)]
+            self.dist.all_gather(allc, mine, group=self.group)
+            counts = [int(c.item()) for c in allc]
+        else:
+            counts = [int(nnz_local)]
+        offsets = [0]
+        for c in counts:
+            offsets.append(offsets[-1] + c)
+        return offsets[:-1], offsets[-1], counts
+
+    def product(self):
+        import torch
+        ip_l, ind_l, dat_l = self.local_spgemm()
+        if ip_l.numel() != self.rows_local + 1:
+            raise ValueError("local indptr must have rows_local + 1 entries")
+        ip64 = ip_l.to(torch.int64)
+        if ip_l.dtype == torch.int32:  # int32 storage of u32 values (generate.DeviceCsr)
+            ip64 &= 0xFFFFFFFF
+        ip64 = ip64 - ip64[0]
+        nnz_l = int(ip64[-1].item())
+        offsets, total, counts = self.piece_offsets(nnz_l, ip_l.device)
+        n = self.bounds[-1]
+        # global indptr in the local index type unless nnz(C) needs 64 bits (the device
+        # mirror makes the same switch at 2^32, common.cuh)
+        ptr_dtype = ip_l.dtype if total < 2 ** 32 or ip_l.dtype == torch.int64 else torch.int64
+        mine = (ip64 + offsets[self.rank]).to(ptr_dtype)
+        if not self.gather or self.world == 1:
+            return mine, ind_l, dat_l, total
+        indptr = torch.empty(n + 1, dtype=ptr_dtype, device=ip_l.device)
+        indices = torch.empty(total, dtype=ind_l.dtype, device=ind_l.device)
+        data = torch.empty(total, dtype=dat_l.dtype, device=dat_l.device)
+        ip_views = [indptr[self.bounds[g]:self.bounds[g + 1]] for g in range(self.world)]
+        ip_views[self.rank].copy_(mine[:-1])
+        indptr[n] = total
+        ends = offsets[1:] + [total]
+        ind_views = [indices[offsets[g]:ends[g]] for g in range(self.world)]
+        dat_views = [data[offsets[g]:ends[g]] for g in range(self.world)]
+        ind_views[self.rank].copy_(ind_l)
+        dat_views[self.rank].copy_(dat_l)
+        for views in (ip_views, ind_views, dat_views):
+            all_gather_uneven(self.dist, views, self.rank, self.group)
+        return indptr, indices, data, total
 
 
 class _DevPtr:

@@ -183,3 +183,42 @@ def spmm_rowmaj(ctx, a, b, c, accumulate=False):
     ctx.check(ctx.lib.sprs_b200_spmm_rowmaj_dev(ctx.h, m.h, _dptr(b), b.stride(0), k, _dptr(c),
                                                 c.stride(0), int(accumulate), _stream_ptr()))
     return c
+
+
+class _DevArray:
+    """Zero-copy torch view of a raw device allocation (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr,
+                                         "data": (ptr, False), "version": 2}
+
+
+def spgemm(ctx, a, b):
+    """C = A B on the device (smmp::mul_csr_csr: symbolic, then numeric into a new mirror).
+    Returns (mirror, indptr, indices, data): the DeviceCsMat that owns C and zero-copy torch
+    views of its arrays (int32 storage of u32 values; int64 indptr when nnz(C) >= 2^32),
+    valid while the mirror is alive -- what RowPartitionedSpGEMM's local_spgemm returns."""
+    ma = a.mirror if isinstance(a, DeviceCsr) else a
+    mb = b.mirror if isinstance(b, DeviceCsr) else b
+    lib = ctx.lib
+    plan, nnz_c, cm = C.c_void_p(), C.c_uint64(), C.c_void_p()
+    ctx.check(lib.sprs_b200_spgemm_symbolic(ctx.h, ma.h, mb.h, C.byref(plan), C.byref(nnz_c)))
+    try:
+        ctx.check(lib.sprs_b200_spgemm_numeric_dev(ctx.h, plan, C.byref(cm)))
+    finally:
+        lib.sprs_b200_spgemm_free(plan)
+    mirror = DeviceCsMat(ctx, cm)
+    d_ip, d_ind, d_dat, ipb = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int()
+    ctx.check(lib.sprs_b200_csmat_device_arrays(cm, C.byref(d_ip), C.byref(ipb), C.byref(d_ind),
+                                                C.byref(d_dat)))
+    dev = _device(ctx)
+    rows, nnz = mirror.rows, int(nnz_c.value)
+    indptr = torch.as_tensor(_DevArray(d_ip.value, rows + 1, "<i4" if ipb.value == 4 else "<i8"),
+                             device=dev)
+    if nnz:
+        indices = torch.as_tensor(_DevArray(d_ind.value, nnz, "<i4"), device=dev)
+        data = torch.as_tensor(_DevArray(d_dat.value, nnz, "<f8"), device=dev)
+    else:
+        indices = torch.empty(0, dtype=torch.int32, device=dev)
+        data = torch.empty(0, dtype=torch.float64, device=dev)
+    return mirror, indptr, indices, data

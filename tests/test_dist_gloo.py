@@ -108,3 +108,86 @@ def test_row_partitioned_spmv_gloo_world2():
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res)
     assert res[0][2] == res[1][2] and 0 < res[0][2][1] < 3000
+
+
+def _worker_spmm_spgemm(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from conftest import rand_csr
+    from oracle import oracle as O
+    from sprs_b200.dist import RowPartitionedSpGEMM, RowPartitionedSpMM, nnz_balanced_bounds
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(77)  # same operands on every rank
+        n, m, k = 1500, 900, 24
+        ip, ind, d = rand_csr(rng, n, m, 12, skew=True, empty_frac=0.2)
+        bounds = nnz_balanced_bounds(ip, world)
+        r0, r1 = bounds[rank], bounds[rank + 1]
+        s0, s1 = int(ip[r0]), int(ip[r1])
+        lip, lind, ld = (ip[r0:r1 + 1] - s0).astype(np.uint32), ind[s0:s1], d[s0:s1]
+
+        # ---- SpMM: rows of C are independent -> bit-identical to the one-process product
+        b = rng.standard_normal((m, k))
+        ref = np.zeros((n, k))
+        O.csr_mulacc_dense_rowmaj(ip, ind, d, b, ref)
+
+        def local_spmm(bt, c_slice):
+            out = np.zeros((r1 - r0, k))
+            O.csr_mulacc_dense_rowmaj(lip, lind, ld, bt.numpy(), out)
+            c_slice.copy_(torch.from_numpy(out))
+
+        c = torch.full((n, k), float("nan"), dtype=torch.float64)
+        got = RowPartitionedSpMM(bounds, rank, world, c, local_spmm, dist=dist).step(
+            torch.from_numpy(b)).numpy()
+        ok = bool(np.array_equal(got, ref))
+        c2 = torch.full((n, k), float("nan"), dtype=torch.float64)
+        part = RowPartitionedSpMM(bounds, rank, world, c2, local_spmm, dist=dist,
+                                  gather=False).step(torch.from_numpy(b)).numpy()
+        ok = ok and bool(np.array_equal(part[r0:r1], ref[r0:r1]))
+        ok = ok and bool(np.isnan(np.delete(part, np.s_[r0:r1], axis=0)).all())
+
+        # ---- SpGEMM: pieces concatenated with an indptr offset (smmp.rs:320-331, 384-404)
+        bip, bind, bd = rand_csr(rng, m, 1100, 9, empty_frac=0.1)
+        cip, cind, cd = O.mul_csr_csr((n, m), (ip, ind, d), (m, 1100), (bip, bind, bd), threads=1)
+
+        def local_spgemm():
+            pip, pind, pd = O.mul_csr_csr((r1 - r0, m), (lip, lind, ld), (m, 1100), (bip, bind, bd), threads=1)
+            return (torch.from_numpy(pip.astype(np.int32)), torch.from_numpy(pind.astype(np.int32)),
+                    torch.from_numpy(pd))
+
+        gip, gind, gd, total = RowPartitionedSpGEMM(bounds, rank, world, local_spgemm,
+                                                    dist=dist).product()
+        ok = ok and total == int(cip[-1])
+        ok = ok and bool(np.array_equal(gip.numpy(), cip.astype(np.int32)))
+        ok = ok and bool(np.array_equal(gind.numpy(), cind.astype(np.int32)))
+        ok = ok and bool(np.array_equal(gd.numpy().view(np.uint64), cd.view(np.uint64)))
+        # row-distributed form: this rank's rows with global indptr values
+        pip, pind, pd, total2 = RowPartitionedSpGEMM(bounds, rank, world, local_spgemm, dist=dist,
+                                                     gather=False).product()
+        ok = ok and total2 == total
+        ok = ok and bool(np.array_equal(pip.numpy(), cip[r0:r1 + 1].astype(np.int32)))
+        ok = ok and bool(np.array_equal(pind.numpy(), cind[int(cip[r0]):int(cip[r1])].astype(np.int32)))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_partitioned_spmm_spgemm_gloo_world2():
+    import torch.multiprocessing as mp
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_spmm_spgemm, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res

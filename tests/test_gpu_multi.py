@@ -75,6 +75,39 @@ def _worker(rank, world, port, q, late_modes=False):
                                                               dist, dev, mode=mode, barrier=barrier))
             else:
                 print("no multicast support on this box: mcast modes not exercised", flush=True)
+            # SURVEY 8e "next": row-partitioned SpMM and SpGEMM reproduce the 1-GPU products
+            from sprs_b200.dist import RowPartitionedSpGEMM, RowPartitionedSpMM
+            k = 16
+            b = torch.randn(n, k, device=dev, dtype=torch.float64,
+                            generator=torch.Generator(device=dev).manual_seed(3))
+            c_ref = torch.zeros(n, k, device=dev, dtype=torch.float64)
+            G.spmm_rowmaj(ctx, full, b, c_ref)
+            c = torch.full((n, k), float("nan"), device=dev, dtype=torch.float64)
+            mm = RowPartitionedSpMM(bounds, rank, world, c,
+                                    lambda bt, cs: G.spmm_rowmaj(ctx, a, bt, cs), dist=dist)
+            c_got = mm.step(b)
+            torch.cuda.synchronize()
+            oks.append(bool(torch.equal(c_got, c_ref)))
+            small = G.rmat_csr(ctx, 30_000, 8, seed=11)
+            sb = nnz_balanced_bounds(small.indptr, world)
+            blk = small.slice_rows(sb[rank], sb[rank + 1])
+            keep = []
+
+            def local_spgemm():
+                m, ip_t, ind_t, dat_t = G.spgemm(ctx, blk, small)
+                keep.append(m)
+                return ip_t, ind_t, dat_t
+
+            gip, gind, gdat, total = RowPartitionedSpGEMM(sb, rank, world, local_spgemm,
+                                                          dist=dist).product()
+            m1, ip1, ind1, dat1 = G.spgemm(ctx, small, small)
+            torch.cuda.synchronize()
+            oks.append(total == ind1.numel() and bool(torch.equal(gip, ip1)) and
+                       bool(torch.equal(gind, ind1)))
+            # values: rows above 128 entries accumulate with shared-memory atomics (order not
+            # fixed), so they agree to rounding, like any two runs of the 1-GPU product
+            oks.append(bool(((gdat - dat1).abs() <= 1e-9 * dat1.abs().max()).all()))
+            del keep, m1
         q.put((rank, ok_nccl, all(oks)))
     finally:
         dist.destroy_process_group()
