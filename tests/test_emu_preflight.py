@@ -85,3 +85,20 @@ def test_emu_gpu_suite(emu):
         if proc.returncode != 0 or " passed" not in tail or "failed" in tail:
             failures.append("%s: exit %d\n%s\n%s" % (name, proc.returncode, tail, err[-2000:]))
     assert not failures, "\n\n".join(failures)
+
+
+def test_emu_structure_fuzz(emu):
+    """tools/fuzz_emu.py: matrices whose row lengths sit on the kernels' internal boundaries
+    (tile sizes, register-path row counts, lane groups, SpGEMM bins) through every product of
+    the C ABI against the oracle; a fixed slice of the campaign that found nothing in ~7000
+    cases across the default and opt-in kernel variants."""
+    runs = [({}, "1"), ({"SPRS_B200_SPGEMM_V2": "1", "SPRS_B200_SPMV_VARIANT": "256,0,8,3"}, "50001"),
+            ({"SPRS_B200_FORCE_INDPTR64": "1", "SPRS_B200_SPMM_UNROLL": "4",
+              "SPRS_B200_E2E_PIPELINE": "2"}, "90001")]
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "fuzz_emu.py"), "--cases", "40",
+                               "--seed", seed], env=dict(os.environ, **env), cwd=ROOT,
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for env, seed in runs]
+    for p in procs:
+        out, _ = p.communicate(timeout=900)
+        assert p.returncode == 0 and "0 failing" in out, out[-3000:]
