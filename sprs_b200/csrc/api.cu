@@ -151,9 +151,12 @@ int csmat_chunk_table(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, uint64_t n_c
         acc += taper ? n_chunks - c : 1;
     }
     (*tiles)[n_chunks] = m->n_tiles;
-    for (uint64_t c = 1; c <= n_chunks; ++c)  // never an empty chunk
+    // never an empty chunk: strictly increasing cut points (n_chunks <= n_tiles, so they
+    // exist) -- push duplicates up, then pull anything that ran into the end back down
+    for (uint64_t c = 1; c < n_chunks; ++c)
         if ((*tiles)[c] <= (*tiles)[c - 1]) (*tiles)[c] = (*tiles)[c - 1] + 1;
-    (*tiles)[n_chunks] = m->n_tiles;
+    for (uint64_t c = n_chunks; c-- > 1;)
+        if ((*tiles)[c] >= (*tiles)[c + 1]) (*tiles)[c] = (*tiles)[c + 1] - 1;
     for (uint64_t c = 0; c <= n_chunks; ++c) {
         uint32_t r = 0;  // tile_row[0] == 0, tile_row[n_tiles] == rows
         SPRS_CUDA(ctx, cudaMemcpyAsync(&r, m->d_tile_row + (*tiles)[c], sizeof(r),

@@ -123,6 +123,12 @@ def test_chunked_push_hub_rows_degenerate_shapes(sp, monkeypatch):
     _run_case(sp, monkeypatch, empty, 50, 10, None, chunked=4)
     one_target = rand_csr(rng, 500, 400, 30)
     _run_case(sp, monkeypatch, one_target, 500, 400, None, n_targets=1, chunked=3)
+    # as many chunks as tiles (5 tiles of 384, 8 chunks asked): the tapered cut points used
+    # to collide at the end ("bad tile range", found by tools/fuzz_emu.py)
+    lens = np.full(40, 48)                              # 1920 non-zeros = exactly 5 tiles
+    ip = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+    ind = np.concatenate([np.sort(rng.choice(300, 48, replace=False)) for _ in lens]).astype(np.uint32)
+    _run_case(sp, monkeypatch, (ip, ind, rng.standard_normal(1920)), 40, 300, None, chunked=8)
 
 
 # ---------------------------------------------------------------- NVSwitch multicast exchange

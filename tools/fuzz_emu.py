@@ -90,6 +90,42 @@ def gate(got, ref, bound, what):
     return None
 
 
+def push_case(sp, a, rows, cols, rng):
+    import ctypes as C
+    import torch
+    from sprs_b200 import generate as G
+    ctx = sp.Context.default()
+    mirror = a.device().h
+    offset = int(rng.integers(0, 9))
+    n_targets = int(rng.integers(2, 5))
+    total = rows + offset + 3
+    x = torch.from_numpy(rng.standard_normal(cols))
+    ref = torch.full((rows,), -7.0, dtype=torch.float64)
+    accumulate = int(rng.integers(0, 2))
+    ctx.check(ctx.lib.sprs_b200_spmv_dev(ctx.h, mirror, C.c_void_p(x.data_ptr()),
+                                         C.c_void_p(ref.data_ptr()), accumulate, None))
+    for name in ("chunked", "stream"):
+        bufs = [torch.full((total,), -7.0, dtype=torch.float64) for _ in range(n_targets)]
+        ptrs = (C.c_void_p * n_targets)(*[b.data_ptr() for b in bufs])
+        if name == "chunked":
+            st = ctx.lib.sprs_b200_spmv_chunked_push_dev(
+                ctx.h, mirror, C.c_void_p(x.data_ptr()), offset, n_targets, ptrs, accumulate,
+                int(rng.integers(0, 9)), None)
+        else:
+            st = ctx.lib.sprs_b200_spmv_stream_push_dev(
+                ctx.h, mirror, C.c_void_p(x.data_ptr()), offset, n_targets, ptrs, accumulate,
+                int(rng.integers(0, 6)), None)
+        ctx.check(st)
+        want = ref.numpy()
+        for q, b in enumerate(bufs):
+            got = b.numpy()
+            if not np.array_equal(got[offset:offset + rows].view(np.uint64), want.view(np.uint64)):
+                return "%s push: target %d differs from the plain SpMV" % (name, q)
+            if not (np.all(got[:offset] == -7.0) and np.all(got[offset + rows:] == -7.0)):
+                return "%s push: target %d written outside the row block" % (name, q)
+    return None
+
+
 def one_case(sp, O, seed):
     rng = np.random.default_rng(seed)
     rows = int(rng.choice([1, 2, 7, 33, 100, 257, 600]))
@@ -119,6 +155,12 @@ def one_case(sp, O, seed):
         O.mul_acc_mat_vec_csr(ip, ind, finite, x, ref0)
         if not np.array_equal(af * x, ref0):
             errs.append("spmv: short rows in one tile not bit-exact")
+    # ---- pipelined all-gathers (chunked push / stream push) into local "peer" buffers:
+    #      bit-identical to the plain device SpMV, nothing written outside the row block
+    if rows >= 2 and os.environ.get("SPRS_B200_FUZZ_PUSH", "1") == "1":
+        e = push_case(sp, af, rows, cols, rng)
+        if e:
+            errs.append(e)
     # ---- SpMM: bit-exact, k on both sides of the k >= 8 rule
     k = int(rng.choice([1, 3, 8, 9, 32, 33, 64, 70]))
     b = rng.standard_normal((cols, k))
