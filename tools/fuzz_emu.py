@@ -126,10 +126,40 @@ def push_case(sp, a, rows, cols, rng):
     return None
 
 
+def solver_case(sp, O, rng, n, ip, ind, d):
+    """A + (row abs sum + 1) on the diagonal -> strictly dominant; device solve vs oracle."""
+    import scipy.sparse as sparse
+    A = sparse.csr_matrix((d, ind.astype(np.int64), ip.astype(np.int64)), shape=(n, n))
+    A = (A + sparse.diags(np.asarray(abs(A).sum(axis=1)).ravel() + 1.0)).tocsr()
+    A.sort_indices()
+    csr = (A.indptr.astype(np.uint32), A.indices.astype(np.uint32), A.data.copy())
+    b = rng.standard_normal(n)
+    a = sp.CsMat((n, n), *csr)
+    tol = 1e-10
+    try:
+        res = sp.linalg.BiCGSTAB.solve(a, np.zeros(n), b, tol, 300)
+    except sp.linalg.NotConverged as ex:
+        ok, ref = O.BiCGSTAB.solve(csr, np.zeros(n), b, tol, 300)
+        return None if not ok else "bicgstab: device Err, oracle Ok after %d" % ref.iteration_count()
+    ok, ref = O.BiCGSTAB.solve(csr, np.zeros(n), b, tol, 300)
+    if not ok:
+        return "bicgstab: device Ok, oracle Err"
+    if not np.allclose(res.x(), ref.x(), rtol=1e-6, atol=1e-9):
+        return "bicgstab: x differs from the oracle"
+    if np.linalg.norm(b - A @ res.x()) >= tol * 1.001:
+        return "bicgstab: accepted solution misses the tolerance"
+    # rounding differences grow along slowly converging trajectories: a relative band
+    if abs(res.iteration_count() - ref.iteration_count()) > max(3, ref.iteration_count() // 5):
+        return "bicgstab: %d iterations vs oracle %d" % (res.iteration_count(), ref.iteration_count())
+    return None
+
+
 def one_case(sp, O, seed):
     rng = np.random.default_rng(seed)
     rows = int(rng.choice([1, 2, 7, 33, 100, 257, 600]))
     cols = int(rng.choice([1, 5, 64, 500, 1153, 4200]))
+    if rng.integers(0, 4) == 0:
+        cols = rows  # square: also feeds the solver
     lens = row_lengths(rng, rows, cols)
     ip, ind, d = make_csr(rng, rows, cols, lens)
     idx = rng.choice([np.uint32, np.uint64])
@@ -176,6 +206,33 @@ def one_case(sp, O, seed):
         e = gate(np.asarray(c), cref, cb, "spmm-colmaj k=%d" % k)
         if e:
             errs.append(e)
+    # ---- CSC operands (device CSC -> CSR, then the CSR kernels: same ascending-column sums)
+    #      and arbitrary-stride dense views (prod.rs:632-651)
+    acsc = af.to_other_storage()
+    yc = np.zeros(rows)
+    sp.prod.mul_acc_mat_vec_csc(acsc, x, yc) if af.is_csr() else None
+    refc, bc = np.zeros(rows), np.zeros(rows)
+    O.mul_acc_mat_vec_csr(ip, ind, finite, x, refc)
+    O.mul_acc_mat_vec_csr(ip, ind, np.abs(finite), np.abs(x), bc)
+    e = gate(yc, refc, bc, "csc spmv")
+    if e:
+        errs.append(e)
+    kk = int(rng.choice([8, 13, 40]))
+    big = rng.standard_normal((2 * cols + 1, 2 * kk + 3))
+    view = big[::2][:cols, ::-2][:, :kk] if rng.integers(0, 2) else np.asfortranarray(big[:cols, :kk])
+    outbig = np.zeros((rows * 2 + 1, kk + 2))
+    out = outbig[1::2][:rows, 1:kk + 1]
+    (sp.prod.csc_mulacc_dense_rowmaj if rng.integers(0, 2) else sp.prod.csc_mulacc_dense_colmaj)(
+        acsc, view, out)
+    want = np.zeros((rows, kk))
+    O.csr_mulacc_dense_rowmaj(ip, ind, finite, np.ascontiguousarray(view), want)
+    wb = np.zeros((rows, kk))
+    O.csr_mulacc_dense_rowmaj(ip, ind, np.abs(finite), np.abs(np.ascontiguousarray(view)), wb)
+    e = gate(np.ascontiguousarray(out), want, wb, "csc dense product on strided views")
+    if e:
+        errs.append(e)
+    if outbig[0::2].any() or outbig[:, 0].any() or outbig[:, kk + 1].any():
+        errs.append("dense product wrote outside its output view")
     # ---- storage conversion: bit-exact, both directions
     t = a.to_other_storage()
     tip, tind, td = O.convert_mat_storage(rows, cols, ip, ind, d)
@@ -213,6 +270,11 @@ def one_case(sp, O, seed):
         _, _, cb = O.mul_csr_csr((rows, cols), (ip, ind, np.abs(finite)), (cols, bcols),
                                  (bip, bind, np.abs(bd)), threads=1)
         e = gate(cm.data, cd, cb, "spgemm values")
+        if e:
+            errs.append(e)
+    # ---- BiCGSTAB on a diagonally dominant system built from the same pattern
+    if rows == cols and rows >= 2:
+        e = solver_case(sp, O, rng, rows, ip, ind, finite)
         if e:
             errs.append(e)
     # ---- triplets: shuffled COO with duplicates
