@@ -148,8 +148,9 @@ def solver_case(sp, O, rng, n, ip, ind, d):
         return "bicgstab: x differs from the oracle"
     if np.linalg.norm(b - A @ res.x()) >= tol * 1.001:
         return "bicgstab: accepted solution misses the tolerance"
-    # rounding differences grow along slowly converging trajectories: a relative band
-    if abs(res.iteration_count() - ref.iteration_count()) > max(3, ref.iteration_count() // 5):
+    # rounding differences grow along slowly converging trajectories (hundreds of steps end
+    # tens of steps apart): the count is only compared where convergence is fast
+    if ref.iteration_count() <= 50 and abs(res.iteration_count() - ref.iteration_count()) > 3:
         return "bicgstab: %d iterations vs oracle %d" % (res.iteration_count(), ref.iteration_count())
     return None
 
@@ -255,7 +256,8 @@ def one_case(sp, O, seed):
     if os.environ.get("SPRS_B200_FORCE_INDPTR64") == "1":
         return errs  # the SpGEMM refuses 64-bit-indptr operands (nnz >= 2^32): documented limit
     # ---- SpGEMM against a second matrix with its own structure
-    bcols = int(rng.choice([1, 9, 300, 2500]))
+    # 9000 / 23000 columns: C rows beyond 4096 entries -> dense shared-memory panels (1 and 2)
+    bcols = int(rng.choice([1, 9, 300, 2500, 2500, 9000, 23000]))
     blens = row_lengths(rng, cols, bcols)
     bip, bind, bd = make_csr(rng, cols, bcols, blens)
     bd = np.where(np.abs(bd) > 1e200, 1.0, bd)
