@@ -128,6 +128,14 @@ int ctx_scratch(sprs_b200_ctx* ctx, int i, size_t bytes, void** out) {
     return SPRS_B200_OK;
 }
 
+constexpr unsigned TILE_COUNTER_RING = 64;
+int ctx_tile_counter(sprs_b200_ctx* ctx, unsigned long long** out) {
+    if (!ctx->d_tile_counters)
+        SPRS_CUDA(ctx, cudaMalloc((void**)&ctx->d_tile_counters, TILE_COUNTER_RING * 8));
+    *out = ctx->d_tile_counters + (ctx->tile_counter_next++ % TILE_COUNTER_RING);
+    return SPRS_B200_OK;
+}
+
 int ctx_side_stream(sprs_b200_ctx* ctx) {
     if (ctx->side_stream) return SPRS_B200_OK;
     int lo = 0, hi = 0;  // numerically lower = higher priority
@@ -230,6 +238,7 @@ int sprs_b200_ctx_destroy(sprs_b200_ctx* ctx) {
     for (int i = 0; i < 4; ++i)
         if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->d_tile_counters) cudaFree(ctx->d_tile_counters);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);

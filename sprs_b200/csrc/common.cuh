@@ -29,6 +29,10 @@ struct sprs_b200_ctx {
     // kernel and the fork/join events that tie it to the caller's stream; created on first use
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // dynamic tile hand-out of the SpMV (spmv.cu): a ring of 8-byte counters, one per launch
+    // (zeroed on the launch's stream), so launches in flight on different streams never share
+    unsigned long long* d_tile_counters = nullptr;
+    unsigned tile_counter_next = 0;
     // chunked host path (api.cu, SPRS_B200_E2E_PIPELINE=2): copy stream + one event per chunk
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_chunk[SPRS_E2E_MAX_CHUNKS] = {};
@@ -129,6 +133,8 @@ int spmv_launch_tile_range(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const d
 // chunk cannot overlap with compute) instead of equal.  Synchronises `s` (api.cu).
 int csmat_chunk_table(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, uint64_t n_chunks, bool taper,
                       cudaStream_t s, std::vector<uint64_t>* tiles, std::vector<uint64_t>* rows);
+// next counter of the ctx's ring for a dynamically scheduled SpMV launch (api.cu)
+int ctx_tile_counter(sprs_b200_ctx* ctx, unsigned long long** out);
 // high-priority side stream + fork/join events of the ctx, created on first use (api.cu)
 int ctx_side_stream(sprs_b200_ctx* ctx);
 int spmm_rowmaj_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_b,

@@ -305,8 +305,16 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
                      const double* __restrict__ x, SpmvTargets yt,
                      double* __restrict__ carry, uint64_t nnz, uint32_t rows, uint64_t t_begin,
                      uint64_t n_tiles /* end of this launch's tile range */, int accumulate,
-                     unsigned long long* progress, int chunk_shift) {
+                     unsigned long long* progress, int chunk_shift,
+                     unsigned long long* tile_counter) {
     constexpr int EPL = WT / 32;               // non-zeros per lane per tile
+    // SIGNAL flavour with a one-stage ring and a tile counter: tiles are HANDED OUT (every warp
+    // claims the next unclaimed tile of the launch) instead of dealt round-robin, so CTAs that
+    // share their SM with the put kernel, or start late because it took their slot, simply
+    // claim fewer tiles; a static deal would leave their share for a second wave.  Claims are
+    // made two tiles ahead, so the atomic's round trip never sits in front of a gather.
+    // Which warp reduces a tile does not change any sum.
+    constexpr bool DYN = SIGNAL && (STAGES <= 1);
     constexpr bool DIRECT = STAGES == 0;       // no TMA ring: stream through registers
     constexpr int STAGE_BYTES = DIRECT ? WT * 8 : WT * 12;
     constexpr int NST = DIRECT ? 1 : STAGES;
@@ -316,8 +324,19 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
     unsigned char* wsm = smem_raw + (size_t)warp * NST * STAGE_BYTES;
     // this launch covers tiles [t_begin, n_tiles): the whole matrix, or one chunk of it when the
     // caller pipelines something behind finished row ranges (spmv_launch_tile_range)
-    const uint64_t gw = t_begin + (uint64_t)blockIdx.x * NWARPS + warp;
+    const bool dyn = DYN && tile_counter != nullptr;
+    uint64_t gw = t_begin + (uint64_t)blockIdx.x * NWARPS + warp;
     const uint64_t GW = (uint64_t)gridDim.x * NWARPS;
+    uint64_t t_claimed = 0;  // dyn: this warp's next tile, claimed one iteration ago
+    if (dyn) {
+        unsigned long long c0 = 0, c1 = 0;
+        if (lane == 0) {
+            c0 = atomicAdd(tile_counter, 1ull);
+            c1 = atomicAdd(tile_counter, 1ull);
+        }
+        gw = t_begin + __shfl_sync(0xffffffffu, c0, 0);
+        t_claimed = t_begin + __shfl_sync(0xffffffffu, c1, 0);
+    }
     const uint64_t pol_stream = policy_evict_first();
     const uint64_t polx = policy_evict_last();
 
@@ -359,7 +378,9 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
         const uint64_t rr = (uint64_t)r0 + lane;
         b_first = rr <= rl + 1 ? (uint64_t)indptr[rr] : 0;
     }
-    for (uint64_t t = gw; t < n_tiles; t += GW) {
+    for (uint64_t t = gw; t < n_tiles;) {
+        unsigned long long claim = 0;  // dyn: the tile after next, in flight during this tile
+        if (dyn && lane == 0) claim = atomicAdd(tile_counter, 1ull);
         const uint64_t k0 = t * (uint64_t)WT;
         const uint64_t k1 = (k0 + WT < nnz) ? k0 + WT : nnz;
         const int cnt = (int)(k1 - k0);
@@ -367,7 +388,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
         double* sprod = (double*)(wsm + (size_t)s * STAGE_BYTES);
         uint32_t* sidx = (uint32_t*)(wsm + (size_t)s * STAGE_BYTES + WT * 8);
         const uint64_t r_last = (r1 < rows) ? (uint64_t)r1 : (uint64_t)r1 - 1;
-        const uint64_t tnext = t + GW;
+        const uint64_t tnext = dyn ? t_claimed : t + GW;
         uint32_t r0n = 0, r1n = 0;
         const int nrows_t = (r_last - r0 + 1) > 64 ? 64 : (int)(r_last - r0 + 1);
         const bool regpath = full && nrows_t <= SPMV_REG_ROWS;  // warp-uniform
@@ -465,17 +486,21 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
         __syncwarp();
         // refill this stage (generic-proxy accesses above must be ordered before the
         // async-proxy writes of the next bulk copy)
-        const uint64_t tn = t + (uint64_t)NST * GW;
+        const uint64_t tn = dyn ? tnext : t + (uint64_t)NST * GW;
         if (!DIRECT && lane == 0 && tn < n_tiles) {
             fence_proxy_async();
             SPMV_ISSUE(tn, s);
         }
-        if (SIGNAL) {
+        if (SIGNAL && progress) {
             ++sig_count;
             if (tnext >= n_tiles || (tnext >> chunk_shift) != (t >> chunk_shift)) {
                 __threadfence();  // every lane: its y stores are visible device-wide ...
                 __syncwarp();     // ... before lane 0 publishes the count
-                if (lane == 0) atomicAdd(&progress[t >> chunk_shift], sig_count);
+                if (lane == 0) {
+                    __threadfence();  // release by the publishing thread itself (cumulative
+                                      // over what the barrier made visible to it)
+                    atomicAdd(&progress[t >> chunk_shift], sig_count);
+                }
                 sig_count = 0;
             }
         }
@@ -483,6 +508,8 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
         r0 = r0n;
         r1 = r1n;
         b_first = b_next;
+        t = tnext;
+        if (dyn) t_claimed = t_begin + __shfl_sync(0xffffffffu, claim, 0);
     }
 }
 
@@ -543,10 +570,24 @@ SpmvVariant spmv_variant() {
     return v;
 }
 
+// SPRS_B200_SPMV_DYNAMIC: unset = tiles are handed out dynamically in the pipelined launches
+// (stream push, chunked push, chunked host path: kernels that share SMs with a put kernel);
+// 1 = in every single-target SpMV; 0 = nowhere (the static round-robin deal).
+int spmv_dynamic_mode() {
+    static const int mode = [] {
+        const char* e = getenv("SPRS_B200_SPMV_DYNAMIC");
+        return e ? atoi(e) : -1;
+    }();
+    return mode;
+}
+
 struct SpmvSignal {  // progress counters of the pipelined all-gather; null = no signalling
     unsigned long long* progress = nullptr;
     int chunk_shift = 0;
     uint64_t t0 = 0, t1 = 0;  // tile range of this launch; t1 == 0: the whole matrix
+    // dynamic tile hand-out (needs the SIGNAL flavour; null = the static round-robin deal):
+    // an 8-byte counter, zeroed on the launch's stream right before the kernel
+    unsigned long long* tile_counter = nullptr;
 };
 
 template <typename P, int WT, int STAGES, int NWARPS, int CTAS>
@@ -555,7 +596,9 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
                    cudaStream_t s) {
     // CTAS resident CTAs per SM is also the kernel's __launch_bounds__ minBlocks: it sets the
     // register budget (ptxas otherwise picks ~40 registers and spills the gather buffers).
-    const int flavour = sig.progress ? 2 : (yt.n > 1 ? 1 : 0);
+    // the hand-out lives in the single-target SIGNAL flavour only
+    unsigned long long* const tile_counter = yt.n <= 1 ? sig.tile_counter : nullptr;
+    const int flavour = (sig.progress || tile_counter) ? 2 : (yt.n > 1 ? 1 : 0);
     auto kern = flavour == 2   ? spmv_warp_kernel<P, WT, STAGES, NWARPS, CTAS, false, true>
                 : flavour == 1 ? spmv_warp_kernel<P, WT, STAGES, NWARPS, CTAS, true, false>
                                : spmv_warp_kernel<P, WT, STAGES, NWARPS, CTAS, false, false>;
@@ -581,10 +624,12 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
     uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
     const uint64_t need = (t1 - t0 + NWARPS - 1) / NWARPS;
     if (grid > need) grid = need;
+    if (tile_counter) SPRS_CUDA(ctx, cudaMemsetAsync(tile_counter, 0, 8, s));
     kern<<<(unsigned)grid, NWARPS * 32, smem, s>>>((const P*)m->d_indptr, m->d_indices, m->d_data,
                                                    m->d_tile_row, d_x, yt, m->d_carry, m->nnz,
                                                    (uint32_t)m->rows, t0, t1, accumulate,
-                                                   sig.progress, sig.chunk_shift);
+                                                   sig.progress, sig.chunk_shift,
+                                                   tile_counter);
     return SPRS_B200_OK;
 }
 
@@ -642,10 +687,12 @@ int spmv_launch_targets(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const doub
         SPRS_FAIL(ctx, SPRS_B200_ERR_STORAGE, "Storage mismatch: spmv needs a CSR mirror");
     if (m->rows == 0) return SPRS_B200_OK;
     if (!m->d_tile_row) SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "csmat has no SpMV partition");
+    SpmvSignal sig;
+    if (spmv_dynamic_mode() == 1 && yt.n <= 1) SPRS_TRY(ctx_tile_counter(ctx, &sig.tile_counter));
     if (m->indptr_bytes == 4)
-        SPRS_TRY(launch_dispatch<uint32_t>(ctx, m, d_x, yt, accumulate, SpmvSignal(), s));
+        SPRS_TRY(launch_dispatch<uint32_t>(ctx, m, d_x, yt, accumulate, sig, s));
     else
-        SPRS_TRY(launch_dispatch<uint64_t>(ctx, m, d_x, yt, accumulate, SpmvSignal(), s));
+        SPRS_TRY(launch_dispatch<uint64_t>(ctx, m, d_x, yt, accumulate, sig, s));
     ctx->launches += 1;
     if (m->n_tiles > 1) {
         const unsigned fgrid = (unsigned)((m->n_tiles - 1 + 255) / 256);
@@ -792,6 +839,7 @@ int spmv_launch_stream_push(sprs_b200_ctx* ctx, sprs_b200_csmat* m, const double
     SpmvSignal sig;
     sig.progress = m->d_progress;
     sig.chunk_shift = m->chunk_shift;
+    if (spmv_dynamic_mode() != 0) SPRS_TRY(ctx_tile_counter(ctx, &sig.tile_counter));
     if (put_ctas <= 0) put_ctas = 16;
     if (const char* e = getenv("SPRS_B200_PUSH_CTAS")) put_ctas = atoi(e) > 0 ? atoi(e) : put_ctas;
     if (put_ctas > ctx->sm_count) put_ctas = ctx->sm_count;
@@ -860,6 +908,7 @@ int spmv_launch_tile_range(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const d
     SpmvSignal sig;
     sig.t0 = t0;
     sig.t1 = t1;
+    if (spmv_dynamic_mode() != 0) SPRS_TRY(ctx_tile_counter(ctx, &sig.tile_counter));
     if (m->indptr_bytes == 4)
         SPRS_TRY(launch_dispatch<uint32_t>(ctx, m, d_x, yt, accumulate, sig, s));
     else

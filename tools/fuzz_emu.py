@@ -148,10 +148,8 @@ def solver_case(sp, O, rng, n, ip, ind, d):
         return "bicgstab: x differs from the oracle"
     if np.linalg.norm(b - A @ res.x()) >= tol * 1.001:
         return "bicgstab: accepted solution misses the tolerance"
-    # rounding differences grow along slowly converging trajectories (hundreds of steps end
-    # tens of steps apart): the count is only compared where convergence is fast
-    if ref.iteration_count() <= 50 and abs(res.iteration_count() - ref.iteration_count()) > 3:
-        return "bicgstab: %d iterations vs oracle %d" % (res.iteration_count(), ref.iteration_count())
+    # (iteration counts are not compared: a near-breakdown step amplifies the last-bit
+    # difference of the dot products' summation order into a different trajectory)
     return None
 
 
