@@ -15,6 +15,7 @@ SPRS_B200_TEST_E2E_CHUNKED=1 timeout 600 python -m pytest tests/test_gpu_zzz_e2e
 SPRS_B200_TEST_SPGEMM_V2=1 timeout 600 python -m pytest tests/test_gpu_zzz_spgemm_v2.py -m gpu -q > $out/pytest_spgemm_v2.txt 2>&1; echo "spgemm_v2 tests exit $?" >> $out/summary.txt
 # 2. headline bench (N=1) and the secondary workloads (SpGEMM with the panel kernel: first timing)
 timeout 600 python bench.py --steps 20 --warmup 5 > $out/bench_n1.json 2> $out/bench_n1.err; echo "bench exit $?" >> $out/summary.txt
+SPRS_B200_SPMV_DYNAMIC=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extra > $out/bench_n1_dynamic.json 2> $out/bench_n1_dynamic.err; echo "bench dynamic exit $?" >> $out/summary.txt
 SPRS_B200_E2E_PIPELINE=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extra > $out/bench_n1_e2e_pipeline.json 2> $out/bench_n1_e2e_pipeline.err; echo "bench e2e pipeline exit $?" >> $out/summary.txt
 SPRS_B200_E2E_PIPELINE=2 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extra > $out/bench_n1_e2e_chunked.json 2> $out/bench_n1_e2e_chunked.err; echo "bench e2e chunked exit $?" >> $out/summary.txt
 for pw in 8 4; do SPRS_B200_SPMM_PANEL=$pw timeout 300 python bench.py --workload spmm_rand_1m_k64 --steps 10 --warmup 3 --no-cpu-baseline > $out/bench_spmm_panel$pw.json 2> $out/bench_spmm_panel$pw.err; done
@@ -37,7 +38,7 @@ cat $out/summary.txt
 tail -3 $out/pytest_gpu.txt $out/pytest_stream_push.txt
 tail -c 600 $out/bench_n1.json; echo; python - <<'PY'
 import json
-for f in ("bench_n1", "bench_n1_e2e_pipeline", "bench_n1_e2e_chunked", "bench_spmm", "bench_spmm_unroll4", "bench_spmm_panel8", "bench_spmm_panel4"):
+for f in ("bench_n1", "bench_n1_dynamic", "bench_n1_e2e_pipeline", "bench_n1_e2e_chunked", "bench_spmm", "bench_spmm_unroll4", "bench_spmm_panel8", "bench_spmm_panel4"):
     try:
         d = json.loads(open("gpurun_out/r2_first/%s.json" % f).read().strip().splitlines()[-1])
         print(f, "ms/step %.3f" % d["ms_per_step"], "value %.1f" % d["value"], "e2e", d.get("e2e", {}).get("value"))
