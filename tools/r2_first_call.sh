@@ -23,6 +23,9 @@ timeout 600 python bench.py --workload spgemm_rmat_500k --steps 3 --warmup 1 > $
 SPRS_B200_SPGEMM_V2=1 timeout 600 python bench.py --workload spgemm_rmat_500k --steps 3 --warmup 1 --no-cpu-baseline > $out/bench_spgemm_v2.json 2> $out/bench_spgemm_v2.err; echo "spgemm v2 exit $?" >> $out/summary.txt
 SPRS_B200_SPMM_UNROLL=4 timeout 300 python bench.py --workload spmm_rand_1m_k64 --steps 10 --warmup 3 --no-cpu-baseline > $out/bench_spmm_unroll4.json 2> $out/bench_spmm_unroll4.err
 timeout 300 python bench.py --workload spmm_rand_1m_k64 --steps 10 --warmup 3 > $out/bench_spmm.json 2> $out/bench_spmm.err; echo "spmm exit $?" >> $out/summary.txt
+# 2b. can a cluster's distributed shared memory out-gather L1TEX? (tools/dsmem_gather_bench.cu)
+nvcc -O3 -gencode arch=compute_100a,code=sm_100a tools/dsmem_gather_bench.cu -o tools/dsmem_gather_bench > $out/dsmem_build.txt 2>&1 \
+  && timeout 120 tools/dsmem_gather_bench > $out/dsmem_gather.txt 2>&1; echo "dsmem bench exit $?" >> $out/summary.txt
 # 3. BiCGSTAB: cost of a step next to its two SpMVs (config 5 matrix)
 timeout 600 python tools/time_bicgstab.py > $out/bicgstab.json 2> $out/bicgstab.err; echo "bicgstab exit $?" >> $out/summary.txt
 # 4. per-kernel launch list of the SpGEMM (where does the time go now?)
