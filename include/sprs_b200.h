@@ -267,6 +267,17 @@ int sprs_b200_bicgstab_new(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, const
 int sprs_b200_bicgstab_new_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
                                const double* d_x0, const double* d_b, uint64_t n,
                                sprs_b200_bicgstab** out);
+/* Operator form: y = A x is delegated to `matvec` (called with device pointers to n doubles
+ * each and the stream the solver works on; it must ENQUEUE y = A x on that stream and return
+ * 0).  This is how the solver runs on a row-partitioned matrix: the callback is the
+ * distributed SpMV + all-gather of y (sprs_b200/dist.py), every rank keeps full-length
+ * vectors and computes the same dot products in the same order, so all ranks take the same
+ * steps and restarts without exchanging a scalar.  x0 / b: host pointers, or device pointers
+ * when device_pointers != 0.                                                              */
+typedef int (*sprs_b200_matvec_fn)(void* user, const double* d_x, double* d_y, void* stream);
+int sprs_b200_bicgstab_new_op(sprs_b200_ctx* ctx, uint64_t n, sprs_b200_matvec_fn matvec,
+                              void* user, const double* x0, const double* b,
+                              int device_pointers, sprs_b200_bicgstab** out);
 int sprs_b200_bicgstab_free(sprs_b200_bicgstab* s);
 /* one iteration; *err_out (optional) = the running error estimate |r| */
 int sprs_b200_bicgstab_step(sprs_b200_bicgstab* s, double* err_out);

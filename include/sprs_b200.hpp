@@ -21,6 +21,7 @@
 #include <array>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -436,6 +437,17 @@ class BiCGSTAB {
         ctx.check(sprs_b200_bicgstab_new(ctx.handle(), a.device(), x0.data(), b.data(),
                                          b.size(), &h_));
     }
+    // Operator form (sprs_b200_bicgstab_new_op): y = A x is `matvec(d_x, d_y, stream)` with
+    // device pointers to n doubles, enqueued on `stream` -- a matrix-free operator or the
+    // row-partitioned SpMV + all-gather of a multi-GPU caller.  a() is not available.
+    using MatVec = std::function<void(const double* d_x, double* d_y, void* stream)>;
+    BiCGSTAB(size_t n, MatVec matvec, const Array1& x0, const Array1& b)
+        : a_(nullptr), n_(n), op_(std::make_unique<MatVec>(std::move(matvec))) {
+        if (x0.size() != n || b.size() != n) throw Panic("Dimension mismatch");
+        Context& ctx = Context::thread_default();
+        ctx.check(sprs_b200_bicgstab_new_op(ctx.handle(), n, &BiCGSTAB::trampoline, op_.get(),
+                                            x0.data(), b.data(), 0, &h_));
+    }
     BiCGSTAB(const BiCGSTAB&) = delete;
     BiCGSTAB& operator=(const BiCGSTAB&) = delete;
     ~BiCGSTAB() { sprs_b200_bicgstab_free(h_); }
@@ -487,11 +499,21 @@ class BiCGSTAB {
         return v;
     }
     Array1 vec(int which) const {
-        Array1 out(a_->rows());
+        Array1 out(a_ ? a_->rows() : n_);
         check(sprs_b200_bicgstab_get(h_, which, out.data(), out.size()));
         return out;
     }
+    static int trampoline(void* user, const double* d_x, double* d_y, void* stream) {
+        try {
+            (*static_cast<MatVec*>(user))(d_x, d_y, stream);
+            return 0;
+        } catch (...) {
+            return 1;  // never unwind through the C frames: the call fails with a status
+        }
+    }
     const CsMatI<I, Iptr>* a_;
+    size_t n_ = 0;
+    std::unique_ptr<MatVec> op_;
     sprs_b200_bicgstab* h_ = nullptr;
 };
 }  // namespace bicgstab

@@ -24,6 +24,10 @@ pub const SPRS_B200_BICGSTAB_RHAT: c_int = 2;
 pub const SPRS_B200_BICGSTAB_P: c_int = 3;
 pub const SPRS_B200_BICGSTAB_B: c_int = 4;
 
+/// y = A x callback of the operator-form solver: device pointers to n doubles, a cudaStream_t.
+pub type sprs_b200_matvec_fn = Option<unsafe extern "C" fn(
+    user: *mut c_void, d_x: *const c_double, d_y: *mut c_double, stream: *mut c_void) -> c_int>;
+
 extern "C" {
     pub fn sprs_b200_version() -> c_int;
     pub fn sprs_b200_ctx_create(device: c_int, out: *mut *mut sprs_b200_ctx) -> c_int;
@@ -81,6 +85,10 @@ extern "C" {
     pub fn sprs_b200_bicgstab_new(
         ctx: *mut sprs_b200_ctx, mat: *const sprs_b200_csmat, x0: *const c_double,
         b: *const c_double, n: u64, out: *mut *mut sprs_b200_bicgstab) -> c_int;
+    pub fn sprs_b200_bicgstab_new_op(
+        ctx: *mut sprs_b200_ctx, n: u64, matvec: sprs_b200_matvec_fn, user: *mut c_void,
+        x0: *const c_double, b: *const c_double, device_pointers: c_int,
+        out: *mut *mut sprs_b200_bicgstab) -> c_int;
     pub fn sprs_b200_bicgstab_free(s: *mut sprs_b200_bicgstab) -> c_int;
     pub fn sprs_b200_bicgstab_step(s: *mut sprs_b200_bicgstab, err_out: *mut c_double) -> c_int;
     pub fn sprs_b200_bicgstab_soft_restart(s: *mut sprs_b200_bicgstab) -> c_int;

@@ -14,6 +14,9 @@ CSR, CSC = 0, 1
 _vp, _u64, _i64, _int, _dp = C.c_void_p, C.c_uint64, C.c_int64, C.c_int, C.c_void_p
 _dense_sig = [_vp, _vp, _dp, _u64, _u64, _i64, _i64, _dp, _u64, _u64, _i64, _i64]
 
+# sprs_b200_matvec_fn: int (*)(void* user, const double* d_x, double* d_y, void* stream)
+MATVEC_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)
+
 # name -> (restype, argtypes); one entry per symbol declared in include/sprs_b200.h
 PROTOTYPES = {
     "sprs_b200_version": (_int, []),
@@ -70,6 +73,8 @@ PROTOTYPES = {
     "sprs_b200_spgemm_free": (_int, [_vp]),
     "sprs_b200_bicgstab_new": (_int, [_vp, _vp, _dp, _dp, _u64, C.POINTER(_vp)]),
     "sprs_b200_bicgstab_new_dev": (_int, [_vp, _vp, _dp, _dp, _u64, C.POINTER(_vp)]),
+    "sprs_b200_bicgstab_new_op": (_int, [_vp, _u64, MATVEC_FN, _vp, _dp, _dp, _int,
+                                         C.POINTER(_vp)]),
     "sprs_b200_bicgstab_free": (_int, [_vp]),
     "sprs_b200_bicgstab_step": (_int, [_vp, C.POINTER(C.c_double)]),
     "sprs_b200_bicgstab_soft_restart": (_int, [_vp]),

@@ -228,6 +228,10 @@ __global__ void __launch_bounds__(RED_THREADS)
 struct sprs_b200_bicgstab {
     sprs_b200_ctx* ctx = nullptr;
     const sprs_b200_csmat* csr = nullptr;  // borrowed (the operand, or its cached CSR form)
+    // operator form (sprs_b200_bicgstab_new_op): y = A x is the caller's, e.g. the
+    // row-partitioned SpMV + all-gather of sprs_b200/dist.py; csr stays null
+    sprs_b200_matvec_fn op = nullptr;
+    void* op_user = nullptr;
     uint64_t n = 0;
     double* d_block = nullptr;  // one allocation: 8 vectors of `pitch` doubles
     uint64_t pitch = 0;
@@ -265,6 +269,11 @@ int finish_reduce(sprs_b200_bicgstab* s, cudaStream_t st) {
 // y = A x  (`&a * &x`: a fresh zero vector is accumulated into, csmat.rs:2119-2160)
 int matvec(sprs_b200_bicgstab* s, const double* d_x, double* d_y, cudaStream_t st) {
     if (s->n == 0) return SPRS_B200_OK;
+    if (s->op) {
+        if (s->op(s->op_user, d_x, d_y, (void*)st) != 0)
+            SPRS_FAIL(s->ctx, SPRS_B200_ERR_ARGUMENT, "bicgstab: the matvec callback failed");
+        return SPRS_B200_OK;
+    }
     return spmv_launch(s->ctx, s->csr, d_x, d_y, /*accumulate=*/0, st);
 }
 
@@ -285,20 +294,24 @@ int recompute_residual(sprs_b200_bicgstab* s) {
     return SPRS_B200_OK;
 }
 
-int create_common(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, const double* x0,
-                  const double* b, uint64_t n, cudaMemcpyKind kind, sprs_b200_bicgstab** out) {
-    if (!ctx || !mat || !out) return SPRS_B200_ERR_ARGUMENT;
+int create_common(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, sprs_b200_matvec_fn op,
+                  void* op_user, const double* x0, const double* b, uint64_t n,
+                  cudaMemcpyKind kind, sprs_b200_bicgstab** out) {
+    if (!ctx || (!mat && !op) || !out) return SPRS_B200_ERR_ARGUMENT;
     *out = nullptr;
     // `&a * &x0` and `&b - &(..)` panic on mismatched dimensions (prod.rs:170, binop.rs:455);
     // A p with p = r needs a square matrix
-    if (mat->rows != n || mat->cols != n) SPRS_FAIL(ctx, SPRS_B200_ERR_DIMENSION, "Dimension mismatch");
+    if (mat && (mat->rows != n || mat->cols != n))
+        SPRS_FAIL(ctx, SPRS_B200_ERR_DIMENSION, "Dimension mismatch");
     if (n && (!x0 || !b)) return SPRS_B200_ERR_ARGUMENT;
     SPRS_CUDA(ctx, cudaSetDevice(ctx->device));
     const sprs_b200_csmat* csr = nullptr;
-    SPRS_TRY(csmat_csr_view(ctx, mat, &csr));
+    if (mat) SPRS_TRY(csmat_csr_view(ctx, mat, &csr));
     auto* s = new sprs_b200_bicgstab();
     s->ctx = ctx;
     s->csr = csr;
+    s->op = mat ? nullptr : op;
+    s->op_user = op_user;
     s->n = n;
     s->pitch = (n + 31) / 32 * 32 + 32;  // 256-byte aligned vectors
     int st = SPRS_B200_OK;
@@ -345,13 +358,21 @@ int create_common(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, const double* 
 
 int sprs_b200_bicgstab_new(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, const double* x0,
                            const double* b, uint64_t n, sprs_b200_bicgstab** out) {
-    return create_common(ctx, mat, x0, b, n, cudaMemcpyHostToDevice, out);
+    return create_common(ctx, mat, nullptr, nullptr, x0, b, n, cudaMemcpyHostToDevice, out);
 }
 
 int sprs_b200_bicgstab_new_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
                                const double* d_x0, const double* d_b, uint64_t n,
                                sprs_b200_bicgstab** out) {
-    return create_common(ctx, mat, d_x0, d_b, n, cudaMemcpyDeviceToDevice, out);
+    return create_common(ctx, mat, nullptr, nullptr, d_x0, d_b, n, cudaMemcpyDeviceToDevice, out);
+}
+
+int sprs_b200_bicgstab_new_op(sprs_b200_ctx* ctx, uint64_t n, sprs_b200_matvec_fn matvec,
+                              void* user, const double* x0, const double* b,
+                              int device_pointers, sprs_b200_bicgstab** out) {
+    if (!matvec) return SPRS_B200_ERR_ARGUMENT;
+    return create_common(ctx, nullptr, matvec, user, x0, b, n,
+                         device_pointers ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, out);
 }
 
 int sprs_b200_bicgstab_free(sprs_b200_bicgstab* s) {

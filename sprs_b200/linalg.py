@@ -72,27 +72,69 @@ class BiCGSTAB:
         return cls(a, x0, b)
 
     @classmethod
+    def with_operator(cls, ctx, n, matvec, x0, b):
+        """The same solver with y = A x delegated to `matvec(d_x, d_y, stream)` (raw device
+        addresses of n doubles each and the cudaStream_t to enqueue on, as ints): a
+        matrix-free operator, or the row-partitioned SpMV + all-gather of sprs_b200.dist
+        (every rank keeps full-length vectors and takes identical steps, see
+        dist.row_partitioned_bicgstab).  sprs_b200_bicgstab_new_op."""
+        from . import _lib
+        x0 = _dense(x0, n)
+        b = _dense(b, n)
+        self = cls.__new__(cls)
+
+        def thunk(_user, d_x, d_y, stream):
+            try:
+                matvec(int(d_x or 0), int(d_y or 0), int(stream or 0))
+                return 0
+            except Exception as e:  # an exception must not unwind through the C frames
+                self._op_error = e
+                return 1
+
+        self._op_error = None
+        self._thunk = _lib.MATVEC_FN(thunk)  # kept alive with the solver
+        self._a, self._dev, self._ctx, self._n = None, None, ctx, n
+        h = C.c_void_p()
+        st = ctx.lib.sprs_b200_bicgstab_new_op(ctx.h, n, self._thunk, None,
+                                               x0.ctypes.data_as(C.c_void_p),
+                                               b.ctypes.data_as(C.c_void_p), 0, C.byref(h))
+        if st and self._op_error is not None:
+            raise self._op_error
+        ctx.check(st)
+        self._h = h
+        return self
+
+    def _check(self, st):
+        if st and getattr(self, "_op_error", None) is not None:
+            e, self._op_error = self._op_error, None
+            raise e
+        self._ctx.check(st)
+
+    @classmethod
     def solve(cls, a, x0, b, tol, max_iter):
         """BiCGSTAB::solve (bicgstab.rs:151-175).  Ok -> the solver; Err -> NotConverged."""
-        s = cls(a, x0, b)
+        return cls(a, x0, b).run(tol, max_iter)
+
+    def run(self, tol, max_iter):
+        """The loop of `solve` on an existing solver (bicgstab.rs:156-175)."""
         conv = C.c_int(0)
-        s._ctx.check(s._ctx.lib.sprs_b200_bicgstab_solve(s._h, float(tol), int(max_iter),
-                                                         C.byref(conv)))
+        self._check(self._ctx.lib.sprs_b200_bicgstab_solve(self._h, float(tol), int(max_iter),
+                                                           C.byref(conv)))
         if not conv.value:
-            raise NotConverged(s)
-        return s
+            raise NotConverged(self)
+        return self
 
     def step(self):
         """One iteration (bicgstab.rs:198-234); returns the running error estimate."""
         err = C.c_double()
-        self._ctx.check(self._ctx.lib.sprs_b200_bicgstab_step(self._h, C.byref(err)))
+        self._check(self._ctx.lib.sprs_b200_bicgstab_step(self._h, C.byref(err)))
         return err.value
 
     def soft_restart(self):
         self._ctx.check(self._ctx.lib.sprs_b200_bicgstab_soft_restart(self._h))
 
     def hard_restart(self):
-        self._ctx.check(self._ctx.lib.sprs_b200_bicgstab_hard_restart(self._h))
+        self._check(self._ctx.lib.sprs_b200_bicgstab_hard_restart(self._h))
 
     def with_restart_threshold(self, thresh):
         self._ctx.check(self._ctx.lib.sprs_b200_bicgstab_set_restart_threshold(self._h,

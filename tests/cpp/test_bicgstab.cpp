@@ -78,6 +78,20 @@ static void dominant_system() {
     for (size_t i = 0; i < n; ++i) rr += (b[i] - ax[i]) * (b[i] - ax[i]);
     CHECK(std::sqrt(rr) < 1e-8 * 1.001);
     CHECK(std::fabs(std::sqrt(rr) - res.second->err()) <= 1e-12);
+    // operator form: the same SpMV behind a caller-supplied operator -> the same bits per step
+    {
+        Context& ctx = Context::thread_default();
+        BiCGSTAB<uint32_t, uint32_t> s_mat(a, x0, b);
+        BiCGSTAB<uint32_t, uint32_t> s_op(n, [&](const double* d_x, double* d_y, void* stream) {
+            ctx.check(sprs_b200_spmv_dev(ctx.handle(), a.device(), d_x, d_y, 0, stream));
+        }, x0, b);
+        CHECK(s_op.err() == s_mat.err());
+        for (int it = 0; it < 4; ++it) CHECK(s_op.step() == s_mat.step());
+        const Array1 xo = s_op.x(), xm = s_mat.x();
+        bool same = true;
+        for (size_t i = 0; i < n; ++i) same = same && xo[i] == xm[i];
+        CHECK(same);
+    }
     // an impossible tolerance runs into the iteration limit: Err, state still returned
     auto res2 = BiCGSTAB<uint32_t, uint32_t>::solve(a, x0, b, 0.0, 3);
     CHECK(!res2.first);

@@ -191,3 +191,82 @@ def test_row_partitioned_spmm_spgemm_gloo_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res), res
+
+
+def _worker_bicgstab(rank, world, port, q):
+    """Row-partitioned BiCGSTAB end to end on the CPU: the solver and the local SpMV are the
+    library's kernels on the emulator (tests/emu, test infrastructure), the exchange is gloo."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    import ctypes as C
+    import scipy.sparse as sparse
+    import torch
+    import torch.distributed as dist
+    import sprs_b200 as sp
+    from conftest import emu_library
+    from oracle import oracle as O
+    from sprs_b200.dist import RowPartitionedSpMV, nnz_balanced_bounds, row_partitioned_bicgstab
+    sp._lib.LIB_PATH = emu_library()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(2024)  # same system on every rank
+        n = 1200
+        A = sparse.random(n, n, density=10 / n, random_state=rng, format="csr")
+        A = (A + sparse.diags(np.asarray(abs(A).sum(axis=1)).ravel() + 1.0)).tocsr()
+        A.sort_indices()
+        ip, ind, d = A.indptr.astype(np.uint32), A.indices.astype(np.uint32), A.data.copy()
+        b = rng.standard_normal(n)
+        bounds = nnz_balanced_bounds(ip, world)
+        r0, r1 = bounds[rank], bounds[rank + 1]
+        s0, s1 = int(ip[r0]), int(ip[r1])
+        ctx = sp.Context.default()
+        blk = sp.CsMat((r1 - r0, n), ip[r0:r1 + 1] - s0, ind[s0:s1], d[s0:s1], ctx=ctx)
+        mirror = blk.device()
+
+        def local_spmv(xv, y_slice):  # the library's SpMV kernel on this rank's row block
+            out = torch.empty(r1 - r0, dtype=torch.float64)
+            ctx.check(ctx.lib.sprs_b200_spmv_dev(ctx.h, mirror.h, C.c_void_p(xv.data_ptr()),
+                                                 C.c_void_p(out.data_ptr()), 0, None))
+            y_slice.copy_(out)
+
+        y = torch.zeros(n, dtype=torch.float64)
+        op = RowPartitionedSpMV(bounds, rank, world, y, local_spmv, dist=dist)
+        tol = 1e-10
+        solver = row_partitioned_bicgstab(ctx, op, n, np.zeros(n), b, "cpu").run(tol, 200)
+        x = solver.x()
+        ok_ref, ref = O.BiCGSTAB.solve((ip, ind, d), np.zeros(n), b, tol, 200)
+        ok = ok_ref and bool(np.allclose(x, ref.x(), rtol=1e-7, atol=1e-10))
+        ok = ok and float(np.linalg.norm(b - A @ x)) < tol * 1.001
+        ok = ok and solver.hard_restart_count() >= 1
+        # an exception inside the operator surfaces as itself, not as a status code
+        def broken(d_x, d_y, stream):
+            raise KeyError("operator failed")
+        try:
+            sp.linalg.BiCGSTAB.with_operator(ctx, n, broken, np.zeros(n), b)
+            ok = False
+        except KeyError:
+            pass
+        q.put((rank, ok, solver.iteration_count(), x.tobytes()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_partitioned_bicgstab_gloo_world2():
+    import torch.multiprocessing as mp
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_bicgstab, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _, _ in res), [(r, ok, it) for r, ok, it, _ in res]
+    # every rank took the same steps and holds the same bits without exchanging a scalar
+    assert res[0][2] == res[1][2] and res[0][3] == res[1][3]

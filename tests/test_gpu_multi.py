@@ -108,6 +108,37 @@ def _worker(rank, world, port, q, late_modes=False):
             # fixed), so they agree to rounding, like any two runs of the 1-GPU product
             oks.append(bool(((gdat - dat1).abs() <= 1e-9 * dat1.abs().max()).all()))
             del keep, m1
+            # row-partitioned BiCGSTAB (operator form over the put exchange): same bits on
+            # every rank, the solution of the 1-GPU solver to rounding
+            import numpy as np
+            import scipy.sparse as sparse
+            from sprs_b200.dist import row_partitioned_bicgstab
+            rs = np.random.default_rng(5)
+            ns = 20_000
+            S = sparse.random(ns, ns, density=8 / ns, random_state=rs, format="csr")
+            S = (S + sparse.diags(np.asarray(abs(S).sum(axis=1)).ravel() + 1.0)).tocsr()
+            S.sort_indices()
+            sip, sind, sd = S.indptr.astype(np.uint32), S.indices.astype(np.uint32), S.data.copy()
+            rhs = rs.standard_normal(ns)
+            bb = nnz_balanced_bounds(sip, world)
+            q0, q1 = bb[rank], bb[rank + 1]
+            blkm = sp.CsMat((q1 - q0, ns), sip[q0:q1 + 1] - sip[q0], sind[sip[q0]:sip[q1]],
+                            sd[sip[q0]:sip[q1]], ctx=ctx)
+            pops = [PushAllGatherSpMV(ctx, blkm.device(), bb, rank, world, ns, dist, dev)
+                    for _ in range(2)]   # two y buffers: see row_partitioned_bicgstab
+            sol = row_partitioned_bicgstab(ctx, pops, ns, np.zeros(ns), rhs, dev).run(1e-9, 200)
+            one = sp.linalg.BiCGSTAB.solve(sp.CsMat((ns, ns), sip, sind, sd, ctx=ctx), np.zeros(ns),
+                                           rhs, 1e-9, 200)
+            xs = sol.x()
+            oks.append(bool(np.allclose(xs, one.x(), rtol=1e-7, atol=1e-10)))
+            oks.append(float(np.linalg.norm(rhs - S @ xs)) < 1.001e-9)
+            mine = torch.from_numpy(xs).to(dev)
+            other = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(other, mine)
+            oks.append(all(bool(torch.equal(o, mine)) for o in other))
+            del sol
+            for po in pops:
+                po.close()
         q.put((rank, ok_nccl, all(oks)))
     finally:
         dist.destroy_process_group()

@@ -158,6 +158,37 @@ def test_bicgstab_err_and_contracts(sp):
     assert s2.step() == s0.__class__(a, np.zeros(n), b).step()  # repeatable to the last bit
 
 
+def test_bicgstab_operator_form_matches_matrix_form(sp):
+    """sprs_b200_bicgstab_new_op: y = A x through a caller-supplied operator (here the same
+    device SpMV, enqueued on the solver's stream) -- the same bits as the matrix form, step by
+    step.  This is the hook the row-partitioned solver hangs its SpMV + all-gather on."""
+    import ctypes as C
+    n = 3000
+    A, csr, b = dominant_system(n, 9, 31)
+    a = sp.CsMat((n, n), *csr)
+    ctx, mirror = a.context(), a.device()
+    calls = []
+
+    def matvec(d_x, d_y, stream):
+        calls.append(stream)
+        ctx.check(ctx.lib.sprs_b200_spmv_dev(ctx.h, mirror.h, C.c_void_p(d_x), C.c_void_p(d_y), 0,
+                                             C.c_void_p(stream)))
+
+    s_op = sp.linalg.BiCGSTAB.with_operator(ctx, n, matvec, np.zeros(n), b)
+    s_mat = sp.linalg.BiCGSTAB(a, np.zeros(n), b)
+    assert len(calls) == 1 and s_op.err() == s_mat.err()
+    for _ in range(5):
+        assert s_op.step() == s_mat.step()
+    assert np.array_equal(s_op.x(), s_mat.x()) and np.array_equal(s_op.p(), s_mat.p())
+    assert len(calls) == 11
+    s_op.run(1e-9, 100)
+    s_mat.run(1e-9, 100)
+    assert s_op.iteration_count() == s_mat.iteration_count()
+    assert np.array_equal(s_op.x(), s_mat.x())
+    with pytest.raises(ZeroDivisionError):       # the operator's exception, not a status code
+        sp.linalg.BiCGSTAB.with_operator(ctx, n, lambda *a: 1 // 0, np.zeros(n), b)
+
+
 def test_cpp_bicgstab():
     exe = os.path.join(ROOT, "tests", "cpp", "test_bicgstab")
     if not os.path.exists(exe):
