@@ -318,7 +318,12 @@ class FusedAllGatherSpMV:
     theirs.  step() launches ONE SpMV whose epilogue stores every finished row of this
     rank's block into all `world` buffers over NVLink (sprs_b200_spmv_allgather_dev); a
     stream-ordered 1-element all-reduce is the only remaining collective: it is the barrier
-    after which every rank's y is complete."""
+    after which every rank's y is complete.
+
+    An iterative caller that reads y on every rank and then calls step() again must either
+    finish reading before ANY rank can start the next step (a second barrier), or alternate
+    between two operators (two y buffers): a rank that runs ahead stores its rows of the next
+    product straight into its peers' y (row_partitioned_bicgstab does the latter)."""
 
     def __init__(self, ctx, mirror, bounds, rank, world, n, dist, device):
         import ctypes as C
