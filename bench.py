@@ -233,7 +233,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "overlap", "fused", "push", "stream", "chunked", "mcast", "mcast-push", "nccl"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "overlap", "fused", "push", "stream", "chunked", "mcast", "mcast-push", "mcast-stream", "mcast-chunked", "nccl"],
                     help="N>1 all-gather of y: 'overlap' = row block cut into chunks, each "
                          "chunk's y slice pushed to the peers by DMA copies on a second stream "
                          "while the next chunk computes; 'fused' = the SpMV kernel itself stores "
@@ -317,7 +317,7 @@ def main():
         # fused kernel measured 0.82 ms against 0.61 ms of pure compute -> fused from 6 GPUs up
         args.exchange = "fused" if world >= 6 else "push"
     fused = world > 1 and args.exchange in ("fused", "overlap", "push", "stream", "chunked",
-                                            "mcast", "mcast-push")
+                                            "mcast", "mcast-push", "mcast-stream", "mcast-chunked")
 
     def make_op(a_blk, bnds):
         if world > 1 and args.exchange == "overlap":
@@ -325,7 +325,7 @@ def main():
                                         chunks=args.chunks, row_cost=row_cost)
         elif fused and args.exchange.startswith("mcast"):
             o = McastAllGatherSpMV(ctx, a_blk.mirror, bnds, rank, world, n, dist, dev,
-                                   mode="push" if args.exchange == "mcast-push" else "fused",
+                                   mode=args.exchange.partition("-")[2] or "fused",
                                    barrier=args.barrier)
         elif fused:
             cls = {"push": PushAllGatherSpMV, "stream": StreamAllGatherSpMV,
@@ -524,6 +524,13 @@ def main():
                            "mcast-push": "SpMV, then one push kernel storing this rank's y slice "
                                          "to the NVSwitch multicast address of y + barrier (%s)"
                                          % args.barrier,
+                           "mcast-stream": "SpMV publishing its progress + concurrent put kernel "
+                                           "storing finished row chunks to the NVSwitch multicast "
+                                           "address of y + barrier (%s)" % args.barrier,
+                           "mcast-chunked": "SpMV in 4 chunks of decreasing size; behind each "
+                                            "chunk's event a side stream stores its rows to the "
+                                            "NVSwitch multicast address of y + barrier (%s)"
+                                            % args.barrier,
                            "nccl": "NCCL all_gather(y), unequal slices"}[args.exchange]),
                        "l2_policy": "inputs (%.1f GB) exceed L2 (126 MB); no flush needed" %
                                     (alg_bytes / 1e9),

@@ -476,14 +476,18 @@ class McastAllGatherSpMV:
       * mode "fused": the SpMV kernel itself (sprs_b200_spmv_allgather_dev with targets
         [local y, multicast y]) -- one extra store per finished row instead of world-1;
       * mode "push": the plain SpMV into the local y, then the put kernel copying this
-        rank's slice to the multicast address (sprs_b200_peer_push_dev with one "peer").
+        rank's slice to the multicast address (sprs_b200_peer_push_dev with one "peer");
+      * modes "stream" / "chunked": the pipelined puts of StreamAllGatherSpMV /
+        ChunkedPushAllGatherSpMV with the multicast address as their only remote target --
+        finished row chunks leave once, while the SpMV is still running.
 
     Barrier after the stores: the 1-element NCCL all-reduce of the other modes, or
     (barrier="symm") the signal-pad barrier of the symmetric-memory handle, a device-side
     flag exchange in peer memory with no NCCL kernel.
     Fails loudly when the devices have no multicast support (no silent fallback).
     Not yet run on hardware (written after round 1's GPU budget): opt-in
-    (`bench.py --exchange mcast|mcast-push`), to be measured by tools/r2_scale_probe.sh."""
+    (`bench.py --exchange mcast|mcast-push|mcast-stream|mcast-chunked`), to be measured by
+    tools/r2_scale_probe.sh."""
 
     def __init__(self, ctx, mirror, bounds, rank, world, n, dist, device, mode="fused",
                  barrier="nccl", group=None):
@@ -492,8 +496,8 @@ class McastAllGatherSpMV:
         import torch.distributed._symmetric_memory as symm
         from . import generate as G
         from .sparse import ThirdPartyError
-        if mode not in ("fused", "push") or barrier not in ("nccl", "symm"):
-            raise ValueError("mode: fused|push, barrier: nccl|symm")
+        if mode not in ("fused", "push", "stream", "chunked") or barrier not in ("nccl", "symm"):
+            raise ValueError("mode: fused|push|stream|chunked, barrier: nccl|symm")
         self.ctx, self.mirror, self.bounds, self.rank, self.world = ctx, mirror, bounds, rank, world
         self.dist, self.n, self.mode, self.barrier = dist, n, mode, barrier
         grp = group if group is not None else dist.group.WORLD
@@ -529,6 +533,14 @@ class McastAllGatherSpMV:
             ctx.check(ctx.lib.sprs_b200_spmv_allgather_dev(
                 ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()), r0, len(self._targets),
                 self._targets, 0, s))
+        elif self.mode == "stream":
+            ctx.check(ctx.lib.sprs_b200_spmv_stream_push_dev(
+                ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()), r0, len(self._targets),
+                self._targets, 0, 0, s))
+        elif self.mode == "chunked":
+            ctx.check(ctx.lib.sprs_b200_spmv_chunked_push_dev(
+                ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()), r0, len(self._targets),
+                self._targets, 0, 0, s))
         else:
             ctx.check(ctx.lib.sprs_b200_spmv_dev(ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()),
                                                  C.c_void_p(self._own + 8 * r0), 0, s))

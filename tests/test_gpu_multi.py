@@ -69,7 +69,7 @@ def _worker(rank, world, port, q, late_modes=False):
             import torch.distributed._symmetric_memory as symm
             from torch._C._autograd import DeviceType
             if symm._SymmetricMemory.has_multicast_support(DeviceType.CUDA, dev.index):
-                for mode in ("fused", "push"):
+                for mode in ("fused", "push", "stream", "chunked"):
                     for barrier in ("nccl", "symm"):
                         check_mode(lambda: McastAllGatherSpMV(ctx, a.mirror, bounds, rank, world, n,
                                                               dist, dev, mode=mode, barrier=barrier))

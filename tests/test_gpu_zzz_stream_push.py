@@ -161,7 +161,8 @@ class _FakeDist:
         self.all_reduces += 1
 
 
-@pytest.mark.parametrize("mode,barrier", [("fused", "nccl"), ("push", "symm"), ("fused", "symm")])
+@pytest.mark.parametrize("mode,barrier", [("fused", "nccl"), ("push", "symm"), ("fused", "symm"),
+                                          ("stream", "nccl"), ("chunked", "symm")])
 def test_mcast_allgather_host_logic(sp, monkeypatch, mode, barrier):
     import torch
     import torch.distributed._symmetric_memory as symm

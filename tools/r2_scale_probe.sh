@@ -3,7 +3,7 @@
 #   gpurun --gpus 8 --timeout 900 -- 'bash tools/r2_scale_probe.sh 8 "mcast mcast-push chunked stream fused push"'
 # mcast / mcast-push = NVSwitch multicast stores (one store per row instead of 7); a third word
 # selects their barrier: BARRIER=symm bash tools/r2_scale_probe.sh 8 "mcast mcast-push"
-n=${1:-8}; modes=${2:-"mcast mcast-push chunked stream fused push"}; barrier=${BARRIER:-nccl}
+n=${1:-8}; modes=${2:-"mcast mcast-push mcast-stream mcast-chunked chunked stream fused push"}; barrier=${BARRIER:-nccl}
 out=gpurun_out/r2_scale; mkdir -p $out
 for ex in $modes; do
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 \
