@@ -272,6 +272,29 @@ def one_case(sp, O, seed):
         e = gate(cm.data, cd, cb, "spgemm values")
         if e:
             errs.append(e)
+        # storage dispatch (csmat.rs:1895-1949): CSC operands route through transposes; the
+        # result is CSC only for CSC x CSR / CSC x CSC, and always the same matrix
+        if (seed & 3) == 0 and rows * cols <= 200000:
+            a_csc, b_csc = af2.to_other_storage(), bm.to_other_storage()
+            for lhs, rhs, want_csc in ((af2, b_csc, False), (a_csc, bm, True), (a_csc, b_csc, True)):
+                got = lhs * rhs
+                if got.is_csc() != want_csc:
+                    errs.append("spgemm dispatch: wrong result storage")
+                    continue
+                g = got.to_other_storage() if want_csc else got
+                if not (np.array_equal(g.indptr, cip) and np.array_equal(g.indices, cind)):
+                    errs.append("spgemm dispatch: pattern differs from CSR x CSR")
+                elif gate(g.data, cd, cb, "spgemm dispatch values"):
+                    errs.append("spgemm dispatch: values differ from CSR x CSR")
+    # ---- row slices: slice_outer + proper_indptr upload (slicing.rs:65-89), SpMV on the view
+    if rows >= 3:
+        lo = int(rng.integers(0, rows - 1))
+        hi = int(rng.integers(lo + 1, rows + 1))
+        sl = af.slice_outer(lo, hi)
+        ys = sl * x
+        e = gate(ys, refc[lo:hi], bc[lo:hi], "spmv on a row slice")
+        if e:
+            errs.append(e)
     # ---- BiCGSTAB on a diagonally dominant system built from the same pattern
     if rows == cols and rows >= 2:
         e = solver_case(sp, O, rng, rows, ip, ind, finite)
