@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <cstring>
 #include <functional>
+#include <limits>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -220,6 +221,10 @@ class CsMatI {
     }
     // to_other_storage (csmat.rs:1405-1426) through the device counting sort
     CsMatI to_other_storage() const {
+        // raw::convert_mat_storage asserts that rows() fits the index type before any work
+        // (csmat.rs:1794-1797; sprs/tests/gh374.rs)
+        if ((uint64_t)rows_ > (uint64_t)std::numeric_limits<I>::max())
+            throw Panic("Index type is not large enough to hold the number of rows requested");
         Context& ctx = Context::thread_default();
         sprs_b200_csmat* t = nullptr;
         ctx.check(sprs_b200_csmat_to_other_storage(ctx.handle(), device(), &t));

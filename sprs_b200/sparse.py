@@ -369,6 +369,12 @@ class CsMat:
 
     def to_other_storage(self):
         """to_other_storage (csmat.rs:1405-1426) via the device counting sort."""
+        # raw::convert_mat_storage asserts that rows() fits the index type before any work
+        # (csmat.rs:1794-1797; sprs/tests/gh374.rs)
+        if self.rows() > np.iinfo(self.indices.dtype).max:
+            raise SprsPanic("Index type is not large enough to hold the number of rows requested "
+                            "(I::max_value=%d vs. required %d)"
+                            % (np.iinfo(self.indices.dtype).max, self.rows()))
         d = self.device().to_other_storage()
         ip, ind, dat = d.download(self.indices.dtype, self.indptr.dtype)
         return CsMat(self.shape, ip, ind, dat, CSC if self.storage == CSR else CSR,

@@ -75,6 +75,15 @@ def test_host_structure_checks():
     assert m.transpose_view().shape == (3, 2) and m.transpose_view().is_csc()
     s = sp.CsMat.new((4, 4), [0, 1, 2, 3, 4], [0, 1, 2, 3], np.ones(4)).slice_outer(1, 3)
     assert s.shape == (2, 4) and s.indptr[0] == 1 and s.nnz() == 2
+    # sprs/tests/gh374.rs: a transposition whose row count does not fit the index type panics
+    # before any work (csmat.rs:1794-1797).  2^31 rows with i32 indices; the panic precedes
+    # every use of the arrays, so a header-only object is enough (no 8 GB indptr)
+    big = object.__new__(sp.CsMat)
+    big.storage, big.shape = sp.CSR, (1 << 31, 16)
+    big.indptr, big.indices, big.data = np.zeros(2, np.int64), np.zeros(0, np.int32), np.zeros(0)
+    big._ctx = big._dev = None
+    with pytest.raises(sp.SprsPanic, match="Index type is not large enough to hold"):
+        big.to_other_storage()
 
 
 def test_bicgstab_contract_checks_precede_device_work():
