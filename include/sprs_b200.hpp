@@ -418,6 +418,22 @@ CsVecI<I> operator*(const CsMatI<I, Iptr>& a, const CsVecI<I>& v) {
         }
     return res;
 }
+namespace prod {
+// prod::csvec_dot_by_binary_search (prod.rs:13-72): the matching entries of two sparse
+// vectors multiplied and summed in ascending index order = row_view(vec1) times vec2 through
+// the device merge-dot kernel (same terms, same order, same bits).
+template <class I>
+double csvec_dot_by_binary_search(const CsVecI<I>& vec1, const CsVecI<I>& vec2) {
+    if (vec1.nnz() == 0 || vec2.nnz() == 0) return 0.0;
+    const size_t dim = vec1.dim > vec2.dim ? vec1.dim : vec2.dim;
+    auto row = CsMatI<I, I>::new_({1, dim}, {(I)0, (I)vec1.nnz()}, vec1.indices, vec1.data);
+    Context& ctx = Context::thread_default();
+    double y = 0.0;
+    ctx.check(sprs_b200_csr_mul_csvec(ctx.handle(), row.device(), dim, vec2.nnz(),
+                                      vec2.indices.data(), (int)sizeof(I), vec2.data.data(), &y, 1));
+    return y;
+}
+}  // namespace prod
 // `&v * &A` = row_view(v) * A (vec.rs:1084-1102)
 template <class I, class Iptr>
 CsVecI<I> operator*(const CsVecI<I>& v, const CsMatI<I, Iptr>& a) {

@@ -125,6 +125,17 @@ def csr_mul_csvec(indptr, indices, data, v_indices, v_data):
     return oi[:n].copy(), od[:n].copy()
 
 
+def csvec_dot_by_binary_search(i1, d1, i2, d2):
+    """prod.rs:13-72: dot product of two sparse vectors (indices ascending)."""
+    i1 = np.ascontiguousarray(i1, dtype=np.uint64)
+    i2 = np.ascontiguousarray(i2, dtype=np.uint64)
+    d1 = np.ascontiguousarray(d1, dtype=np.float64)
+    d2 = np.ascontiguousarray(d2, dtype=np.float64)
+    f = getattr(lib(), "oracle_csvec_dot_by_binary_search_" + _suffix(i1, i1))
+    f.restype = C.c_double
+    return float(f(C.c_size_t(len(i1)), _p(i1), _p(d1), C.c_size_t(len(i2)), _p(i2), _p(d2)))
+
+
 def convert_mat_storage(outer, inner, indptr, indices, data):
     """csmat.rs:1782-1829: CSR<->CSC; returns (indptr, indices, data)."""
     indptr, indices, data = _csx(indptr, indices, data)

@@ -179,6 +179,43 @@ size_t csr_mul_csvec(size_t rows, const P* indptr, const I* indices,
     return n_out;
 }
 
+// prod.rs:13-72 csvec_dot_by_binary_search(+_impl): walk the vector with fewer entries,
+// binary-search each index in the (shrinking) tail of the other, mul_acc on a match.
+// The operand order of the product is preserved by the closure (prod.rs:25-32).
+template <class I>
+double csvec_dot_by_binary_search(size_t n1, const I* i1, const double* d1, size_t n2,
+                                  const I* i2, const double* d2) {
+    const bool swapped = n1 > n2;  // vec1.nnz() > vec2.nnz(): search in vec1 instead
+    if (swapped) {
+        std::swap(n1, n2);
+        std::swap(i1, i2);
+        std::swap(d1, d2);
+    }
+    double sum = 0.0;
+    while (n1 != 0 && n2 != 0) {
+        // slice::binary_search: Ok(i) when found, Err(i) = insertion point
+        size_t lo = 0, hi = n2;
+        bool found = false;
+        while (lo < hi) {
+            const size_t mid = lo + (hi - lo) / 2;
+            if (i2[mid] == i1[0]) {
+                found = true;
+                lo = mid;
+                break;
+            }
+            if (i2[mid] < i1[0]) lo = mid + 1;
+            else hi = mid;
+        }
+        if (found) {
+            const double prod = swapped ? d2[lo] * d1[0] : d1[0] * d2[lo];
+            sum = sum + prod;
+        }
+        ++i1, ++d1, --n1;
+        i2 += lo, d2 += lo, n2 -= lo;
+    }
+    return sum;
+}
+
 // csmat.rs:1782-1829  raw::convert_mat_storage : counting-sort transpose
 // (CSR<->CSC).  `inner` = inner dimension of the input.
 template <class I, class P>
@@ -580,6 +617,12 @@ Bicgstab* bicgstab_new(size_t rows, const P* ip, const I* ind, const double* d, 
                                                  const double* d, size_t vn, const I* vi,       \
                                                  const double* vd, I* oi, double* od) {         \
         return csr_mul_csvec<I, P>(rows, ip, ind, d, vn, vi, vd, oi, od);                       \
+    }                                                                                           \
+    extern "C" double oracle_csvec_dot_by_binary_search_##SUF(size_t n1, const I* i1,           \
+                                                              const double* d1, size_t n2,      \
+                                                              const I* i2, const double* d2) {  \
+        (void)sizeof(P);                                                                        \
+        return csvec_dot_by_binary_search<I>(n1, i1, d1, n2, i2, d2);                           \
     }                                                                                           \
     extern "C" void oracle_convert_mat_storage_##SUF(size_t outer, size_t inner, const P* ip,   \
                                                      const I* ind, const double* d, P* oip,     \

@@ -526,6 +526,23 @@ class prod:
         prod._dense("csc_mulacc_dense_colmaj", lhs, rhs, out)
 
     @staticmethod
+    def csvec_dot_by_binary_search(vec1, vec2):
+        """prod.rs:13-72: dot product of two sparse vectors -- the matching entries multiplied
+        and summed in ascending index order.  On the device this is row_view(vec1) times vec2
+        through the merge-dot kernel (csrc/csvec.cu): same terms, same order, same bits."""
+        if vec1.nnz() == 0 or vec2.nnz() == 0:
+            return 0.0
+        dim = max(vec1.dim, vec2.dim)  # the reference does not compare the dimensions here
+        row = CsMat((1, dim), np.array([0, vec1.nnz()]), vec1.indices, vec1.data)
+        ctx = row.context()
+        vi = np.ascontiguousarray(vec2.indices, dtype=np.uint64)
+        vd = np.ascontiguousarray(vec2.data, dtype=np.float64)
+        y = np.empty(1)
+        ctx.check(ctx.lib.sprs_b200_csr_mul_csvec(ctx.h, row.device().h, dim, vi.size, _ptr(vi), 8,
+                                                  _ptr(vd), _ptr(y), 1))
+        return float(y[0])
+
+    @staticmethod
     def csr_mul_csvec(lhs, rhs):
         """prod.rs:162-184: row i of the result is the sorted-merge dot of row i with rhs
         (vec.rs:846-881) -- only entries present in both patterns are multiplied, summed in

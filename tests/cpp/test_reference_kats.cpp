@@ -106,6 +106,14 @@ static void csvec_products() {
     CHECK(CsMat::eye(5) * x == x);
     CsVec zero(0, {}, {});
     CHECK(mat1() * zero == zero);
+    // prod.rs:312-323 test_csvec_dot_by_binary_search
+    CsVec v1(8, {0, 2, 4, 6}, {1., 1., 1., 1.}), v2(8, {1, 3, 5, 7}, {2., 2., 2., 2.}),
+        v3(8, {1, 2, 5, 6}, {3., 3., 3., 3.});
+    CHECK(prod::csvec_dot_by_binary_search(v1, v2) == 0.);
+    CHECK(prod::csvec_dot_by_binary_search(v1, v1) == 4.);
+    CHECK(prod::csvec_dot_by_binary_search(v2, v2) == 16.);
+    CHECK(prod::csvec_dot_by_binary_search(v1, v3) == 6.);
+    CHECK(prod::csvec_dot_by_binary_search(v2, v3) == 12.);
 }
 // prod.rs:503-595 dense products
 static void dense_products() {

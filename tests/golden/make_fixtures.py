@@ -106,6 +106,14 @@ F["kat_csvec"] = {
     "v": {"dim": 5, "indices": [0, 2, 4], "data": [1., 1., 1.]},
     "mat1_times_v": {"dim": 5, "indices": [0, 1, 2], "data": [3., 5., 5.]},
     "v_times_mat1": {"dim": 5, "indices": [2, 3], "data": [8., 11.]}}
+# ---- sprs/src/sparse/prod.rs:312-323 test_csvec_dot_by_binary_search
+F["kat_csvec_dot"] = {
+    "dim": 8,
+    "vec1": {"indices": [0, 2, 4, 6], "data": [1., 1., 1., 1.]},
+    "vec2": {"indices": [1, 3, 5, 7], "data": [2., 2., 2., 2.]},
+    "vec3": {"indices": [1, 2, 5, 6], "data": [3., 3., 3., 3.]},
+    "expected": [["vec1", "vec2", 0.], ["vec1", "vec1", 4.], ["vec2", "vec2", 16.],
+                 ["vec1", "vec3", 6.], ["vec2", "vec3", 12.]]}
 # ---- sprs/src/lib.rs:54-60 README: eye(5) * CsVec == x
 F["kat_readme_eye"] = {"n": 5, "x": {"dim": 5, "indices": [0, 2, 4], "data": [1., 2., 3.]}}
 # ---- sprs/src/sparse/smmp.rs:476-489 mul_zero_rows ; csmat.rs:3047-3052 issue_99

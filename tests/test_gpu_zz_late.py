@@ -267,3 +267,18 @@ def test_csr_mul_csvec_structural_zeros_non_finite(sp, O):
     # skipped); row 2: 3 - 3 = 0 dropped; row 3: Inf*0 + 7 = NaN kept; row 4 empty; row 5: -0.0
     assert res.indices.tolist() == [0, 3]
     assert res.data[0] == 21.0 and np.isnan(res.data[1])
+
+
+def test_csvec_dot_by_binary_search(sp, O, fixtures):
+    """prod.rs:13-72 and its test (:312-323): the device result equals the reference's
+    answers and, on random vectors, the oracle's bits."""
+    k = fixtures["kat_csvec_dot"]
+    vec = {n: sp.CsVec(k["dim"], k[n]["indices"], k[n]["data"]) for n in ("vec1", "vec2", "vec3")}
+    for n1, n2, want in k["expected"]:
+        assert sp.prod.csvec_dot_by_binary_search(vec[n1], vec[n2]) == want
+    rng = np.random.default_rng(8)
+    for n1, n2 in ((5, 900), (900, 5), (300, 300), (0, 4), (1, 1)):
+        i1, i2 = (np.sort(rng.choice(1000, n, replace=False)) for n in (n1, n2))
+        d1, d2 = rng.standard_normal(n1), rng.standard_normal(n2)
+        got = sp.prod.csvec_dot_by_binary_search(sp.CsVec(1000, i1, d1), sp.CsVec(1000, i2, d2))
+        assert got == O.csvec_dot_by_binary_search(i1, d1, i2, d2)

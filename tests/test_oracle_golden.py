@@ -196,6 +196,22 @@ def test_mul_zero_rows_and_issue_99():
     assert cip.tolist() == [0] * 11 and len(cind) == 0
 
 
+def test_csvec_dot_by_binary_search(fixtures):
+    """prod.rs:312-323."""
+    k = fixtures["kat_csvec_dot"]
+    for n1, n2, want in k["expected"]:
+        a, b = k[n1], k[n2]
+        assert O.csvec_dot_by_binary_search(a["indices"], a["data"], b["indices"], b["data"]) == want
+    # random: equals the merge dot (same terms, ascending order), whichever vector is shorter
+    rng = np.random.default_rng(3)
+    for n1, n2 in ((5, 200), (200, 5), (60, 60), (0, 9)):
+        i1, i2 = (np.sort(rng.choice(300, n, replace=False)) for n in (n1, n2))
+        d1, d2 = rng.standard_normal(n1), rng.standard_normal(n2)
+        oi, od = O.csr_mul_csvec(np.array([0, n1], np.uint64), i1.astype(np.uint64), d1, i2, d2)
+        want = od[0] if len(od) else 0.0
+        assert O.csvec_dot_by_binary_search(i1, d1, i2, d2) == want
+
+
 def test_csvec_products(fixtures):
     """prod.rs:461-468 mul_csr_csvec; lib.rs:54-60 README eye(5)*CsVec;
     prod.rs:470-474 zero-dim CsVec handled by the host wrapper."""
