@@ -418,20 +418,40 @@ CsVecI<I> operator*(const CsMatI<I, Iptr>& a, const CsVecI<I>& v) {
         }
     return res;
 }
-namespace prod {
-// prod::csvec_dot_by_binary_search (prod.rs:13-72): the matching entries of two sparse
-// vectors multiplied and summed in ascending index order = row_view(vec1) times vec2 through
-// the device merge-dot kernel (same terms, same order, same bits).
+// Sum of v1[i] * rhs[i] over the common pattern in ascending index order (dot_acc,
+// vec.rs:846-881) on the device: row_view(v1) through the merge-dot kernel (csrc/csvec.cu),
+// the reference's terms in the reference's order.
 template <class I>
-double csvec_dot_by_binary_search(const CsVecI<I>& vec1, const CsVecI<I>& vec2) {
-    if (vec1.nnz() == 0 || vec2.nnz() == 0) return 0.0;
-    const size_t dim = vec1.dim > vec2.dim ? vec1.dim : vec2.dim;
-    auto row = CsMatI<I, I>::new_({1, dim}, {(I)0, (I)vec1.nnz()}, vec1.indices, vec1.data);
+double merge_dot(const CsVecI<I>& v1, size_t dim, const std::vector<I>& idx,
+                 const std::vector<double>& dat) {
+    if (v1.nnz() == 0 || idx.empty()) return 0.0;
+    auto row = CsMatI<I, I>::new_({1, dim}, {(I)0, (I)v1.nnz()}, v1.indices, v1.data);
     Context& ctx = Context::thread_default();
     double y = 0.0;
-    ctx.check(sprs_b200_csr_mul_csvec(ctx.handle(), row.device(), dim, vec2.nnz(),
-                                      vec2.indices.data(), (int)sizeof(I), vec2.data.data(), &y, 1));
+    ctx.check(sprs_b200_csr_mul_csvec(ctx.handle(), row.device(), dim, idx.size(), idx.data(),
+                                      (int)sizeof(I), dat.data(), &y, 1));
     return y;
+}
+// CsVecBase::dot (vec.rs:825-881) with a sparse rhs; panics if the dimensions differ
+template <class I>
+double dot(const CsVecI<I>& v1, const CsVecI<I>& v2) {
+    if (v1.dim != v2.dim) throw Panic("Dimension mismatch");
+    return merge_dot(v1, v1.dim, v2.indices, v2.data);
+}
+// CsVecBase::dot_dense (vec.rs:894-904) / dot with a dense rhs
+template <class I>
+double dot_dense(const CsVecI<I>& v1, const Array1& rhs) {
+    if (v1.dim != rhs.size()) throw Panic("Dimension mismatch");
+    std::vector<I> all(rhs.size());
+    for (size_t i = 0; i < all.size(); ++i) all[i] = (I)i;
+    return merge_dot(v1, v1.dim, all, std::vector<double>(rhs.data(), rhs.data() + rhs.size()));
+}
+namespace prod {
+// prod::csvec_dot_by_binary_search (prod.rs:13-72): the same sum (matching entries in
+// ascending index order); the reference does not compare the dimensions here.
+template <class I>
+double csvec_dot_by_binary_search(const CsVecI<I>& vec1, const CsVecI<I>& vec2) {
+    return merge_dot(vec1, vec1.dim > vec2.dim ? vec1.dim : vec2.dim, vec2.indices, vec2.data);
 }
 }  // namespace prod
 // `&v * &A` = row_view(v) * A (vec.rs:1084-1102)

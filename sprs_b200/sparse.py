@@ -185,6 +185,38 @@ class CsVec:
         return "CsVec(dim=%d, indices=%s, data=%s)" % (self.dim, self.indices.tolist(),
                                                         self.data.tolist())
 
+    def _merge_dot(self, dim, idx, dat):
+        """Sum of self[i] * rhs[i] over the common pattern in ascending index order (dot_acc,
+        vec.rs:846-881) on the device: row_view(self) through the merge-dot kernel
+        (csrc/csvec.cu) -- the reference's terms in the reference's order."""
+        if self.nnz() == 0 or len(idx) == 0:
+            return 0.0
+        row = CsMat((1, dim), np.array([0, self.nnz()]), self.indices, self.data)
+        ctx = row.context()
+        vi = np.ascontiguousarray(idx, dtype=np.uint64)
+        vd = np.ascontiguousarray(dat, dtype=np.float64)
+        y = np.empty(1)
+        ctx.check(ctx.lib.sprs_b200_csr_mul_csvec(ctx.h, row.device().h, dim, vi.size, _ptr(vi), 8,
+                                                  _ptr(vd), _ptr(y), 1))
+        return float(y[0])
+
+    def dot(self, rhs):
+        """CsVecBase::dot / dot_acc (vec.rs:825-881): rhs is a CsVec (sorted-merge dot) or any
+        dense vector (every entry of self meets one of rhs).  Panics if the dimensions differ
+        (`assert_eq!(self.dim(), rhs.dim())`, vec.rs:856)."""
+        if isinstance(rhs, CsVec):
+            if self.dim != rhs.dim:
+                raise SprsPanic("Dimension mismatch: %d != %d" % (self.dim, rhs.dim))
+            return self._merge_dot(self.dim, rhs.indices, rhs.data)
+        return self.dot_dense(rhs)
+
+    def dot_dense(self, rhs):
+        """CsVecBase::dot_dense (vec.rs:894-904)."""
+        d = np.ascontiguousarray(rhs, dtype=np.float64)
+        if d.ndim != 1 or d.size != self.dim:
+            raise SprsPanic("Dimension mismatch: %d != %d" % (self.dim, d.size))
+        return self._merge_dot(self.dim, np.arange(self.dim, dtype=np.uint64), d)
+
     # `&v * &A` = row_view(v) * A (vec.rs:1084-1102)
     def __mul__(self, rhs):
         if isinstance(rhs, CsMat):
@@ -530,17 +562,8 @@ class prod:
         """prod.rs:13-72: dot product of two sparse vectors -- the matching entries multiplied
         and summed in ascending index order.  On the device this is row_view(vec1) times vec2
         through the merge-dot kernel (csrc/csvec.cu): same terms, same order, same bits."""
-        if vec1.nnz() == 0 or vec2.nnz() == 0:
-            return 0.0
-        dim = max(vec1.dim, vec2.dim)  # the reference does not compare the dimensions here
-        row = CsMat((1, dim), np.array([0, vec1.nnz()]), vec1.indices, vec1.data)
-        ctx = row.context()
-        vi = np.ascontiguousarray(vec2.indices, dtype=np.uint64)
-        vd = np.ascontiguousarray(vec2.data, dtype=np.float64)
-        y = np.empty(1)
-        ctx.check(ctx.lib.sprs_b200_csr_mul_csvec(ctx.h, row.device().h, dim, vi.size, _ptr(vi), 8,
-                                                  _ptr(vd), _ptr(y), 1))
-        return float(y[0])
+        # the reference does not compare the dimensions here
+        return vec1._merge_dot(max(vec1.dim, vec2.dim), vec2.indices, vec2.data)
 
     @staticmethod
     def csr_mul_csvec(lhs, rhs):

@@ -114,6 +114,16 @@ static void csvec_products() {
     CHECK(prod::csvec_dot_by_binary_search(v2, v2) == 16.);
     CHECK(prod::csvec_dot_by_binary_search(v1, v3) == 6.);
     CHECK(prod::csvec_dot_by_binary_search(v2, v3) == 12.);
+    // vec.rs:1649-1689 dot_product (+ the two panics)
+    CHECK(dot(v1, v2) == 0. && dot(v1, v1) == 4. && dot(v2, v2) == 16. && dot(v1, v3) == 6. &&
+          dot(v2, v3) == 12.);
+    Array1 dense(8);
+    for (size_t i = 0; i < 8; ++i) dense[i] = (double)(i + 1);
+    CHECK(dot_dense(v1, dense) == 16.);
+    bool p1 = false, p2 = false;
+    try { dot(v1, CsVec(9, {1, 3, 5, 7}, {2., 2., 2., 2.})); } catch (const Panic&) { p1 = true; }
+    try { dot_dense(v1, Array1(9, 1.0)); } catch (const Panic&) { p2 = true; }
+    CHECK(p1 && p2);
 }
 // prod.rs:503-595 dense products
 static void dense_products() {

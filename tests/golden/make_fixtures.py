@@ -113,7 +113,11 @@ F["kat_csvec_dot"] = {
     "vec2": {"indices": [1, 3, 5, 7], "data": [2., 2., 2., 2.]},
     "vec3": {"indices": [1, 2, 5, 6], "data": [3., 3., 3., 3.]},
     "expected": [["vec1", "vec2", 0.], ["vec1", "vec1", 4.], ["vec2", "vec2", 16.],
-                 ["vec1", "vec3", 6.], ["vec2", "vec3", 12.]]}
+                 ["vec1", "vec3", 6.], ["vec2", "vec3", 12.]],
+    # sprs/src/sparse/vec.rs:1649-1689 dot_product (same vectors and answers through
+    # CsVec::dot) + the dense right-hand side and the two dimension panics
+    "dense": [1., 2., 3., 4., 5., 6., 7., 8.], "vec1_dot_dense": 16.,
+    "panic_dims": {"sparse": 9, "dense": 9}}
 # ---- sprs/src/lib.rs:54-60 README: eye(5) * CsVec == x
 F["kat_readme_eye"] = {"n": 5, "x": {"dim": 5, "indices": [0, 2, 4], "data": [1., 2., 3.]}}
 # ---- sprs/src/sparse/smmp.rs:476-489 mul_zero_rows ; csmat.rs:3047-3052 issue_99

@@ -282,3 +282,19 @@ def test_csvec_dot_by_binary_search(sp, O, fixtures):
         d1, d2 = rng.standard_normal(n1), rng.standard_normal(n2)
         got = sp.prod.csvec_dot_by_binary_search(sp.CsVec(1000, i1, d1), sp.CsVec(1000, i2, d2))
         assert got == O.csvec_dot_by_binary_search(i1, d1, i2, d2)
+
+
+def test_csvec_dot(sp, fixtures):
+    """vec.rs:1649-1689 dot_product / dot_product_panics / dot_product_panics2."""
+    k = fixtures["kat_csvec_dot"]
+    vec = {n: sp.CsVec(k["dim"], k[n]["indices"], k[n]["data"]) for n in ("vec1", "vec2", "vec3")}
+    for n1, n2, want in k["expected"]:
+        assert vec[n1].dot(vec[n2]) == want
+    dense = np.array(k["dense"])
+    assert vec["vec1"].dot(dense) == k["vec1_dot_dense"]
+    assert vec["vec1"].dot_dense(list(dense)) == k["vec1_dot_dense"]
+    assert vec["vec1"].dot_dense(np.linspace(1., 8., 8)) == k["vec1_dot_dense"]
+    with pytest.raises(sp.SprsPanic):
+        vec["vec1"].dot(sp.CsVec(k["panic_dims"]["sparse"], k["vec2"]["indices"], k["vec2"]["data"]))
+    with pytest.raises(sp.SprsPanic):
+        vec["vec1"].dot(np.arange(float(k["panic_dims"]["dense"])))
