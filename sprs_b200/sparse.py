@@ -356,9 +356,24 @@ class CsMat:
 
     transpose_into = transpose_view
 
-    def slice_outer(self, start, stop):
+    def __iter__(self):
+        """`into_iter` of a matrix view (csmat.rs): (value, (row, col)) in storage order."""
+        ip = self.indptr.astype(np.int64) - int(self.indptr[0])
+        for o in range(self.outer_dims()):
+            for k in range(int(ip[o]), int(ip[o + 1])):
+                i = int(self.indices[k])
+                yield float(self.data[k]), ((o, i) if self.is_csr() else (i, o))
+
+    def slice_outer(self, start=None, stop=None):
         """slice_outer (slicing.rs:65-89): contiguous outer block, NON-zero-based indptr
-        kept as is (indptr.rs:122-124); the upload rebases it (proper_indptr)."""
+        kept as is (indptr.rs:122-124); the upload rebases it (proper_indptr).  None = the
+        open end of a range (`..5`, `9..`, `..`); a `slice` object is accepted as well."""
+        if isinstance(start, slice):
+            start, stop = start.start, start.stop
+        start = 0 if start is None else int(start)
+        stop = self.outer_dims() if stop is None else int(stop)
+        if not 0 <= start <= stop <= self.outer_dims():
+            raise SprsPanic("Index out of bounds")  # range.rs / indptr.rs slice asserts
         t = object.__new__(CsMat)
         t.storage = self.storage
         n = stop - start

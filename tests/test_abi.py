@@ -75,6 +75,15 @@ def test_host_structure_checks():
     assert m.transpose_view().shape == (3, 2) and m.transpose_view().is_csc()
     s = sp.CsMat.new((4, 4), [0, 1, 2, 3, 4], [0, 1, 2, 3], np.ones(4)).slice_outer(1, 3)
     assert s.shape == (2, 4) and s.indptr[0] == 1 and s.nnz() == 2
+    # sprs/tests/slicing.rs:4-17, 50-75: slice_outer on eye(11), closed and open ranges
+    eye = sp.CsMat.eye(11)
+    assert list(eye.slice_outer(2, 7)) == [(1.0, (i, i + 2)) for i in range(5)]
+    assert list(eye.slice_outer(None, 5)) == [(1.0, (i, i)) for i in range(5)]
+    assert list(eye.slice_outer(9, None)) == [(1.0, (0, 9)), (1.0, (1, 10))]
+    assert list(eye.slice_outer(slice(9, None))) == [(1.0, (0, 9)), (1.0, (1, 10))]
+    assert eye.slice_outer() == eye
+    with pytest.raises(sp.SprsPanic):
+        eye.slice_outer(5, 12)
     # sprs/tests/gh374.rs: a transposition whose row count does not fit the index type panics
     # before any work (csmat.rs:1794-1797).  2^31 rows with i32 indices; the panic precedes
     # every use of the arrays, so a header-only object is enough (no 8 GB indptr)
