@@ -93,7 +93,6 @@ def gate(got, ref, bound, what):
 def push_case(sp, a, rows, cols, rng):
     import ctypes as C
     import torch
-    from sprs_b200 import generate as G
     ctx = sp.Context.default()
     mirror = a.device().h
     offset = int(rng.integers(0, 9))
