@@ -133,3 +133,91 @@ def test_bench_flags(fake_gpu, monkeypatch, capsys):
     line = _run_bench(monkeypatch, capsys, ["--steps", "2", "--no-cpu-baseline", "--no-extra"])
     assert "cpu_baseline" not in line and "extra" not in line
     assert line["warmup"] >= 3  # W >= 3 whatever the flag says
+
+
+# ---- tools/scale_modes.py (all exchange modes in one multi-GPU launch): control-flow dry run
+def _scale_modes_worker(rank, world, port, q):
+    import os
+    import socket  # noqa: F401
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import io
+    import contextlib
+    import torch.distributed as dist
+    import sprs_b200
+    from sprs_b200 import dist as D
+    from sprs_b200 import generate as G
+    real_device = torch.device
+    torch.device = lambda *a, **k: real_device("cpu")
+    torch.cuda.set_device = lambda d: None
+    torch.cuda.synchronize = lambda *a: None
+    torch.cuda.empty_cache = lambda: None
+    torch.cuda.Event = _FakeEvent
+    real_init = dist.init_process_group
+    dist.init_process_group = lambda backend, **k: real_init("gloo")
+    ctx = _FakeCtx()
+    sprs_b200.Context.default = classmethod(lambda cls, device=None: ctx)
+
+    def make_matrix(c, gen, n, npr, seed):
+        rng = np.random.default_rng(seed % (1 << 32))
+        return _FakeCsr(sps.random(n, n, density=npr / n, format="csr", random_state=rng,
+                                   data_rvs=rng.standard_normal))
+
+    def spmv(c, a, x, y, accumulate=False):
+        y.copy_(torch.from_numpy(a.m @ x.numpy()))
+        return y
+
+    G.make_matrix, G.spmv = make_matrix, spmv
+    G.normal_vector = lambda c, n, seed=1: torch.from_numpy(np.random.default_rng(seed).standard_normal(n))
+
+    class FakePeerOp(D.RowPartitionedSpMV):  # stands in for every peer-buffer exchange class
+        def __init__(self, c, mirror, bounds, rank, world, n, dist_, device, **kw):
+            if kw.get("mode") == "chunked" and kw.get("barrier") == "symm":
+                raise RuntimeError("pretend this combination is unavailable")  # the skip path
+            blk = mirror.owner
+            super().__init__(bounds, rank, world, torch.zeros(n, dtype=torch.float64),
+                             lambda xv, ys: spmv(c, blk, xv, ys), dist=dist_)
+
+        def close(self):
+            pass
+
+    for name in ("PushAllGatherSpMV", "FusedAllGatherSpMV", "StreamAllGatherSpMV",
+                 "ChunkedPushAllGatherSpMV", "McastAllGatherSpMV"):
+        setattr(D, name, FakePeerOp)
+    import scale_modes
+    sys.argv = ["scale_modes.py", "--n", "3000", "--npr", "10", "--steps", "2", "--warmup", "1",
+                "--modes", "push fused nccl mcast-push mcast-chunked stream"]
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        scale_modes.main()
+    q.put((rank, buf.getvalue()))
+
+
+def test_scale_modes_control_flow_gloo_world2():
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_scale_modes_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    lines = [json.loads(l) for l in res[0].splitlines() if l.startswith("{")]
+    assert res[1].strip() == ""                      # rank 0 alone reports
+    modes = [(d["mode"], d["barrier"]) for d in lines if "mode" in d]
+    assert modes == [("push", "nccl"), ("fused", "nccl"), ("nccl", "nccl"), ("mcast-push", "nccl"),
+                     ("mcast-push", "symm"), ("mcast-chunked", "nccl"), ("mcast-chunked", "symm"),
+                     ("stream", "nccl")]
+    done = [d for d in lines if "ms_per_step" in d]
+    assert len(done) == 7 and all(d["correct"] and d["speedup_vs_n1"] > 0 for d in done)
+    assert [d for d in lines if "skipped" in d][0]["mode"] == "mcast-chunked"
+    assert any("partition_round" in d for d in lines) and any("setup_seconds" in d for d in lines)

@@ -1,10 +1,19 @@
 #!/bin/bash
-# 8-GPU probe of the exchange modes incl. the pipelined put (charged 8x: keep it short).
-#   gpurun --gpus 8 --timeout 900 -- 'bash tools/r2_scale_probe.sh 8 "mcast mcast-push chunked stream fused push"'
-# mcast / mcast-push = NVSwitch multicast stores (one store per row instead of 7); a third word
-# selects their barrier: BARRIER=symm bash tools/r2_scale_probe.sh 8 "mcast mcast-push"
-n=${1:-8}; modes=${2:-"mcast mcast-push mcast-stream mcast-chunked chunked stream fused push"}; barrier=${BARRIER:-nccl}
+# 8-GPU probe of the exchange modes (charged 8x: keep it short).  Default: ONE launch that
+# shares the matrix, the rendezvous and the partition across all modes (tools/scale_modes.py,
+# ~3 min at 8 GPUs instead of ~1.2 min per mode):
+#   gpurun --gpus 8 --timeout 900 -- 'bash tools/r2_scale_probe.sh 8'
+# Per-mode bench.py runs (the contract's own command line) for the one or two winners:
+#   gpurun --gpus 8 --timeout 900 -- 'bash tools/r2_scale_probe.sh 8 "mcast-push fused"'
+n=${1:-8}; modes=${2:-}; barrier=${BARRIER:-nccl}
 out=gpurun_out/r2_scale; mkdir -p $out
+if [ -z "$modes" ]; then
+  timeout 800 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 \
+    --master-port $((29600 + RANDOM % 300)) tools/scale_modes.py --steps 20 \
+    2> $out/err_${n}_all.txt | tee $out/scale_modes_${n}.jsonl
+  echo "scale_modes exit ${PIPESTATUS[0]}"; tail -n 5 $out/err_${n}_all.txt
+  exit 0
+fi
 for ex in $modes; do
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 \
     --master-port $((29600 + RANDOM % 300)) bench.py --gpus $n --steps 20 --warmup 5 --no-cpu-baseline \
