@@ -18,6 +18,9 @@ pub const SPRS_B200_ERR_STORAGE: c_int = 2;
 pub const SPRS_B200_ERR_CUDA: c_int = 3;
 pub const SPRS_B200_ERR_NCCL: c_int = 4;
 pub const SPRS_B200_ERR_INDEX_RANGE: c_int = 5;
+pub const SPRS_B200_ERR_ARGUMENT: c_int = 6;
+pub const SPRS_B200_ERR_STRUCTURE: c_int = 7;
+pub const SPRS_B200_ERR_UNSUPPORTED: c_int = 8;
 pub const SPRS_B200_BICGSTAB_X: c_int = 0;
 pub const SPRS_B200_BICGSTAB_R: c_int = 1;
 pub const SPRS_B200_BICGSTAB_RHAT: c_int = 2;
@@ -100,4 +103,82 @@ extern "C" {
         s: *const sprs_b200_bicgstab, counts: *mut u64, scalars: *mut c_double) -> c_int;
     pub fn sprs_b200_bicgstab_get(
         s: *const sprs_b200_bicgstab, which: c_int, out: *mut c_double, len: u64) -> c_int;
+    // ---- the rest of include/sprs_b200.h: device-resident entry points, the device COO->CSR,
+    // multi-GPU plumbing (one process per GPU) and the synthetic-input generators
+    pub fn sprs_b200_ctx_device(ctx: *const sprs_b200_ctx) -> c_int;
+    pub fn sprs_b200_ctx_sm_count(ctx: *const sprs_b200_ctx) -> c_int;
+    pub fn sprs_b200_ctx_synchronize(ctx: *mut sprs_b200_ctx) -> c_int;
+    pub fn sprs_b200_csmat_from_device(
+        ctx: *mut sprs_b200_ctx, storage: c_int, rows: u64, cols: u64, nnz: u64,
+        d_indptr: *const u32, d_indices: *const u32, d_data: *const c_double,
+        out: *mut *mut sprs_b200_csmat) -> c_int;
+    pub fn sprs_b200_csmat_storage(m: *const sprs_b200_csmat) -> c_int;
+    pub fn sprs_b200_csmat_rows(m: *const sprs_b200_csmat) -> u64;
+    pub fn sprs_b200_csmat_cols(m: *const sprs_b200_csmat) -> u64;
+    pub fn sprs_b200_csmat_device_arrays(
+        m: *const sprs_b200_csmat, d_indptr: *mut *const c_void, indptr_bytes: *mut c_int,
+        d_indices: *mut *const u32, d_data: *mut *const c_double) -> c_int;
+    pub fn sprs_b200_csmat_from_triplets(
+        ctx: *mut sprs_b200_ctx, rows: u64, cols: u64, n: u64, row_inds: *const c_void,
+        col_inds: *const c_void, index_bytes: c_int, data: *const c_double,
+        out: *mut *mut sprs_b200_csmat) -> c_int;
+    pub fn sprs_b200_csmat_from_triplets_dev(
+        ctx: *mut sprs_b200_ctx, rows: u64, cols: u64, n: u64, d_row: *const u32,
+        d_col: *const u32, d_val: *const c_double, out: *mut *mut sprs_b200_csmat) -> c_int;
+    pub fn sprs_b200_csmat_check_structure(
+        ctx: *mut sprs_b200_ctx, m: *const sprs_b200_csmat, n_violations: *mut u64) -> c_int;
+    pub fn sprs_b200_spmv_dev(
+        ctx: *mut sprs_b200_ctx, mat: *const sprs_b200_csmat, d_x: *const c_double,
+        d_y: *mut c_double, accumulate: c_int, stream: *mut c_void) -> c_int;
+    pub fn sprs_b200_spmm_rowmaj_dev(
+        ctx: *mut sprs_b200_ctx, mat: *const sprs_b200_csmat, d_b: *const c_double, ldb: u64,
+        k: u64, d_c: *mut c_double, ldc: u64, accumulate: c_int, stream: *mut c_void) -> c_int;
+    pub fn sprs_b200_launch_count(ctx: *const sprs_b200_ctx) -> u64;
+    pub fn sprs_b200_peer_alloc(
+        ctx: *mut sprs_b200_ctx, bytes: u64, d_ptr: *mut *mut c_void, ipc_handle: *mut u8) -> c_int;
+    pub fn sprs_b200_peer_open(
+        ctx: *mut sprs_b200_ctx, ipc_handle: *const u8, d_ptr: *mut *mut c_void) -> c_int;
+    pub fn sprs_b200_peer_close(ctx: *mut sprs_b200_ctx, d_ptr: *mut c_void) -> c_int;
+    pub fn sprs_b200_peer_free(ctx: *mut sprs_b200_ctx, d_ptr: *mut c_void) -> c_int;
+    pub fn sprs_b200_copy_dev(
+        ctx: *mut sprs_b200_ctx, dst: *mut c_void, src: *const c_void, bytes: u64,
+        stream: *mut c_void) -> c_int;
+    pub fn sprs_b200_peer_push_dev(
+        ctx: *mut sprs_b200_ctx, d_y_own: *const c_double, row_offset: u64, rows: u64,
+        n_peers: c_int, d_y_peers: *const *mut c_double, stream: *mut c_void) -> c_int;
+    pub fn sprs_b200_spmv_allgather_dev(
+        ctx: *mut sprs_b200_ctx, mat: *const sprs_b200_csmat, d_x: *const c_double,
+        row_offset: u64, n_targets: c_int, d_y_bufs: *const *mut c_double, accumulate: c_int,
+        stream: *mut c_void) -> c_int;
+    pub fn sprs_b200_spmv_stream_push_dev(
+        ctx: *mut sprs_b200_ctx, mat: *mut sprs_b200_csmat, d_x: *const c_double, row_offset: u64,
+        n_targets: c_int, d_y_bufs: *const *mut c_double, accumulate: c_int, put_ctas: c_int,
+        stream: *mut c_void) -> c_int;
+    pub fn sprs_b200_spmv_chunked_push_dev(
+        ctx: *mut sprs_b200_ctx, mat: *const sprs_b200_csmat, d_x: *const c_double,
+        row_offset: u64, n_targets: c_int, d_y_bufs: *const *mut c_double, accumulate: c_int,
+        n_chunks: c_int, stream: *mut c_void) -> c_int;
+    pub fn sprs_b200_spgemm_numeric_dev(
+        ctx: *mut sprs_b200_ctx, plan: *mut sprs_b200_spgemm, c: *mut *mut sprs_b200_csmat) -> c_int;
+    pub fn sprs_b200_spgemm_nprod(plan: *const sprs_b200_spgemm) -> u64;
+    pub fn sprs_b200_bicgstab_new_dev(
+        ctx: *mut sprs_b200_ctx, mat: *const sprs_b200_csmat, d_x0: *const c_double,
+        d_b: *const c_double, n: u64, out: *mut *mut sprs_b200_bicgstab) -> c_int;
+    pub fn sprs_b200_bicgstab_get_dev(
+        s: *const sprs_b200_bicgstab, which: c_int, d_out: *mut *const c_double) -> c_int;
+    pub fn sprs_b200_gen_rmat_keys(
+        ctx: *mut sprs_b200_ctx, seed: u64, scale: c_int, n_rows: u64, n_cols: u64, a: c_double,
+        b: c_double, c: c_double, first: u64, count: u64, d_keys: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn sprs_b200_gen_uniform_keys(
+        ctx: *mut sprs_b200_ctx, seed: u64, n_rows: u64, n_cols: u64, first: u64, count: u64,
+        d_keys: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn sprs_b200_gen_normal_from_keys(
+        ctx: *mut sprs_b200_ctx, seed: u64, d_keys: *const u64, count: u64, d_out: *mut c_double,
+        stream: *mut c_void) -> c_int;
+    pub fn sprs_b200_gen_split_keys(
+        ctx: *mut sprs_b200_ctx, d_keys: *const u64, count: u64, d_rows: *mut u32,
+        d_cols: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn sprs_b200_gen_hash_keys(
+        ctx: *mut sprs_b200_ctx, seed: u64, d_keys: *const u64, count: u64, d_out: *mut u64,
+        stream: *mut c_void) -> c_int;
 }

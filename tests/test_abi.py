@@ -128,3 +128,15 @@ def test_cpp_host_mirror_logic_without_gpu():
     r = subprocess.run([exe] + (["gpu"] if has_gpu else []), capture_output=True, text=True,
                        timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_rust_sys_crate_declares_every_symbol():
+    """rust/sprs-b200-sys (source only: no Rust toolchain in the image) declares exactly the
+    functions of include/sprs_b200.h -- the crate is what INTEGRATION.md hands a maintainer."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "sprs_b200.h")).read(), flags=re.S)
+    in_header = set(re.findall(r"\b(sprs_b200_[a-z0-9_]+)\s*\(", header))
+    rust = open(os.path.join(root, "rust", "sprs-b200-sys", "src", "lib.rs")).read()
+    in_rust = set(re.findall(r"pub fn (sprs_b200_[a-z0-9_]+)", rust))
+    assert in_header == in_rust, (sorted(in_header - in_rust), sorted(in_rust - in_header))
