@@ -140,3 +140,31 @@ def test_rust_sys_crate_declares_every_symbol():
     rust = open(os.path.join(root, "rust", "sprs-b200-sys", "src", "lib.rs")).read()
     in_rust = set(re.findall(r"pub fn (sprs_b200_[a-z0-9_]+)", rust))
     assert in_header == in_rust, (sorted(in_header - in_rust), sorted(in_rust - in_header))
+
+
+def test_ctypes_prototypes_match_header_arity_and_widths():
+    """Every ctypes signature in sprs_b200/_lib.py has the parameter count of its C prototype,
+    64-bit integers where the header says uint64_t / int64_t and pointers where it has '*' (a
+    mismatch would only show as a corrupted argument at run time)."""
+    import ctypes as C
+    from sprs_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "sprs_b200.h")).read(), flags=re.S)
+    protos = re.findall(r"\b(?:int|uint64_t|const char\*)\s+(sprs_b200_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;",
+                        header, flags=re.S)
+    assert len(protos) >= 60
+    for name, params in protos:
+        ps = [" ".join(p.split()) for p in params.split(",")]
+        ps = [] if ps == ["void"] else ps
+        _, args = _lib.PROTOTYPES[name]
+        assert len(ps) == len(args), name
+        for p, a in zip(ps, args):
+            is_ptr = "*" in p or "[" in p or p.startswith("sprs_b200_matvec_fn")
+            if is_ptr:
+                assert a in (C.c_void_p, C.c_char_p, _lib.MATVEC_FN) or hasattr(a, "contents"), (name, p)
+            elif p.startswith(("uint64_t", "int64_t")):
+                assert C.sizeof(a) == 8, (name, p)
+            elif p.startswith("double"):
+                assert a is C.c_double, (name, p)
+            else:
+                assert p.startswith("int ") and a is C.c_int, (name, p)
