@@ -159,6 +159,9 @@ class RowPartitionedSpMM:
     def __init__(self, bounds, rank, world, c_full, local_spmm, dist=None, group=None,
                  gather=True):
         self.bounds, self.rank, self.world = bounds, rank, world
+        if gather and not c_full.is_contiguous():
+            # the all-gather receives into flat views of the row slices: they must alias c_full
+            raise ValueError("RowPartitionedSpMM(gather=True) needs a contiguous row-major C")
         self.c = c_full
         self.views = [c_full[bounds[g]:bounds[g + 1]] for g in range(world)]
         self.local_spmm = local_spmm
