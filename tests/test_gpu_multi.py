@@ -64,12 +64,14 @@ def _worker(rank, world, port, q, late_modes=False):
                                                        chunks=3))
             check_mode(lambda: PushAllGatherSpMV(ctx, a.mirror, bounds, rank, world, n, dist, dev))
         if late_modes:
+            # the modes whose put kernel WAITS on the SpMV (stream, mcast-stream) run last: they
+            # are the only ones that can trap, and a trap loses the CUDA context
             check_mode(lambda: ChunkedPushAllGatherSpMV(ctx, a.mirror, bounds, rank, world, n, dist, dev))
-            check_mode(lambda: StreamAllGatherSpMV(ctx, a.mirror, bounds, rank, world, n, dist, dev))
             import torch.distributed._symmetric_memory as symm
             from torch._C._autograd import DeviceType
-            if symm._SymmetricMemory.has_multicast_support(DeviceType.CUDA, dev.index):
-                for mode in ("fused", "push", "stream", "chunked"):
+            has_mc = symm._SymmetricMemory.has_multicast_support(DeviceType.CUDA, dev.index)
+            if has_mc:
+                for mode in ("fused", "push", "chunked"):
                     for barrier in ("nccl", "symm"):
                         check_mode(lambda: McastAllGatherSpMV(ctx, a.mirror, bounds, rank, world, n,
                                                               dist, dev, mode=mode, barrier=barrier))
@@ -139,6 +141,10 @@ def _worker(rank, world, port, q, late_modes=False):
             del sol
             for po in pops:
                 po.close()
+            check_mode(lambda: StreamAllGatherSpMV(ctx, a.mirror, bounds, rank, world, n, dist, dev))
+            if has_mc:
+                check_mode(lambda: McastAllGatherSpMV(ctx, a.mirror, bounds, rank, world, n, dist,
+                                                      dev, mode="stream", barrier="nccl"))
         q.put((rank, ok_nccl, all(oks)))
     finally:
         dist.destroy_process_group()
