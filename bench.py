@@ -224,6 +224,96 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def pick_exchange_by_measurement(op, args, ctx, a, bounds, rank, world, n, dist, dev, x, mcast_cls):
+    """`--exchange auto` at 6+ GPUs: the exchange measured in round 1 (fused peer stores) runs
+    against the NVSwitch-multicast exchanges ON THIS BOX, untimed, before the benchmark proper:
+    each candidate must construct on every rank, reproduce the validated operator's y (checked
+    from a NaN-filled buffer after one step, so a row that has not landed by the barrier
+    fails it) and beat it by more than 2 % over 5 device-timed steps (max over ranks) to be
+    selected.  A candidate that is unavailable, raises or disagrees is dropped; the report of
+    what was tried goes into the JSON line (config.exchange_trial).  SPRS_B200_AUTO_TRIAL=0
+    switches the trial off (the round-1 choice is then used as is)."""
+    import torch
+
+    def agree(flag):
+        t = torch.tensor([1.0 if flag else 0.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item() > 0.5)
+
+    def timed(o, steps=5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(2):
+            o.step(x)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        for _ in range(steps):
+            o.step(x)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    report = {}
+    base_name = args.exchange
+    base_ms = timed(op)
+    report[base_name] = round(base_ms, 4)
+    y_ref = op.y.clone()
+    scale = float(y_ref.abs().max().item()) + 1e-300
+    best_op, best_name, best_ms = op, base_name, base_ms
+    supported = False
+    try:
+        import torch.distributed._symmetric_memory as symm
+        from torch._C._autograd import DeviceType
+        supported = bool(symm._SymmetricMemory.has_multicast_support(DeviceType.CUDA, dev.index))
+    except Exception as e:
+        report["probe"] = "no symmetric-memory multicast probe: %r" % (e,)
+    if not agree(supported):
+        report.setdefault("probe", "NVSwitch multicast not supported on every rank")
+        return op, base_name, report
+    for cand in ("mcast-push", "mcast"):
+        c_op, err = None, None
+        try:
+            c_op = mcast_cls(ctx, a.mirror, bounds, rank, world, n, dist, dev,
+                             mode=cand.partition("-")[2] or "fused", barrier=args.barrier)
+        except Exception as e:
+            err = repr(e)
+        if not agree(c_op is not None):
+            report[cand] = "unavailable: %s" % (err or "failed on another rank")
+            if c_op is not None:
+                c_op.close()
+            continue
+        ok, ms = False, None
+        try:
+            c_op.y.fill_(float("nan"))
+            torch.cuda.synchronize()
+            dist.barrier()
+            got = c_op.step(x)
+            torch.cuda.synchronize()
+            ok = bool(((got - y_ref).abs() <= 1e-9 * scale).all().item())
+            dist.barrier()
+        except Exception as e:
+            err = repr(e)
+        if not agree(ok):
+            report[cand] = "rejected: result differs from the validated exchange" if err is None \
+                else "rejected: %s" % err
+            c_op.close()
+            continue
+        ms = timed(c_op)
+        report[cand] = round(ms, 4)
+        if ms < 0.98 * best_ms:
+            if best_op is not op:
+                best_op.close()
+            best_op, best_name, best_ms = c_op, cand, ms
+        else:
+            c_op.close()
+    if best_op is not op and hasattr(op, "close"):
+        op.close()
+    report["selected"] = best_name
+    return best_op, best_name, report
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -238,7 +328,9 @@ def main():
                          "chunk's y slice pushed to the peers by DMA copies on a second stream "
                          "while the next chunk computes; 'fused' = the SpMV kernel itself stores "
                          "every finished row into the peers' buffers; 'nccl' = one NCCL "
-                         "all_gather after the kernel")
+                         "all_gather after the kernel; 'auto' = push below 6 GPUs, fused from 6 "
+                         "up, where an untimed trial may replace it by a multicast exchange that "
+                         "reproduces its result and is faster (pick_exchange_by_measurement)")
     ap.add_argument("--chunks", type=int, default=4)
     ap.add_argument("--barrier", default="nccl", choices=["nccl", "symm"],
                     help="mcast modes: barrier after the stores -- 1-element NCCL all_reduce, or "
@@ -310,6 +402,7 @@ def main():
         except Exception as e:  # a reported baseline must never take the GPU number down
             cpu_base = {"error": repr(e)}
     t_gen = time.time() - t_gen
+    auto_exchange = args.exchange == "auto"
     if args.exchange == "auto":
         # measured (profiles/r1_multi_gpu.md): the own put kernel is the fastest exchange at
         # 2 and 4 GPUs (2.27 / 1.33 ms vs nccl 2.39 / 1.36, fused 2.43 / 1.38); its cost grows
@@ -379,6 +472,11 @@ def main():
             rebalanced += 1
         del full
         torch.cuda.empty_cache()
+    exchange_trial = None
+    trial_min = int(os.environ.get("SPRS_B200_AUTO_TRIAL_MIN_GPUS", "6"))
+    if auto_exchange and world >= trial_min and os.environ.get("SPRS_B200_AUTO_TRIAL", "1") != "0":
+        op, args.exchange, exchange_trial = pick_exchange_by_measurement(
+            op, args, ctx, a, bounds, rank, world, n, dist, dev, x, McastAllGatherSpMV)
     y = op.y
     y_views = [y[bounds[g]:bounds[g + 1]] for g in range(world)]
     local_nnz = a.nnz
@@ -532,6 +630,7 @@ def main():
                                             "NVSwitch multicast address of y + barrier (%s)"
                                             % args.barrier,
                            "nccl": "NCCL all_gather(y), unequal slices"}[args.exchange]),
+                       "exchange_trial": exchange_trial,
                        "l2_policy": "inputs (%.1f GB) exceed L2 (126 MB); no flush needed" %
                                     (alg_bytes / 1e9),
                        "gen_seconds": round(t_gen, 1)},

@@ -221,3 +221,122 @@ def test_scale_modes_control_flow_gloo_world2():
     assert len(done) == 7 and all(d["correct"] and d["speedup_vs_n1"] > 0 for d in done)
     assert [d for d in lines if "skipped" in d][0]["mode"] == "mcast-chunked"
     assert any("partition_round" in d for d in lines) and any("setup_seconds" in d for d in lines)
+
+
+# ---- bench.py N > 1 control flow (partition calibration, re-cuts, the exchange trial of
+#      `--exchange auto`, the JSON line) on two gloo ranks with the GPU pieces faked
+def _bench_n2_worker(rank, world, port, q):
+    import os
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank), SPRS_BENCH_NO_SAMPLER="1",
+                      SPRS_B200_AUTO_TRIAL_MIN_GPUS="2")
+    import contextlib
+    import io
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm
+    import sprs_b200
+    from sprs_b200 import dist as D
+    from sprs_b200 import generate as G
+    real_device = torch.device
+    torch.device = lambda *a, **k: real_device("cpu")
+    torch.cuda.set_device = lambda d: None
+    torch.cuda.synchronize = lambda *a: None
+    torch.cuda.empty_cache = lambda: None
+    torch.Tensor.pin_memory = lambda self: self
+
+    class Event(_FakeEvent):
+        ms = 1.0
+
+        def elapsed_time(self, other):
+            return Event.ms
+
+    torch.cuda.Event = Event
+    real_init = dist.init_process_group
+    dist.init_process_group = lambda backend, **k: real_init("gloo")
+    symm._SymmetricMemory.has_multicast_support = staticmethod(lambda *a: True)
+    ctx = _FakeCtx()
+    sprs_b200.Context.default = classmethod(lambda cls, device=None: ctx)
+
+    def make_matrix(c, gen, n, npr, seed):
+        rng = np.random.default_rng(seed % (1 << 32))
+        return _FakeCsr(sps.random(n, n, density=npr / n, format="csr", random_state=rng,
+                                   data_rvs=rng.standard_normal))
+
+    def spmv(c, a, x, y, accumulate=False):
+        y.copy_(torch.from_numpy(a.m @ x.numpy()))
+        return y
+
+    G.make_matrix, G.spmv = make_matrix, spmv
+    G.normal_vector = lambda c, n, seed=1: torch.from_numpy(np.random.default_rng(seed).standard_normal(n))
+    closed = []
+
+    class FakePeerOp(D.RowPartitionedSpMV):
+        speed = 1.0
+
+        def __init__(self, c, mirror, bounds, rank_, world_, n, dist_, device, mode=None, barrier=None):
+            self.tag = mode
+            if mode == "fused":          # pretend plain `mcast` computes something else
+                self.wrong = True
+            blk = mirror.owner
+            super().__init__(bounds, rank_, world_, torch.zeros(n, dtype=torch.float64),
+                             lambda xv, ys: spmv(c, blk, xv, ys), dist=dist_)
+
+        def step(self, xv):
+            Event.ms = 0.5 if self.tag == "push" else 1.0   # only mcast-push is "faster"
+            out = super().step(xv)
+            if getattr(self, "wrong", False):
+                out[0] += 1.0
+            return out
+
+        def close(self):
+            closed.append(self.tag)
+
+    class Plain(FakePeerOp):             # the non-mcast peer classes take no mode/barrier
+        def __init__(self, c, mirror, bounds, rank_, world_, n, dist_, device):
+            super().__init__(c, mirror, bounds, rank_, world_, n, dist_, device)
+
+    for name in ("PushAllGatherSpMV", "FusedAllGatherSpMV", "StreamAllGatherSpMV",
+                 "ChunkedPushAllGatherSpMV"):
+        setattr(D, name, Plain)
+    D.McastAllGatherSpMV = FakePeerOp
+    import bench
+    bench.WORKLOADS["spmv_rmat_10m"] = ("spmv", 3000, 10, "rmat")
+    sys.argv = ["bench.py", "--gpus", "2", "--steps", "2", "--warmup", "3", "--no-cpu-baseline",
+                "--no-extra"]
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        bench.main()
+    q.put((rank, buf.getvalue(), closed))
+
+
+def test_bench_n2_auto_exchange_trial_gloo():
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_bench_n2_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r: (out, closed) for r, out, closed in (q.get(timeout=240) for _ in procs)}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    lines = [l for l in res[0][0].splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and res[1][0].strip() == ""
+    line = json.loads(lines[0])
+    for k in REQUIRED:
+        assert k in line, k
+    assert line["n_gpus"] == 2 and line["scaling"] == "strong"
+    trial = line["config"]["exchange_trial"]
+    # the validated exchange (push at 2 GPUs) was timed, mcast-push beat it and was selected,
+    # plain mcast was rejected because its result differed
+    # (the fake event reports 1.0 / 0.5 ms for the 5 timed steps)
+    assert trial["push"] == 0.2 and trial["mcast-push"] == 0.1 and trial["selected"] == "mcast-push"
+    assert trial["mcast"].startswith("rejected")
+    assert "multicast" in line["config"]["collective"]
+    assert "fused" in res[0][1] and None in res[0][1]      # the loser and the base op were closed
