@@ -51,7 +51,8 @@ enum {
     SPRS_B200_ERR_INDEX_RANGE = 5, /* "Index type is not large enough" (csmat.rs:1794)   */
     SPRS_B200_ERR_ARGUMENT = 6,    /* null pointer, bad width, bad handle                */
     SPRS_B200_ERR_STRUCTURE = 7,   /* indptr not monotone / index out of bounds          */
-    SPRS_B200_ERR_UNSUPPORTED = 8
+    SPRS_B200_ERR_UNSUPPORTED = 8,
+    SPRS_B200_ERR_COMM = 9         /* multi-GPU rendezvous / barrier failure; see last_error */
 };
 
 int sprs_b200_version(void);
@@ -192,6 +193,12 @@ int sprs_b200_peer_close(sprs_b200_ctx* ctx, void* d_ptr);
 int sprs_b200_peer_free(sprs_b200_ctx* ctx, void* d_ptr);
 int sprs_b200_copy_dev(sprs_b200_ctx* ctx, void* dst, const void* src, uint64_t bytes,
                        void* stream);
+/* host <-> device copies for callers that own no CUDA runtime of their own (a Rust host
+ * filling a symmetric buffer): enqueued on `stream`, which is synchronised before returning */
+int sprs_b200_copy_to_device(sprs_b200_ctx* ctx, void* d_dst, const void* h_src, uint64_t bytes,
+                             void* stream);
+int sprs_b200_copy_to_host(sprs_b200_ctx* ctx, void* h_dst, const void* d_src, uint64_t bytes,
+                           void* stream);
 /* all-gather "put": copy y[row_offset .. row_offset+rows) of this rank's buffer into the same
  * position of n_peers peer buffers with one kernel (coalesced stores over NVLink).        */
 int sprs_b200_peer_push_dev(sprs_b200_ctx* ctx, const double* d_y_own, uint64_t row_offset,
@@ -199,19 +206,7 @@ int sprs_b200_peer_push_dev(sprs_b200_ctx* ctx, const double* d_y_own, uint64_t 
 int sprs_b200_spmv_allgather_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
                                  const double* d_x, uint64_t row_offset, int n_targets,
                                  double* const* d_y_bufs, int accumulate, void* stream);
-/* Pipelined variant of the same contract: the SpMV writes only this rank's buffer
- * (d_y_bufs[0]) and publishes its progress; a put kernel of `put_ctas` CTAs (0 = default)
- * on a side stream of the ctx follows it chunk by chunk, applies the carries of the rows
- * that end in the chunk (rows cut by a tile boundary) and copies the now final rows into
- * d_y_bufs[1..) while the SpMV is still running.  The other buffers may be peer GPUs' memory
- * or mapped pinned host memory.  `stream` is joined with the side stream before the call
- * returns control to it, so the caller's barrier goes on `stream` as for the fused form.
- * The mirror keeps the progress counters: not const.  Do not run under a tool that
- * serialises kernels (ncu): the put kernel waits for the SpMV and traps after ~3 s.    */
-int sprs_b200_spmv_stream_push_dev(sprs_b200_ctx* ctx, sprs_b200_csmat* mat, const double* d_x,
-                                   uint64_t row_offset, int n_targets, double* const* d_y_bufs,
-                                   int accumulate, int put_ctas, void* stream);
-/* The same all-gather without any kernel waiting on another: the tile stream of the block is
+/* The same all-gather pipelined by plain stream ordering: the tile stream of the block is
  * launched in `n_chunks` chunks of decreasing size (0 = default 4, at most 8); behind each
  * chunk's event a side stream of the ctx copies the rows that chunk completed (carries
  * applied) into d_y_bufs[1..) with a put kernel while the next chunk computes; `stream` is
@@ -221,6 +216,76 @@ int sprs_b200_spmv_chunked_push_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* m
                                     const double* d_x, uint64_t row_offset, int n_targets,
                                     double* const* d_y_bufs, int accumulate, int n_chunks,
                                     void* stream);
+
+/* ---- multi-GPU communicator (SURVEY 8b "comm_init / spmv_rowpart", 8e): the ranks of ONE
+ * node -- one process per GPU (the torchrun layout) or threads of one process -- meet through
+ * a 64-byte id that rank 0 creates and the caller ships to the other ranks by any transport
+ * (the way an ncclUniqueId travels: MPI, a file, an environment variable, torch.distributed).
+ * No torch, no NCCL underneath: a POSIX shared-memory segment carries the host barrier and the
+ * handle exchange; device buffers are shared through CUDA IPC, or through CUDA VMM handles
+ * bound to an NVSwitch multicast object when every rank's device supports one.
+ * All calls below except _rank/_world/_ptr are COLLECTIVE: every rank makes them in the same
+ * order.  A rank that fails marks the communicator failed; the others return ERR_COMM instead
+ * of waiting for it.                                                                       */
+#define SPRS_B200_MAX_RANKS 8
+typedef struct sprs_b200_comm sprs_b200_comm;
+typedef struct sprs_b200_symm sprs_b200_symm;     /* one buffer per rank, mapped on every rank */
+int sprs_b200_comm_unique_id(char id[64]);
+int sprs_b200_comm_init_rank(sprs_b200_ctx* ctx, const char id[64], int rank, int world,
+                             sprs_b200_comm** out);
+int sprs_b200_comm_free(sprs_b200_comm* comm);
+int sprs_b200_comm_rank(const sprs_b200_comm* comm);
+int sprs_b200_comm_world(const sprs_b200_comm* comm);
+/* 1 when symm_alloc(want_multicast) will bind an NVSwitch multicast address (every device
+ * supports it, one process and one device per rank; SPRS_B200_COMM_MULTICAST=0 disables it) */
+int sprs_b200_comm_multicast_supported(const sprs_b200_comm* comm);
+/* all-gather of one small host record per rank (bytes <= 512): all = world * bytes */
+int sprs_b200_comm_allgather_host(sprs_b200_comm* comm, const void* mine, uint64_t bytes,
+                                  void* all);
+int sprs_b200_comm_barrier_host(sprs_b200_comm* comm);
+/* stream-ordered device barrier (one tiny kernel exchanging epoch flags in peer memory): what
+ * every rank enqueued on its stream before its barrier -- e.g. the stores of its y rows into
+ * the other ranks' buffers -- has completed when the barrier completes on any rank.        */
+int sprs_b200_comm_barrier_dev(sprs_b200_comm* comm, void* stream);
+/* synchronises `stream`; ERR_COMM if a device barrier gave up waiting for a peer */
+int sprs_b200_comm_check(sprs_b200_comm* comm, void* stream);
+/* `bytes` of zero-initialised device memory on every rank, every rank's buffer mapped into
+ * every rank; with want_multicast (and support) also one multicast address whose stores the
+ * switch replicates into all of them.                                                       */
+int sprs_b200_symm_alloc(sprs_b200_comm* comm, uint64_t bytes, int want_multicast,
+                         sprs_b200_symm** out);
+int sprs_b200_symm_free(sprs_b200_symm* buf);
+void* sprs_b200_symm_ptr(const sprs_b200_symm* buf, int rank);
+void* sprs_b200_symm_multicast_ptr(const sprs_b200_symm* buf); /* NULL when not bound */
+uint64_t sprs_b200_symm_bytes(const sprs_b200_symm* buf);
+/* slice_outer cut points (slicing.rs:65-89): bounds[0..nparts], bounds[g] = first row whose
+ * cost prefix nnz + row_cost*rows reaches g/nparts of the total (row_cost in non-zero
+ * equivalents; 0 balances non-zeros only).  Host arrays, indptr width 4 or 8.             */
+int sprs_b200_partition_rows(const void* indptr, int indptr_bytes, uint64_t rows, int nparts,
+                             double row_cost, uint64_t* bounds);
+/* How the rows of y reach the other ranks in spmv_rowpart: FUSED = the SpMV kernel stores each
+ * finished row into every target itself; PUSH = plain SpMV, then one put kernel copying the
+ * rank's slice (coalesced 16-byte stores).  With a multicast-bound y there is ONE remote
+ * target (the multicast address: the row leaves the GPU once and the switch replicates it),
+ * otherwise world-1 peer mappings.  AUTO = the measured default.            */
+enum { SPRS_B200_EXCHANGE_AUTO = 0, SPRS_B200_EXCHANGE_FUSED = 1, SPRS_B200_EXCHANGE_PUSH = 2 };
+/* Row-partitioned y = A x (device-resident): this rank's CSR row block `mat` (rows
+ * row_offset .. row_offset + mat.rows of A, slice_outer + proper_indptr), x replicated
+ * (d_x: cols doubles on this device), y a symmetric buffer of n doubles.  Enqueues on
+ * `stream`: SpMV of the block, the all-gather of the slice into EVERY rank's y, the device
+ * barrier.  When that work has completed on a rank, its y holds the whole product.  A caller
+ * that reads y and calls again must use two y buffers in turn (a fast rank stores rows of
+ * product k+1 into a peer that may still read product k).                                  */
+int sprs_b200_spmv_rowpart(sprs_b200_comm* comm, const sprs_b200_csmat* mat, const double* d_x,
+                           sprs_b200_symm* y, uint64_t row_offset, int exchange, void* stream);
+/* `&A * &x` on a row-partitioned matrix with HOST vectors, each rank touching only its own
+ * slices: x_slice = x[col_offset .. col_offset+col_count) is uploaded into the symmetric x
+ * buffer (cols doubles) and all-gathered over NVLink, the local block multiplied, y_slice
+ * (this rank's mat.rows rows) downloaded.  Blocking; the union of the ranks' column slices
+ * must cover 0..cols.                                                                       */
+int sprs_b200_mul_mat_vec_rowpart(sprs_b200_comm* comm, const sprs_b200_csmat* mat,
+                                  sprs_b200_symm* x, const double* x_slice, uint64_t col_offset,
+                                  uint64_t col_count, double* y_slice, uint64_t y_len);
 
 /* ---- sparse x sparse: smmp::mul_csr_csr (smmp.rs:196-237), two calls so the
  * CALLER allocates the output Vecs, like symbolic -> numeric (smmp.rs:81,151).

@@ -60,10 +60,28 @@ PROTOTYPES = {
     "sprs_b200_peer_close": (_int, [_vp, _vp]),
     "sprs_b200_peer_free": (_int, [_vp, _vp]),
     "sprs_b200_copy_dev": (_int, [_vp, _vp, _vp, _u64, _vp]),
+    "sprs_b200_copy_to_device": (_int, [_vp, _vp, _vp, _u64, _vp]),
+    "sprs_b200_copy_to_host": (_int, [_vp, _vp, _vp, _u64, _vp]),
+    "sprs_b200_comm_unique_id": (_int, [C.c_char_p]),
+    "sprs_b200_comm_init_rank": (_int, [_vp, C.c_char_p, _int, _int, C.POINTER(_vp)]),
+    "sprs_b200_comm_free": (_int, [_vp]),
+    "sprs_b200_comm_rank": (_int, [_vp]),
+    "sprs_b200_comm_world": (_int, [_vp]),
+    "sprs_b200_comm_multicast_supported": (_int, [_vp]),
+    "sprs_b200_comm_allgather_host": (_int, [_vp, _vp, _u64, _vp]),
+    "sprs_b200_comm_barrier_host": (_int, [_vp]),
+    "sprs_b200_comm_barrier_dev": (_int, [_vp, _vp]),
+    "sprs_b200_comm_check": (_int, [_vp, _vp]),
+    "sprs_b200_symm_alloc": (_int, [_vp, _u64, _int, C.POINTER(_vp)]),
+    "sprs_b200_symm_free": (_int, [_vp]),
+    "sprs_b200_symm_ptr": (_vp, [_vp, _int]),
+    "sprs_b200_symm_multicast_ptr": (_vp, [_vp]),
+    "sprs_b200_symm_bytes": (_u64, [_vp]),
+    "sprs_b200_partition_rows": (_int, [_vp, _int, _u64, _int, C.c_double, _vp]),
+    "sprs_b200_spmv_rowpart": (_int, [_vp, _vp, _dp, _vp, _u64, _int, _vp]),
+    "sprs_b200_mul_mat_vec_rowpart": (_int, [_vp, _vp, _vp, _dp, _u64, _u64, _dp, _u64]),
     "sprs_b200_peer_push_dev": (_int, [_vp, _vp, _u64, _u64, _int, C.POINTER(_vp), _vp]),
     "sprs_b200_spmv_allgather_dev": (_int, [_vp, _vp, _dp, _u64, _int, C.POINTER(_vp), _int, _vp]),
-    "sprs_b200_spmv_stream_push_dev": (_int, [_vp, _vp, _dp, _u64, _int, C.POINTER(_vp), _int,
-                                              _int, _vp]),
     "sprs_b200_spmv_chunked_push_dev": (_int, [_vp, _vp, _dp, _u64, _int, C.POINTER(_vp), _int,
                                                _int, _vp]),
     "sprs_b200_spgemm_symbolic": (_int, [_vp, _vp, _vp, C.POINTER(_vp), C.POINTER(_u64)]),
@@ -92,6 +110,8 @@ PROTOTYPES = {
     "sprs_b200_gen_hash_keys": (_int, [_vp, _u64, _vp, _u64, _vp, _vp]),
 }
 
+_NOT_EMULATED = ("sprs_b200_comm_", "sprs_b200_symm_", "sprs_b200_partition_rows",
+                 "sprs_b200_spmv_rowpart", "sprs_b200_mul_mat_vec_rowpart")
 _lib = None
 
 
@@ -105,7 +125,11 @@ def load():
             "libsprs_b200.so is not built (%s): run `python -c 'import __graft_entry__ as g; "
             "g.build()'` or `make -C sprs_b200/csrc`.  sprs_b200 has no CPU fallback." % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
+    # the CPU emulator build of tests/emu (test infrastructure) has no multi-rank layer
+    emulated = os.path.basename(LIB_PATH).startswith("libsprs_b200_emu")
     for name, (res, args) in PROTOTYPES.items():
+        if emulated and name.startswith(_NOT_EMULATED) and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
         fn.restype = res
         fn.argtypes = args

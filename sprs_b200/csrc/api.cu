@@ -128,14 +128,6 @@ int ctx_scratch(sprs_b200_ctx* ctx, int i, size_t bytes, void** out) {
     return SPRS_B200_OK;
 }
 
-constexpr unsigned TILE_COUNTER_RING = 64;
-int ctx_tile_counter(sprs_b200_ctx* ctx, unsigned long long** out) {
-    if (!ctx->d_tile_counters)
-        SPRS_CUDA(ctx, cudaMalloc((void**)&ctx->d_tile_counters, TILE_COUNTER_RING * 8));
-    *out = ctx->d_tile_counters + (ctx->tile_counter_next++ % TILE_COUNTER_RING);
-    return SPRS_B200_OK;
-}
-
 int ctx_side_stream(sprs_b200_ctx* ctx) {
     if (ctx->side_stream) return SPRS_B200_OK;
     int lo = 0, hi = 0;  // numerically lower = higher priority
@@ -238,7 +230,6 @@ int sprs_b200_ctx_destroy(sprs_b200_ctx* ctx) {
     for (int i = 0; i < 4; ++i)
         if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-    if (ctx->d_tile_counters) cudaFree(ctx->d_tile_counters);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
@@ -385,7 +376,6 @@ int sprs_b200_csmat_free(sprs_b200_csmat* m) {
     }
     if (m->d_tile_row) cudaFree(m->d_tile_row);
     if (m->d_carry) cudaFree(m->d_carry);
-    if (m->d_progress) cudaFree(m->d_progress);
     if (m->csr_cache) sprs_b200_csmat_free(m->csr_cache);
     delete m;
     return SPRS_B200_OK;
@@ -574,13 +564,14 @@ int sprs_b200_spmm_rowmaj_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, co
 // host-buffer entry points.  x / y travel through cudaMemcpyAsync on the ctx stream
 // (true DMA when the caller's buffers are pinned); the call blocks until y is visible.
 
-// Chunked variant of the host path (opt-in: SPRS_B200_E2E_PIPELINE=2, until it has been timed):
-// the tile stream is cut into a few chunks; each chunk's SpMV + carry kernel is followed by an
-// event, and a second stream copies the rows that chunk completed to the host while the next
-// chunk computes -- plain stream/event ordering, no kernel waits on another.  Only the last
-// chunk's copy is left after the SpMV.
+// Chunked variant of the host path: the tile stream is cut into a few chunks; each chunk's
+// SpMV + carry kernel is followed by an event, and a second stream copies the rows that chunk
+// completed to the host while the next chunk computes -- plain stream/event ordering, no kernel
+// waits on another.  Only the last chunk's copy is left after the SpMV.  Bit-identical to the
+// one-shot SpMV (spmv_launch_tile_range).
 static int spmv_host_chunked(sprs_b200_ctx* ctx, const sprs_b200_csmat* csr, const double* d_x,
-                             double* d_y, double* y, int accumulate, cudaStream_t s) {
+                             double* d_y, double* y, int accumulate, int n_chunks_want,
+                             cudaStream_t s) {
     if (!ctx->copy_stream) {
         SPRS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         SPRS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
@@ -589,12 +580,8 @@ static int spmv_host_chunked(sprs_b200_ctx* ctx, const sprs_b200_csmat* csr, con
         for (int i = 0; i < SPRS_E2E_MAX_CHUNKS; ++i)
             SPRS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
     if (csr->e2e_tiles.empty()) {
-        // chunks of at least ~64 tiles per resident warp (tail effects of a launch stay small)
-        const uint64_t per_chunk = (uint64_t)ctx->sm_count * 24 * 64;
-        uint64_t n_chunks = csr->n_tiles / per_chunk;
-        if (const char* e = getenv("SPRS_B200_E2E_CHUNKS")) n_chunks = (uint64_t)atoi(e);
         std::vector<uint64_t> tiles, rows;
-        SPRS_TRY(csmat_chunk_table(ctx, csr, n_chunks, false, s, &tiles, &rows));
+        SPRS_TRY(csmat_chunk_table(ctx, csr, (uint64_t)n_chunks_want, false, s, &tiles, &rows));
         csr->e2e_rows = rows;
         csr->e2e_tiles = tiles;
     }
@@ -644,45 +631,18 @@ static int spmv_host(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, int want_st
             st = SPRS_B200_ERR_CUDA;
             break;
         }
-        // Opt-in (SPRS_B200_E2E_PIPELINE=1, until it has been measured): when the caller's y
-        // is pinned host memory the device can address, the result leaves for the host WHILE
-        // the SpMV runs -- the pipelined put of spmv.cu with the host buffer as the second
-        // target -- instead of one D2H copy after it.
-        double* y_mapped = nullptr;
-        static const int pipeline = [] {
-            const char* v = getenv("SPRS_B200_E2E_PIPELINE");
-            return v ? atoi(v) : 0;
+        // SPRS_B200_E2E_CHUNKS=n (n > 1): the tile stream runs in n chunks and each chunk's
+        // finished rows leave for the host behind its event while the next chunk computes
+        // (spmv_host_chunked); default: one launch, one D2H copy.
+        static const int chunks = [] {
+            const char* v = getenv("SPRS_B200_E2E_CHUNKS");
+            return v ? atoi(v) : SPRS_E2E_DEFAULT_CHUNKS;
         }();
-        if (pipeline == 2 && y_len >= 4096 && csr->nnz) {
+        if (chunks > 1 && y_len >= 4096 && csr->n_tiles >= (uint64_t)chunks * 1024) {
             if ((st = spmv_host_chunked(ctx, csr, (const double*)d_x, (double*)d_y, y, accumulate,
-                                        s)) != SPRS_B200_OK)
+                                        chunks, s)) != SPRS_B200_OK)
                 break;
             e = cudaStreamSynchronize(s);
-            if (e != cudaSuccess) {
-                sprs_b200_set_error(ctx, cudaGetErrorString(e));
-                st = SPRS_B200_ERR_CUDA;
-            }
-            break;
-        }
-        if (pipeline == 1 && y_len >= 4096) {
-            cudaPointerAttributes attr;
-            if (cudaPointerGetAttributes(&attr, y) == cudaSuccess &&
-                attr.type == cudaMemoryTypeHost && attr.devicePointer)
-                y_mapped = (double*)attr.devicePointer;
-            else
-                cudaGetLastError();  // pageable memory: not an error, just the plain path
-        }
-        if (y_mapped) {
-            SpmvTargets yt;
-            yt.n = 2;
-            for (int q = 0; q < SPMV_MAX_TARGETS; ++q) yt.p[q] = nullptr;
-            yt.p[0] = (double*)d_y;
-            yt.p[1] = y_mapped;
-            if ((st = spmv_launch_stream_push(ctx, const_cast<sprs_b200_csmat*>(csr),
-                                              (const double*)d_x, yt, accumulate, 24, s)) !=
-                SPRS_B200_OK)
-                break;
-            e = cudaStreamSynchronize(s);  // joined with the put kernel: y is complete
         } else {
             if ((st = spmv_launch(ctx, csr, (const double*)d_x, (double*)d_y, accumulate, s)) !=
                 SPRS_B200_OK)

@@ -11,6 +11,7 @@
 #include "../../include/sprs_b200.h"
 
 constexpr int SPRS_E2E_MAX_CHUNKS = 8;
+constexpr int SPRS_E2E_DEFAULT_CHUNKS = 1;  // host path: 1 = one launch + one D2H copy (api.cu)
 
 // ---- error plumbing: C functions return int, never throw/abort ----
 struct sprs_b200_ctx {
@@ -25,14 +26,10 @@ struct sprs_b200_ctx {
     size_t h_stage_bytes = 0;
     void* d_scratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t d_scratch_bytes[4] = {0, 0, 0, 0};
-    // pipelined all-gather (spmv_launch_stream_push): high-priority side stream of the put
-    // kernel and the fork/join events that tie it to the caller's stream; created on first use
+    // chunked push (peer.cu): high-priority side stream of the put kernels and the fork/join
+    // events that tie it to the caller's stream; created on first use
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    // dynamic tile hand-out of the SpMV (spmv.cu): a ring of 8-byte counters, one per launch
-    // (zeroed on the launch's stream), so launches in flight on different streams never share
-    unsigned long long* d_tile_counters = nullptr;
-    unsigned tile_counter_next = 0;
     // chunked host path (api.cu, SPRS_B200_E2E_PIPELINE=2): copy stream + one event per chunk
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_chunk[SPRS_E2E_MAX_CHUNKS] = {};
@@ -57,12 +54,6 @@ struct sprs_b200_csmat {
     // CSC mirrors only: the CSR conversion the product kernels run on, built on first use
     // by the host-buffer entry points and kept until the mirror is freed.
     mutable sprs_b200_csmat* csr_cache = nullptr;
-    // pipelined all-gather only: tiles finished per chunk of 2^chunk_shift tiles, summed over
-    // all calls (call number e expects e * tiles_in_chunk); allocated on first use
-    unsigned long long* d_progress = nullptr;
-    int chunk_shift = 0;
-    uint32_t n_chunks = 0;
-    uint64_t push_epoch = 0;
     // chunked host path only: tile and row boundaries of the chunks (host copies, built on
     // first use: chunk c covers tiles [e2e_tiles[c], e2e_tiles[c+1]) and completes rows
     // [e2e_rows[c], e2e_rows[c+1]))
@@ -115,14 +106,11 @@ struct SpmvTargets {
 
 // ---- kernels' launch wrappers (defined in the .cu files) -----------------------
 int spmv_prepare(sprs_b200_ctx* ctx, sprs_b200_csmat* m, cudaStream_t s);
+int spmv_tile_nnz();  // non-zeros per SpMV warp tile (fixed per process)
 int spmv_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x, double* d_y,
                 int accumulate, cudaStream_t s);
 int spmv_launch_targets(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
                         const SpmvTargets& yt, int accumulate, cudaStream_t s);
-// Single-target SpMV into targets.p[0] whose finished row chunks are copied into
-// targets.p[1..n) by a concurrent put kernel while the SpMV still runs (spmv.cu)
-int spmv_launch_stream_push(sprs_b200_ctx* ctx, sprs_b200_csmat* m, const double* d_x,
-                            const SpmvTargets& yt, int accumulate, int put_ctas, cudaStream_t s);
 // One chunk of the tile stream: tiles [t0, t1) + the carries of the rows ending in them; after
 // chunks 0..c (in order, one stream) rows [0, tile_row[t1_c]) of y are final (spmv.cu)
 int spmv_launch_tile_range(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
@@ -133,10 +121,11 @@ int spmv_launch_tile_range(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const d
 // chunk cannot overlap with compute) instead of equal.  Synchronises `s` (api.cu).
 int csmat_chunk_table(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, uint64_t n_chunks, bool taper,
                       cudaStream_t s, std::vector<uint64_t>* tiles, std::vector<uint64_t>* rows);
-// next counter of the ctx's ring for a dynamically scheduled SpMV launch (api.cu)
-int ctx_tile_counter(sprs_b200_ctx* ctx, unsigned long long** out);
 // high-priority side stream + fork/join events of the ctx, created on first use (api.cu)
 int ctx_side_stream(sprs_b200_ctx* ctx);
+// copy `count` doubles at src into the same position of every buffer in dst (peer.cu)
+int peer_push_launch(sprs_b200_ctx* ctx, const double* src, const SpmvTargets& dst, uint64_t count,
+                     cudaStream_t s);
 int spmm_rowmaj_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_b,
                        uint64_t ldb, uint64_t k, double* d_c, uint64_t ldc, int accumulate,
                        cudaStream_t s);

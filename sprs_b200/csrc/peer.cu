@@ -12,25 +12,55 @@
 #include "common.cuh"
 
 namespace {
-// Push `count` doubles starting at row_off from this GPU's y into the same position of every
-// peer buffer (own all-gather "put"): coalesced 8-byte loads, n_peers coalesced stores each.
+// Push `count` doubles from this GPU's y into the same position of every target buffer (the
+// all-gather "put"): peer mappings over NVLink, or ONE NVSwitch multicast address the switch
+// replicates.  16-byte loads and stores on the aligned body (all buffers share the alignment of
+// their common row offset), scalar head / tail.
 __global__ void __launch_bounds__(256)
     peer_push_kernel(const double* __restrict__ src, SpmvTargets dst, uint64_t count) {
+    const uint64_t head = (((uintptr_t)src & 15) && count) ? 1 : 0;  // 8-byte aligned, not 16
+    const uint64_t pairs = (count - head) / 2;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < count; i += 4 * stride) {
-        double v[4];
+    const uint64_t tid = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const double2* s2 = (const double2*)(src + head);
+    for (uint64_t i = tid; i < pairs; i += 4 * stride) {
+        double2 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = (i + u * stride < count) ? src[i + u * stride] : 0.0;
+        for (int u = 0; u < 4; ++u)
+            v[u] = (i + u * stride < pairs) ? s2[i + u * stride] : make_double2(0.0, 0.0);
 #pragma unroll
         for (int q = 0; q < SPMV_MAX_TARGETS; ++q)
             if (q < dst.n) {
+                double2* d2 = (double2*)(dst.p[q] + head);
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (i + u * stride < count) dst.p[q][i + u * stride] = v[u];
+                    if (i + u * stride < pairs) d2[i + u * stride] = v[u];
             }
+    }
+    if (tid == 0) {
+        if (head)
+            for (int q = 0; q < dst.n; ++q) dst.p[q][0] = src[0];
+        if ((count - head) & 1)
+            for (int q = 0; q < dst.n; ++q) dst.p[q][count - 1] = src[count - 1];
     }
 }
 }  // namespace
+
+int peer_push_launch(sprs_b200_ctx* ctx, const double* src, const SpmvTargets& dst, uint64_t count,
+                     cudaStream_t s) {
+    if (count == 0 || dst.n == 0) return SPRS_B200_OK;
+    for (int q = 0; q < dst.n; ++q)
+        if ((((uintptr_t)dst.p[q]) & 15) != (((uintptr_t)src) & 15))
+            SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "peer push: buffers must share their 16-byte alignment");
+    uint64_t blocks = (count / 2 + 1023) / 1024;
+    if (blocks == 0) blocks = 1;
+    const uint64_t cap = (uint64_t)ctx->sm_count * 2;
+    if (blocks > cap) blocks = cap;
+    peer_push_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, dst, count);
+    ctx->launches += 1;
+    SPRS_CUDA(ctx, cudaGetLastError());
+    return SPRS_B200_OK;
+}
 
 extern "C" {
 
@@ -39,19 +69,11 @@ int sprs_b200_peer_push_dev(sprs_b200_ctx* ctx, const double* d_y_own, uint64_t 
     if (!ctx || !d_y_own || (n_peers && !d_y_peers)) return SPRS_B200_ERR_ARGUMENT;
     if (n_peers < 0 || n_peers > SPMV_MAX_TARGETS)
         SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "n_peers must be 0..%d", SPMV_MAX_TARGETS);
-    if (rows == 0 || n_peers == 0) return SPRS_B200_OK;
     SpmvTargets dst;
     dst.n = n_peers;
     for (int q = 0; q < SPMV_MAX_TARGETS; ++q)
         dst.p[q] = q < n_peers ? d_y_peers[q] + row_offset : nullptr;
-    uint64_t blocks = (rows + 1023) / 1024;
-    const uint64_t cap = (uint64_t)ctx->sm_count * 2;
-    if (blocks > cap) blocks = cap;
-    peer_push_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_y_own + row_offset, dst,
-                                                                        rows);
-    ctx->launches += 1;
-    SPRS_CUDA(ctx, cudaGetLastError());
-    return SPRS_B200_OK;
+    return peer_push_launch(ctx, d_y_own + row_offset, dst, rows, (cudaStream_t)stream);
 }
 
 int sprs_b200_peer_alloc(sprs_b200_ctx* ctx, uint64_t bytes, void** d_ptr,
@@ -101,6 +123,24 @@ int sprs_b200_copy_dev(sprs_b200_ctx* ctx, void* dst, const void* src, uint64_t 
     return SPRS_B200_OK;
 }
 
+int sprs_b200_copy_to_device(sprs_b200_ctx* ctx, void* d_dst, const void* h_src, uint64_t bytes,
+                             void* stream) {
+    if (!ctx || (bytes && (!d_dst || !h_src))) return SPRS_B200_ERR_ARGUMENT;
+    SPRS_CUDA(ctx, cudaSetDevice(ctx->device));
+    SPRS_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    SPRS_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    return SPRS_B200_OK;
+}
+
+int sprs_b200_copy_to_host(sprs_b200_ctx* ctx, void* h_dst, const void* d_src, uint64_t bytes,
+                           void* stream) {
+    if (!ctx || (bytes && (!h_dst || !d_src))) return SPRS_B200_ERR_ARGUMENT;
+    SPRS_CUDA(ctx, cudaSetDevice(ctx->device));
+    SPRS_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    SPRS_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    return SPRS_B200_OK;
+}
+
 int sprs_b200_spmv_allgather_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
                                  const double* d_x, uint64_t row_offset, int n_targets,
                                  double* const* d_y_bufs, int accumulate, void* stream) {
@@ -112,20 +152,6 @@ int sprs_b200_spmv_allgather_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
     for (int q = 0; q < SPMV_MAX_TARGETS; ++q)
         yt.p[q] = q < n_targets ? d_y_bufs[q] + row_offset : nullptr;
     return spmv_launch_targets(ctx, mat, d_x, yt, accumulate, (cudaStream_t)stream);
-}
-
-int sprs_b200_spmv_stream_push_dev(sprs_b200_ctx* ctx, sprs_b200_csmat* mat, const double* d_x,
-                                   uint64_t row_offset, int n_targets, double* const* d_y_bufs,
-                                   int accumulate, int put_ctas, void* stream) {
-    if (!ctx || !mat || !d_y_bufs) return SPRS_B200_ERR_ARGUMENT;
-    if (n_targets < 1 || n_targets > SPMV_MAX_TARGETS)
-        SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "n_targets must be 1..%d", SPMV_MAX_TARGETS);
-    SpmvTargets yt;
-    yt.n = n_targets;
-    for (int q = 0; q < SPMV_MAX_TARGETS; ++q)
-        yt.p[q] = q < n_targets ? d_y_bufs[q] + row_offset : nullptr;
-    return spmv_launch_stream_push(ctx, mat, d_x, yt, accumulate, put_ctas,
-                                   (cudaStream_t)stream);
 }
 
 // Pipelined all-gather without any kernel waiting on another (plan B of the stream push): the

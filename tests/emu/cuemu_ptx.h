@@ -12,11 +12,11 @@ struct Mbar {
     int32_t count = 0, pending = 0;
     int64_t tx = 0;
 };
-inline std::unordered_map<const void*, Mbar>& table() {
+static inline std::unordered_map<const void*, Mbar>& table() {
     static std::unordered_map<const void*, Mbar> t;
     return t;
 }
-inline void settle(Mbar& b) {
+static inline void settle(Mbar& b) {
     if (b.pending == 0 && b.tx == 0) {
         b.phase ^= 1u;
         b.pending = b.count;
@@ -25,24 +25,24 @@ inline void settle(Mbar& b) {
 }
 }  // namespace cuemu_ptx
 
-inline void mbar_init(uint64_t* bar, uint32_t count) {
+static inline void mbar_init(uint64_t* bar, uint32_t count) {
     cuemu_ptx::Mbar b;
     b.count = b.pending = (int32_t)count;
     cuemu_ptx::table()[bar] = b;
 }
-inline void fence_mbar_init() {}
-inline void fence_proxy_async() {}
-inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+static inline void fence_mbar_init() {}
+static inline void fence_proxy_async() {}
+static inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     cuemu_ptx::Mbar& b = cuemu_ptx::table().at(bar);
     b.tx += bytes;
     b.pending -= 1;
     cuemu_ptx::settle(b);
 }
-inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
     // try_wait.parity(P) succeeds once the phase of parity P has completed
     while (cuemu_ptx::table().at(bar).phase == parity) cuemu::yield();
 }
-inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t) {
+static inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t) {
     if (bytes % 16 || ((uintptr_t)dst & 15) || ((uintptr_t)src & 15)) {
         fprintf(stderr, "cuemu: cp.async.bulk needs 16-byte aligned addresses and size "
                         "(dst %p src %p bytes %u)\n", dst, src, bytes);
@@ -53,8 +53,8 @@ inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, 
     b.tx -= bytes;
     cuemu_ptx::settle(b);
 }
-inline uint64_t policy_evict_first() { return 0; }
-inline uint64_t policy_evict_last() { return 0; }
-inline double ldg_f64_hint(const double* p, uint64_t) { return *p; }
-inline uint32_t ldg_stream_u32(const uint32_t* p, uint64_t) { return *p; }
-inline double ldg_stream_f64(const double* p, uint64_t) { return *p; }
+static inline uint64_t policy_evict_first() { return 0; }
+static inline uint64_t policy_evict_last() { return 0; }
+static inline double ldg_f64_hint(const double* p, uint64_t) { return *p; }
+static inline uint32_t ldg_stream_u32(const uint32_t* p, uint64_t) { return *p; }
+static inline double ldg_stream_f64(const double* p, uint64_t) { return *p; }

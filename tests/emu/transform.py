@@ -5,7 +5,7 @@ compiles against tests/emu/cuemu.h (see that header).  The product sources are n
   * `kernel<<<grid, block, smem, s>>>(a)`  -> `cuemu::launch(cuemu::cfg(grid, block, smem, s), [&] { kernel(a); })`
   * `extern __shared__ [__align__(N)] T v[];` -> `T* v = (T*)cuemu::dyn_smem();`
   * `__shared__ __align__(N) T v[..];`     -> `alignas(N) static T v[..];`
-  * the inline-PTX wrapper block of spmv.cu -> `#include "cuemu_ptx.h"`
+  * csrc/ptx.cuh (the inline-PTX wrappers)  -> `#include "cuemu_ptx.h"`
   * `#ifdef __CUDACC__`                    -> `#ifdef CUEMU`
 """
 import os
@@ -15,7 +15,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "..", "..", "sprs_b200", "csrc")
 FILES = ["api.cu", "spmv.cu", "spmm.cu", "spgemm.cu", "transpose.cu", "gen.cu", "peer.cu",
-         "solver.cu", "csvec.cu", "common.cuh", "scan.cuh"]
+         "solver.cu", "csvec.cu", "common.cuh", "scan.cuh", "ptx.cuh"]
+# comm.cu (process rendezvous, CUDA IPC / VMM, device barrier) is not emulated: the multi-rank
+# path is covered on hardware by tests/cpp/test_comm_ranks.cpp and tests/test_gpu_comm.py
 
 
 def match_back(s, end):
@@ -77,10 +79,8 @@ def rewrite_launches(s):
 def transform(name, s):
     s = s.replace("#include <cuda_runtime.h>", '#include "cuemu.h"')
     s = s.replace("__CUDACC__", "CUEMU")
-    if name == "spmv.cu":
-        a = s.index("// ---- PTX wrappers")
-        b = s.index("// ---- partition")
-        s = s[:a] + '}  // namespace\n#include "cuemu_ptx.h"\nnamespace {\n' + s[b:]
+    if name == "ptx.cuh":  # the inline-PTX wrappers: replaced wholesale by their stand-ins
+        return '#pragma once\n#include "common.cuh"\n#include "cuemu_ptx.h"\n'
     s = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\[\];",
                lambda m: "%s* %s = (%s*)cuemu::dyn_smem();" % (m.group(1), m.group(2), m.group(1)),
                s)

@@ -1,7 +1,7 @@
 """Structure fuzzer for the kernels' LOGIC on the CPU emulator (tests/emu; test infrastructure).
 
 Random small matrices whose row lengths are drawn to sit ON the kernels' internal boundaries --
-the SpMV tile size (384 non-zeros and the other variants), the 8/9-row register path, lane
+the SpMV tile size (256 non-zeros and the other variants), the 24/25-row register path, lane
 groups, the warp/CTA/bitmap bins of the SpGEMM -- are pushed through the C ABI of the emulated
 library and compared with the oracle: SpMV (values within the parity gate, bit-exact where
 the design promises it), SpMM (bit-exact), SpGEMM (indptr / indices bit-exact, values within
@@ -39,9 +39,9 @@ def setup(schedule):
     return sprs_b200, O
 
 
-BOUNDARY_LENS = [0, 0, 0, 1, 1, 2, 3, 5, 6, 7, 8, 11, 12, 13, 16, 24, 31, 32, 33, 47, 48, 49, 63,
-                 64, 65, 95, 96, 97, 127, 128, 129, 191, 192, 255, 256, 257, 383, 384, 385, 511,
-                 512, 513, 767, 768, 769, 1151, 1152, 1153]
+BOUNDARY_LENS = [0, 0, 0, 1, 1, 2, 3, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16, 24, 31, 32, 33, 47, 48, 49,
+                 63, 64, 65, 95, 96, 97, 127, 128, 129, 191, 192, 193, 255, 256, 257, 319, 320,
+                 321, 383, 384, 385, 511, 512, 513, 767, 768, 769, 1151, 1152, 1153]
 
 
 def row_lengths(rng, rows, cols):
@@ -52,7 +52,7 @@ def row_lengths(rng, rows, cols):
     elif mode == 1:   # constant short rows (register path / group sizes)
         lens = np.full(rows, rng.choice([1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 42, 43, 48, 64, 96, 128]))
     elif mode == 2:   # long empty stretches around tile boundaries
-        lens = rng.choice([0, 0, 0, 0, 384, 383, 1, 2, 768], rows)
+        lens = rng.choice([0, 0, 0, 0, 384, 383, 256, 255, 1, 2, 768, 32, 64], rows)
     elif mode == 3:   # poisson
         lens = rng.poisson(rng.choice([1, 4, 20, 60]), rows)
     elif mode == 4:   # hubs + dust
@@ -60,7 +60,7 @@ def row_lengths(rng, rows, cols):
         for _ in range(rng.integers(1, 4)):
             lens[rng.integers(0, rows)] = rng.choice([384, 385, 700, 1152, 1500, 3000, 4100])
     else:             # tile-aligned prefix sums: every row ends exactly on a multiple of 128/384
-        lens = rng.choice([128, 256, 384, 768, 0], rows)
+        lens = rng.choice([128, 256, 384, 768, 0, 32, 64, 0], rows)
     return np.minimum(lens.astype(np.int64), cols)
 
 
@@ -103,17 +103,18 @@ def push_case(sp, a, rows, cols, rng):
     accumulate = int(rng.integers(0, 2))
     ctx.check(ctx.lib.sprs_b200_spmv_dev(ctx.h, mirror, C.c_void_p(x.data_ptr()),
                                          C.c_void_p(ref.data_ptr()), accumulate, None))
-    for name in ("chunked", "stream"):
+    for name in ("chunked", "fused"):
         bufs = [torch.full((total,), -7.0, dtype=torch.float64) for _ in range(n_targets)]
         ptrs = (C.c_void_p * n_targets)(*[b.data_ptr() for b in bufs])
         if name == "chunked":
             st = ctx.lib.sprs_b200_spmv_chunked_push_dev(
                 ctx.h, mirror, C.c_void_p(x.data_ptr()), offset, n_targets, ptrs, accumulate,
                 int(rng.integers(0, 9)), None)
-        else:
-            st = ctx.lib.sprs_b200_spmv_stream_push_dev(
-                ctx.h, mirror, C.c_void_p(x.data_ptr()), offset, n_targets, ptrs, accumulate,
-                int(rng.integers(0, 6)), None)
+        else:  # the SpMV kernel itself stores every row into all targets (MULTI flavour)
+            if accumulate:
+                continue  # targets 1.. receive target 0's sum: only defined for y = A x
+            st = ctx.lib.sprs_b200_spmv_allgather_dev(
+                ctx.h, mirror, C.c_void_p(x.data_ptr()), offset, n_targets, ptrs, accumulate, None)
         ctx.check(st)
         want = ref.numpy()
         for q, b in enumerate(bufs):
