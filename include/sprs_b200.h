@@ -268,7 +268,10 @@ int sprs_b200_partition_rows(const void* indptr, int indptr_bytes, uint64_t rows
  * rank's slice (coalesced 16-byte stores).  With a multicast-bound y there is ONE remote
  * target (the multicast address: the row leaves the GPU once and the switch replicates it),
  * otherwise world-1 peer mappings.  AUTO = the measured default.            */
-enum { SPRS_B200_EXCHANGE_AUTO = 0, SPRS_B200_EXCHANGE_FUSED = 1, SPRS_B200_EXCHANGE_PUSH = 2 };
+enum { SPRS_B200_EXCHANGE_AUTO = 0, SPRS_B200_EXCHANGE_FUSED = 1, SPRS_B200_EXCHANGE_PUSH = 2,
+       /* OR-ed into `exchange`: leave the closing device barrier to the caller (who then calls
+        * sprs_b200_comm_barrier_dev on the same stream before y is read anywhere) */
+       SPRS_B200_EXCHANGE_NO_BARRIER = 0x100 };
 /* Row-partitioned y = A x (device-resident): this rank's CSR row block `mat` (rows
  * row_offset .. row_offset + mat.rows of A, slice_outer + proper_indptr), x replicated
  * (d_x: cols doubles on this device), y a symmetric buffer of n doubles.  Enqueues on

@@ -737,6 +737,8 @@ int sprs_b200_spmv_rowpart(sprs_b200_comm* c, const sprs_b200_csmat* mat, const 
         SPRS_FAIL(ctx, SPRS_B200_ERR_DIMENSION, "Dimension mismatch: row block exceeds y");
     cudaStream_t s = (cudaStream_t)stream;
     const bool mc = y->mc_ptr != nullptr;
+    const bool no_barrier = (exchange & SPRS_B200_EXCHANGE_NO_BARRIER) != 0;
+    exchange &= ~SPRS_B200_EXCHANGE_NO_BARRIER;
     if (exchange == SPRS_B200_EXCHANGE_AUTO)
         exchange = SPRS_B200_EXCHANGE_PUSH;
     SpmvTargets yt;
@@ -768,7 +770,7 @@ int sprs_b200_spmv_rowpart(sprs_b200_comm* c, const sprs_b200_csmat* mat, const 
     } else {
         SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "comm: unknown exchange mode %d", exchange);
     }
-    return sprs_b200_comm_barrier_dev(c, stream);
+    return no_barrier ? SPRS_B200_OK : sprs_b200_comm_barrier_dev(c, stream);
 }
 
 // `&A * &x` on a row-partitioned matrix with HOST vectors, every rank handling only its own

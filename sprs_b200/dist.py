@@ -313,360 +313,178 @@ class _DevPtr:
                                          "version": 2}
 
 
-class FusedAllGatherSpMV:
-    """Row-partitioned y = A x whose all-gather is fused into the SpMV kernel.
+EXCHANGES = {"auto": 0, "fused": 1, "push": 2}
+NO_BARRIER = 0x100  # sprs_b200.h SPRS_B200_EXCHANGE_NO_BARRIER
 
-    Every rank allocates its full-length y through sprs_b200_peer_alloc, ships the CUDA IPC
-    handle to the other ranks (torch.distributed object all-gather: plumbing), and maps
-    theirs.  step() launches ONE SpMV whose epilogue stores every finished row of this
-    rank's block into all `world` buffers over NVLink (sprs_b200_spmv_allgather_dev); a
-    stream-ordered 1-element all-reduce is the only remaining collective: it is the barrier
-    after which every rank's y is complete.
 
-    An iterative caller that reads y on every rank and then calls step() again must either
-    finish reading before ANY rank can start the next step (a second barrier), or alternate
-    between two operators (two y buffers): a rank that runs ahead stores its rows of the next
-    product straight into its peers' y (row_partitioned_bicgstab does the latter)."""
+class Comm:
+    """ctypes face of sprs_b200_comm (include/sprs_b200.h): the ranks of one node, met through a
+    64-byte id.  Everything behind it -- rendezvous, symmetric buffers (CUDA IPC, or VMM +
+    NVSwitch multicast), the device barrier -- is C++ (csrc/comm.cu); this class only forwards.
+    `Comm.unique_id()` on rank 0, ship the bytes to the other ranks by any transport
+    (torch.distributed / MPI / a pipe), then Comm(ctx, id, rank, world) on every rank."""
 
-    def __init__(self, ctx, mirror, bounds, rank, world, n, dist, device):
+    @staticmethod
+    def unique_id(ctx=None):
         import ctypes as C
-        import torch
-        self.ctx, self.mirror, self.bounds, self.rank, self.world = ctx, mirror, bounds, rank, world
-        self.dist, self.n = dist, n
-        lib = ctx.lib
-        own = C.c_void_p()
-        handle = C.create_string_buffer(64)
-        ctx.check(lib.sprs_b200_peer_alloc(ctx.h, 8 * max(n, 1), C.byref(own), handle))
-        self._own = own
-        handles = [None] * world
-        dist.all_gather_object(handles, bytes(handle.raw))
-        self._peers = []
-        ptrs = [own.value]
-        for g in range(world):
-            if g == rank:
-                continue
-            p = C.c_void_p()
-            ctx.check(lib.sprs_b200_peer_open(ctx.h, handles[g], C.byref(p)))
-            self._peers.append(p)
-            ptrs.append(p.value)
-        self._targets = (C.c_void_p * len(ptrs))(*ptrs)
-        self.y = torch.as_tensor(_DevPtr(own.value, n), device=device)
-        self.y.zero_()
-        self._flag = torch.zeros(1, device=device)
-        torch.cuda.synchronize()
-        dist.barrier()
+        from . import _lib
+        lib = ctx.lib if ctx is not None else _lib.load()
+        buf = C.create_string_buffer(64)
+        st = lib.sprs_b200_comm_unique_id(buf)
+        if st != 0:
+            raise RuntimeError("sprs_b200_comm_unique_id failed: %d" % st)
+        return bytes(buf.raw)
+
+    def __init__(self, ctx, comm_id, rank, world):
+        import ctypes as C
+        self.ctx, self.rank, self.world = ctx, rank, world
+        h = C.c_void_p()
+        ctx.check(ctx.lib.sprs_b200_comm_init_rank(ctx.h, C.create_string_buffer(comm_id, 64), rank,
+                                                   world, C.byref(h)))
+        self.h = h
+
+    @property
+    def multicast(self):
+        return bool(self.ctx.lib.sprs_b200_comm_multicast_supported(self.h))
+
+    def allgather(self, record):
+        """record: bytes (<= 512, same length on every rank) -> list of every rank's record"""
+        import ctypes as C
+        n = len(record)
+        out = C.create_string_buffer(n * self.world)
+        self.ctx.check(self.ctx.lib.sprs_b200_comm_allgather_host(
+            self.h, C.create_string_buffer(record, n), n, out))
+        return [out.raw[g * n:(g + 1) * n] for g in range(self.world)]
+
+    def allgather_f64(self, values):
+        """all-gather of a few float64 per rank -> array (world, len(values))"""
+        rec = np.asarray(values, dtype=np.float64).tobytes()
+        return np.stack([np.frombuffer(r, dtype=np.float64) for r in self.allgather(rec)])
+
+    def barrier_host(self):
+        self.ctx.check(self.ctx.lib.sprs_b200_comm_barrier_host(self.h))
+
+    def barrier_dev(self, stream=None):
+        self.ctx.check(self.ctx.lib.sprs_b200_comm_barrier_dev(self.h, stream))
+
+    def check(self, stream=None):
+        self.ctx.check(self.ctx.lib.sprs_b200_comm_check(self.h, stream))
+
+    def symm(self, nbytes, multicast=True):
+        return SymmBuffer(self, nbytes, multicast)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.check(self.ctx.lib.sprs_b200_comm_free(self.h))
+            self.h = None
+
+
+class SymmBuffer:
+    """sprs_b200_symm: `nbytes` of zeroed device memory on every rank, each rank's buffer mapped
+    on every rank, optionally with the NVSwitch multicast address of all of them."""
+
+    def __init__(self, comm, nbytes, multicast=True):
+        import ctypes as C
+        self.comm, self.nbytes = comm, nbytes
+        h = C.c_void_p()
+        comm.ctx.check(comm.ctx.lib.sprs_b200_symm_alloc(comm.h, nbytes, int(bool(multicast)),
+                                                         C.byref(h)))
+        self.h = h
+
+    def ptr(self, rank=None):
+        r = self.comm.rank if rank is None else rank
+        return int(self.comm.ctx.lib.sprs_b200_symm_ptr(self.h, r) or 0)
+
+    @property
+    def multicast_ptr(self):
+        return int(self.comm.ctx.lib.sprs_b200_symm_multicast_ptr(self.h) or 0)
+
+    def tensor(self, n, device):
+        """zero-copy float64 torch view of this rank's own buffer"""
+        return tensor_view(self.ptr(), n, device)
+
+    def free(self):
+        if getattr(self, "h", None):
+            self.comm.ctx.check(self.comm.ctx.lib.sprs_b200_symm_free(self.h))
+            self.h = None
+
+
+def _stream_ptr(device):
+    import ctypes as C
+    import torch
+    if torch.device(device).type != "cuda":
+        return None
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class CommSpMV:
+    """Row-partitioned y = A x through the C ABI (sprs_b200_spmv_rowpart): this rank's row block
+    is multiplied, the slice is all-gathered into EVERY rank's y over NVLink (exchange: "fused" =
+    stores from the SpMV kernel itself, "push" = one put kernel; through the NVSwitch multicast
+    address of y when the communicator has one) and a device barrier closes the step -- all on
+    torch's current stream.  `y` is this rank's full-length result (a view of the symmetric
+    buffer).  compute() / exchange() split the step the way bench.py times it: compute = SpMV +
+    stores, exchange = the barrier.
+
+    An iterative caller that reads y on every rank and then steps again must alternate between
+    two operators (two y buffers): a rank that runs ahead stores rows of product k+1 into a peer
+    that may still read product k (row_partitioned_bicgstab does that)."""
+
+    def __init__(self, comm, mirror, bounds, n, device, exchange="auto", multicast=True):
+        self.comm, self.mirror, self.bounds, self.n, self.device = comm, mirror, bounds, n, device
+        self.rank, self.world = comm.rank, comm.world
+        self.mode = EXCHANGES[exchange]
+        self.buf = comm.symm(8 * max(n, 2), multicast)
+        self.multicast = self.buf.multicast_ptr != 0
+        self.y = self.buf.tensor(n, device)
 
     @property
     def rows_local(self):
         return self.bounds[self.rank + 1] - self.bounds[self.rank]
 
-    def compute(self, x):
+    def _call(self, x, flags):
         import ctypes as C
-        import torch
-        ctx = self.ctx
-        ctx.check(ctx.lib.sprs_b200_spmv_allgather_dev(
-            ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()), self.bounds[self.rank],
-            len(self._targets), self._targets, 0,
-            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        ctx = self.comm.ctx
+        ctx.check(ctx.lib.sprs_b200_spmv_rowpart(
+            self.comm.h, self.mirror.h, C.c_void_p(x.data_ptr()), self.buf.h,
+            self.bounds[self.rank], self.mode | flags, _stream_ptr(self.device)))
+
+    def compute(self, x):
+        self._call(x, NO_BARRIER)
 
     def exchange(self):
-        if self.world > 1:
-            self.dist.all_reduce(self._flag)  # barrier: all peers' rows have landed
+        self.comm.barrier_dev(_stream_ptr(self.device))
 
     def step(self, x):
-        self.compute(x)
-        self.exchange()
+        self._call(x, 0)
         return self.y
 
     def close(self):
         import torch
-        torch.cuda.synchronize()
-        if self.world > 1:
-            self.dist.barrier()
-        for p in self._peers:
-            self.ctx.lib.sprs_b200_peer_close(self.ctx.h, p)
-        self._peers = []
-        if self._own:
-            self.y = None
-            self.ctx.lib.sprs_b200_peer_free(self.ctx.h, self._own)
-            self._own = None
+        if torch.device(self.device).type == "cuda":
+            torch.cuda.synchronize()
+        self.y = None
+        self.buf.free()
 
 
-class PushAllGatherSpMV(FusedAllGatherSpMV):
-    """Row-partitioned y = A x; the all-gather is this library's own "put": after the
-    (single-target) SpMV, one push kernel copies the rank's y slice into every peer buffer
-    with coalesced stores over NVLink, then the 1-element all-reduce barrier.  Same peer
-    buffers and set-up as FusedAllGatherSpMV; trades the in-kernel overlap for an SpMV that
-    is not slowed down by remote stores."""
+class CommHostSpMV:
+    """`&A * &x` on a row-partitioned matrix with HOST vectors (sprs_b200_mul_mat_vec_rowpart):
+    every rank uploads only its own slice of x (rows bounds[rank] .. bounds[rank+1] of a square
+    system: the same cut as y), the slices are all-gathered over NVLink, the block is multiplied
+    and only the rank's y slice comes back -- h2d + d2h bytes per step = 8 n + 8 n in TOTAL over
+    all ranks."""
 
-    def compute(self, x):
+    def __init__(self, comm, mirror, bounds, n, multicast=True):
+        self.comm, self.mirror, self.bounds, self.n = comm, mirror, bounds, n
+        self.x = comm.symm(8 * max(n, 2), multicast)
+
+    def step(self, x_slice_ptr, y_slice_ptr):
         import ctypes as C
-        import torch
-        ctx = self.ctx
-        s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        r0 = self.bounds[self.rank]
-        ctx.check(ctx.lib.sprs_b200_spmv_dev(ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()),
-                                             C.c_void_p(self._own.value + 8 * r0), 0, s))
-
-    def exchange(self):
-        import ctypes as C
-        import torch
-        if self.world <= 1:
-            return
-        ctx = self.ctx
-        s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        peers = (C.c_void_p * len(self._peers))(*[p.value for p in self._peers])
-        ctx.check(ctx.lib.sprs_b200_peer_push_dev(ctx.h, self._own, self.bounds[self.rank],
-                                                  self.rows_local, len(self._peers), peers, s))
-        self.dist.all_reduce(self._flag)
-
-    def step(self, x):
-        self.compute(x)
-        self.exchange()
-        return self.y
-
-
-class StreamAllGatherSpMV(FusedAllGatherSpMV):
-    """Row-partitioned y = A x with a pipelined all-gather: the SpMV writes only this rank's
-    slice and publishes its progress; a small put kernel on a side stream copies every
-    finished chunk of rows (carries of the rows cut by tile boundaries applied first) into the
-    peer buffers WHILE the SpMV is still running (sprs_b200_spmv_stream_push_dev).  The exchange overlaps the compute like the fused form, without
-    its remote stores in the SpMV warps' own LSU queues.  Same peer buffers and barrier."""
-
-    put_ctas = 0  # 0 = library default
-
-    def compute(self, x):
-        import ctypes as C
-        import torch
-        ctx = self.ctx
-        ctx.check(ctx.lib.sprs_b200_spmv_stream_push_dev(
-            ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()), self.bounds[self.rank],
-            len(self._targets), self._targets, 0, int(self.put_ctas),
-            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-
-
-class ChunkedPushAllGatherSpMV(FusedAllGatherSpMV):
-    """Row-partitioned y = A x with a pipelined all-gather built from plain stream ordering
-    (plan B of StreamAllGatherSpMV: no kernel waits on another).  The rank's tile stream is
-    launched in a few chunks of decreasing size; behind each chunk's event a side stream runs
-    the put kernel for the rows that chunk completed while the next chunk computes
-    (sprs_b200_spmv_chunked_push_dev).  Same peer buffers and barrier as the fused form."""
-
-    n_chunks = 0  # 0 = library default (4)
-
-    def compute(self, x):
-        import ctypes as C
-        import torch
-        ctx = self.ctx
-        ctx.check(ctx.lib.sprs_b200_spmv_chunked_push_dev(
-            ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()), self.bounds[self.rank],
-            len(self._targets), self._targets, 0, int(self.n_chunks),
-            C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-
-
-class McastAllGatherSpMV:
-    """Row-partitioned y = A x whose all-gather goes through the NVSwitch MULTICAST object of
-    y (NVLS): every rank's full-length y is one symmetric allocation bound to a multicast
-    address, and a store to that address is replicated by the switch into the y of ALL ranks.
-    A finished row therefore leaves the GPU ONCE instead of once per peer: at 8 GPUs the
-    NVLink egress of a rank drops from 7 x 10 MB to 10 MB per step.
-
-    Allocation, the exchange of the memory handles between the processes and the multicast
-    binding are `torch.distributed._symmetric_memory` (device-memory plumbing); the stores are
-    this library's kernels, unchanged: `multimem.st` and `st.global` on a multicast address
-    are the same SASS (STG.E.64), so the multicast pointer is simply the second y target of
-
-      * mode "fused": the SpMV kernel itself (sprs_b200_spmv_allgather_dev with targets
-        [local y, multicast y]) -- one extra store per finished row instead of world-1;
-      * mode "push": the plain SpMV into the local y, then the put kernel copying this
-        rank's slice to the multicast address (sprs_b200_peer_push_dev with one "peer");
-      * modes "stream" / "chunked": the pipelined puts of StreamAllGatherSpMV /
-        ChunkedPushAllGatherSpMV with the multicast address as their only remote target --
-        finished row chunks leave once, while the SpMV is still running.
-
-    Barrier after the stores: the 1-element NCCL all-reduce of the other modes, or
-    (barrier="symm") the signal-pad barrier of the symmetric-memory handle, a device-side
-    flag exchange in peer memory with no NCCL kernel.
-    Fails loudly when the devices have no multicast support (no silent fallback).
-    Not yet run on hardware (written after round 1's GPU budget): opt-in
-    (`bench.py --exchange mcast|mcast-push|mcast-stream|mcast-chunked`), to be measured by
-    tools/r2_scale_probe.sh."""
-
-    def __init__(self, ctx, mirror, bounds, rank, world, n, dist, device, mode="fused",
-                 barrier="nccl", group=None):
-        import ctypes as C
-        import torch
-        import torch.distributed._symmetric_memory as symm
-        from . import generate as G
-        from .sparse import ThirdPartyError
-        if mode not in ("fused", "push", "stream", "chunked") or barrier not in ("nccl", "symm"):
-            raise ValueError("mode: fused|push|stream|chunked, barrier: nccl|symm")
-        self.ctx, self.mirror, self.bounds, self.rank, self.world = ctx, mirror, bounds, rank, world
-        self.dist, self.n, self.mode, self.barrier = dist, n, mode, barrier
-        grp = group if group is not None else dist.group.WORLD
-        buf = symm.empty(max(n, 2), dtype=torch.float64, device=device)
-        self._hdl = symm.rendezvous(buf, grp)
-        mc = int(self._hdl.multicast_ptr or 0)
-        if world > 1 and mc == 0:
-            raise ThirdPartyError(0, "NVSwitch multicast is not available for this process group "
-                                     "(symmetric-memory handle has no multicast_ptr)")
-        self._buf = buf
-        self.y = buf[:n]
-        self.y.zero_()
-        self._own = buf.data_ptr()
-        self._mc = mc
-        ptrs = [self._own] + ([mc] if world > 1 else [])
-        self._targets = (C.c_void_p * len(ptrs))(*ptrs)
-        self._mc_only = (C.c_void_p * 1)(mc)
-        self._flag = torch.zeros(1, device=device)
-        G._sync()
-        dist.barrier()
-
-    @property
-    def rows_local(self):
-        return self.bounds[self.rank + 1] - self.bounds[self.rank]
-
-    def compute(self, x):
-        import ctypes as C
-        from . import generate as G
-        ctx = self.ctx
-        s = G._stream_ptr()
-        r0 = self.bounds[self.rank]
-        if self.mode == "fused":
-            ctx.check(ctx.lib.sprs_b200_spmv_allgather_dev(
-                ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()), r0, len(self._targets),
-                self._targets, 0, s))
-        elif self.mode == "stream":
-            ctx.check(ctx.lib.sprs_b200_spmv_stream_push_dev(
-                ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()), r0, len(self._targets),
-                self._targets, 0, 0, s))
-        elif self.mode == "chunked":
-            ctx.check(ctx.lib.sprs_b200_spmv_chunked_push_dev(
-                ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()), r0, len(self._targets),
-                self._targets, 0, 0, s))
-        else:
-            ctx.check(ctx.lib.sprs_b200_spmv_dev(ctx.h, self.mirror.h, C.c_void_p(x.data_ptr()),
-                                                 C.c_void_p(self._own + 8 * r0), 0, s))
-
-    def exchange(self):
-        import ctypes as C
-        from . import generate as G
-        if self.world <= 1:
-            return
-        ctx = self.ctx
-        if self.mode == "push":
-            s = G._stream_ptr()
-            ctx.check(ctx.lib.sprs_b200_peer_push_dev(ctx.h, C.c_void_p(self._own),
-                                                      self.bounds[self.rank], self.rows_local, 1,
-                                                      self._mc_only, s))
-        if self.barrier == "symm":
-            self._hdl.barrier(channel=0)   # stream-ordered, after this rank's stores
-        else:
-            self.dist.all_reduce(self._flag)
-
-    def step(self, x):
-        self.compute(x)
-        self.exchange()
-        return self.y
+        ctx = self.comm.ctx
+        r0, r1 = self.bounds[self.comm.rank], self.bounds[self.comm.rank + 1]
+        ctx.check(ctx.lib.sprs_b200_mul_mat_vec_rowpart(
+            self.comm.h, self.mirror.h, self.x.h, C.c_void_p(x_slice_ptr), r0, r1 - r0,
+            C.c_void_p(y_slice_ptr), r1 - r0))
 
     def close(self):
-        from . import generate as G
-        G._sync()
-        if self.world > 1:
-            self.dist.barrier()
-        self.y = self._buf = self._hdl = None
-
-
-class OverlappedAllGatherSpMV:
-    """Row-partitioned y = A x with the all-gather of y overlapped with the compute.
-
-    This rank's row block is cut into `chunks` sub-blocks (cost-balanced).  The SpMV of
-    sub-block c runs on the compute stream; as soon as it finishes (event), the copy stream
-    pushes that slice of y into every peer's y buffer with peer-to-peer copies (CUDA IPC
-    mappings, DMA engines over NVLink -- no SM time), while sub-block c+1 is computing.
-    Only the last slice's push and one 1-element all-reduce (the barrier after which every
-    rank's y is complete) are exposed."""
-
-    def __init__(self, ctx, local, bounds, rank, world, n, dist, device, chunks=4, row_cost=0.0):
-        import ctypes as C
-        import torch
-        self.ctx, self.rank, self.world, self.dist, self.n = ctx, rank, world, dist, n
-        self.bounds = bounds
-        lib = ctx.lib
-        own = C.c_void_p()
-        handle = C.create_string_buffer(64)
-        ctx.check(lib.sprs_b200_peer_alloc(ctx.h, 8 * max(n, 1), C.byref(own), handle))
-        self._own = own
-        handles = [None] * world
-        dist.all_gather_object(handles, bytes(handle.raw))
-        self._peers = []
-        for g in range(world):
-            if g == rank:
-                continue
-            p = C.c_void_p()
-            ctx.check(lib.sprs_b200_peer_open(ctx.h, handles[g], C.byref(p)))
-            self._peers.append(p)
-        self.y = torch.as_tensor(_DevPtr(own.value, n), device=device)
-        self.y.zero_()
-        # sub-blocks of the local block
-        chunks = max(1, min(chunks, max(local.rows, 1)))
-        cb = nnz_balanced_bounds(local.indptr, chunks, row_cost=row_cost)
-        self.sub = []
-        r0 = bounds[rank]
-        for c in range(chunks):
-            if cb[c + 1] > cb[c]:
-                blk = local if chunks == 1 else local.slice_rows(cb[c], cb[c + 1])
-                self.sub.append((r0 + cb[c], r0 + cb[c + 1], blk))
-        self.copy_stream = torch.cuda.Stream(device=device)
-        self.events = [torch.cuda.Event() for _ in self.sub]
-        self.done = torch.cuda.Event()
-        self._flag = torch.zeros(1, device=device)
-        torch.cuda.synchronize()
-        dist.barrier()
-
-    @property
-    def rows_local(self):
-        return self.bounds[self.rank + 1] - self.bounds[self.rank]
-
-    def step(self, x):
-        import ctypes as C
-        import torch
-        ctx, lib = self.ctx, self.ctx.lib
-        cur = torch.cuda.current_stream()
-        cs = self.copy_stream
-        xp = C.c_void_p(x.data_ptr())
-        for i, (a0, a1, blk) in enumerate(self.sub):
-            ctx.check(lib.sprs_b200_spmv_dev(ctx.h, blk.mirror.h, xp,
-                                             C.c_void_p(self._own.value + 8 * a0), 0,
-                                             C.c_void_p(cur.cuda_stream)))
-            if self.world > 1:
-                self.events[i].record(cur)
-                cs.wait_event(self.events[i])
-                for p in self._peers:
-                    ctx.check(lib.sprs_b200_copy_dev(
-                        ctx.h, C.c_void_p(p.value + 8 * a0), C.c_void_p(self._own.value + 8 * a0),
-                        8 * (a1 - a0), C.c_void_p(cs.cuda_stream)))
-        if self.world > 1:
-            self.done.record(cs)
-            cur.wait_event(self.done)
-            self.dist.all_reduce(self._flag)  # barrier: every peer's pushes have landed
-        return self.y
-
-    def compute(self, x):  # bench.py times compute and exchange together for this mode
-        self.step(x)
-
-    def exchange(self):
-        pass
-
-    def close(self):
-        import torch
-        torch.cuda.synchronize()
-        if self.world > 1:
-            self.dist.barrier()
-        for p in self._peers:
-            self.ctx.lib.sprs_b200_peer_close(self.ctx.h, p)
-        self._peers = []
-        if self._own:
-            self.y = None
-            self.ctx.lib.sprs_b200_peer_free(self.ctx.h, self._own)
-            self._own = None
+        self.x.free()
