@@ -9,15 +9,20 @@ Metric (BASELINE.json): CSR SpMV f64 GFLOP/s and achieved fraction of the HBM ro
 A "step" is one `y = A x` over the whole matrix (all ranks together).  The default
 workload is BASELINE config 5 -- the configuration the metric is quoted on: 10M x 10M
 R-MAT, ~100 nnz/row (~1e9 nnz, 12 GB, fits one GPU) -- at every N (strong scaling:
-contiguous nnz-balanced row blocks per rank, x replicated, all-gather of y).
+contiguous cost-balanced row blocks per rank, x replicated, all-gather of y over NVLink
+through the library's own communicator, include/sprs_b200.h).
 Other workloads: spmv_rand_1m (config 2), spmm_rand_1m_k64 (config 3),
-spgemm_rmat_500k (config 4).  One JSON line is printed by rank 0.
+spgemm_rmat_500k (config 4); at N=1 the default run also reports them under "extra".
+One JSON line is printed by rank 0.
 """
 import argparse
 import json
 import os
+import shutil
 import statistics
+import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -26,7 +31,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-import bench_other  # noqa: E402  (needs ROOT on sys.path)
+import bench_other  # noqa: E402  (needs ROOT on sys.path; imports nothing heavy)
 
 WORKLOADS = {
     # name: (kind, n, nnz_per_row, generator)
@@ -34,7 +39,7 @@ WORKLOADS = {
     "spmv_rand_1m": ("spmv", 1_000_000, 32, "rand"),
     "spmm_rand_1m_k64": ("spmm", 1_000_000, 32, "rand"),
     "spgemm_rmat_500k": ("spgemm", 500_000, 16, "rmat"),
-    # small variants for quick checks
+    # small variant for quick checks and the CPU dry run
     "spmv_rmat_1m": ("spmv", 1_000_000, 100, "rmat"),
 }
 SEEDS = {"spmv_rmat_10m": 0x5EED0005, "spmv_rand_1m": 0x5EED0002, "spmm_rand_1m_k64": 0x5EED0002,
@@ -96,7 +101,6 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + self.err]}
         self.stop_flag = True
         self.t.join()
-        nv = self.nv
         inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
         bits = 0
         for s in inside:
@@ -110,11 +114,55 @@ class ClockSampler:
                 "samples": len(inside)}
 
 
+def rows_to_host(a, rows_t):
+    """Host CSR (uint32 indptr / indices, f64 data) of the given SORTED rows of a DeviceCsr."""
+    import torch
+    ip = a.indptr.to(torch.int64) & 0xFFFFFFFF  # int32 storage of u32 values
+    starts = ip[rows_t]
+    lens = ip[rows_t + 1] - starts
+    sub_ip = torch.zeros(rows_t.numel() + 1, dtype=torch.int64, device=ip.device)
+    torch.cumsum(lens, 0, out=sub_ip[1:])
+    total = int(sub_ip[-1].item())
+    pos = (torch.arange(total, device=ip.device, dtype=torch.int64)
+           - torch.repeat_interleave(sub_ip[:-1], lens) + torch.repeat_interleave(starts, lens))
+    hind = a.indices[pos].cpu().numpy().view(np.uint32)
+    hdat = a.data[pos].cpu().numpy()
+    return sub_ip.cpu().numpy().astype(np.uint32), hind, hdat
+
+
+def parity_vs_oracle(full, x, y, n_random=10000, n_heavy=100, seed=1234):
+    """UNTIMED check of a device result against the CPU oracle (the reference's loop,
+    oracle/sprs_oracle.cpp after prod.rs:274-298) on the heaviest rows plus a random sample of
+    the WHOLE y this rank holds (at N > 1: the all-gathered vector, rows of every rank's block).
+    Gate: |got - ref| <= 1e-6 * sum|terms| per row.  Returns (ok, rows, max ratio of
+    |got - ref| to the gate)."""
+    import torch
+    from oracle import oracle as O
+    n = full.rows
+    ip = full.indptr.to(torch.int64) & 0xFFFFFFFF
+    lens = ip[1:] - ip[:-1]
+    heavy = torch.topk(lens, min(n_heavy, n)).indices
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    rnd = torch.randint(0, n, (min(n_random, n),), generator=g).to(ip.device)
+    rows_t = torch.unique(torch.cat([heavy, rnd]))
+    hip, hind, hdat = rows_to_host(full, rows_t)
+    hx = x.cpu().numpy()
+    ref, bound = np.zeros(rows_t.numel()), np.zeros(rows_t.numel())
+    O.mul_acc_mat_vec_csr(hip, hind, hdat, hx, ref)
+    O.mul_acc_mat_vec_csr(hip, hind, np.abs(hdat), np.abs(hx), bound)
+    got = y[rows_t].cpu().numpy()
+    ratio = np.abs(got - ref) / (1e-6 * bound + 1e-300)
+    worst = float(np.nanmax(ratio)) if ratio.size else 0.0
+    ok = bool(np.all(np.isfinite(got)) and worst <= 1.0)
+    return ok, int(rows_t.numel()), worst
+
+
 def sample_rows_to_host(a, target_nnz, nblocks=8):
     """A bounded sample of the SAME matrix for the CPU baseline: `nblocks` contiguous row
     blocks spread over the matrix, ~target_nnz non-zeros in total, as one host CSR."""
     import torch
-    ip = a.indptr.to(torch.int64)
+    ip = a.indptr.to(torch.int64) & 0xFFFFFFFF
     n = a.rows
     per = max(1, target_nnz // nblocks)
     parts_ip, parts_ind, parts_dat, total, rows = [np.zeros(1, np.int64)], [], [], 0, 0
@@ -166,45 +214,73 @@ def cpu_spmv_baseline(a, x_t, budget_nnz):
             "host_cores": cores}
 
 
+# ---- reference arm -------------------------------------------------------------------
+def generate_to_dir(workload, out_dir):
+    """Child-process entry (`bench.py --gen-to DIR`): builds the workload's matrix and x with the
+    device generator and leaves them as .npy files, so that the reference arm's own process
+    never maps the product library."""
+    import torch
+    import sprs_b200 as sp
+    from sprs_b200 import generate as G
+    kind, n, npr, gen = WORKLOADS[workload]
+    ctx = sp.Context.default(0)
+    torch.cuda.set_device(0)
+    a = G.make_matrix(ctx, gen, n, npr, SEEDS[workload])
+    x = G.normal_vector(ctx, n)
+    np.save(os.path.join(out_dir, "indptr.npy"), a.indptr.cpu().numpy().view(np.uint32))
+    np.save(os.path.join(out_dir, "indices.npy"), a.indices.cpu().numpy().view(np.uint32))
+    np.save(os.path.join(out_dir, "data.npy"), a.data.cpu().numpy())
+    np.save(os.path.join(out_dir, "x.npy"), x.cpu().numpy())
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the
-    Rust reference cannot be built here), on the box's host cores, same metric/config."""
+    """--impl reference: the reference's CPU implementation of the path (oracle port of
+    prod.rs:274-298; the Rust reference cannot be built here), on the box's host cores, same
+    metric, the WHOLE matrix of the same config every step.  The inputs come from a child
+    process (the device generator) through /dev/shm files: this process loads oracle/ only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     kind, n, npr, gen = WORKLOADS[args.workload]
     from oracle import oracle as O
-    # inputs: same generator as the GPU arm when a GPU is present, else a numpy stand-in
-    sample_nnz = 1 << 26
+    tmp_root = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    tmp = tempfile.mkdtemp(prefix="sprs_b200_ref_", dir=tmp_root)
+    src = "device generator in a child process, handed over as .npy files (%s)" % tmp
     try:
-        import torch
-        import sprs_b200 as sp
-        from sprs_b200 import generate as G
-        ctx = sp.Context.default(0)
-        torch.cuda.set_device(0)
-        a = G.make_matrix(ctx, gen, n, npr, SEEDS[args.workload])
-        x = G.normal_vector(ctx, n)
-        hip, hind, hdat, rows = sample_rows_to_host(a, sample_nnz)
-        hx = x.cpu().numpy()
-        src = "device-generated matrix, 8 row blocks"
-        del a, x
-        torch.cuda.empty_cache()
-    except Exception as e:  # no GPU: uniform random sample of the same shape
+        env = dict(os.environ)
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--gen-to", tmp,
+                            "--workload", args.workload], env=env, capture_output=True, text=True,
+                           timeout=900)
+        if r.returncode != 0:
+            raise RuntimeError(r.stderr[-300:])
+        hip = np.load(os.path.join(tmp, "indptr.npy"))
+        hind = np.load(os.path.join(tmp, "indices.npy"))
+        hdat = np.load(os.path.join(tmp, "data.npy"))
+        hx = np.load(os.path.join(tmp, "x.npy"))
+        rows, whole = n, True
+    except Exception as e:  # no GPU for the generator: uniform random stand-in of the same shape
         rng = np.random.default_rng(SEEDS[args.workload])
-        rows = sample_nnz // npr
+        rows = (1 << 24) // npr
         hind = rng.integers(0, n, size=rows * npr, dtype=np.uint32).reshape(rows, npr)
         hind.sort(axis=1)
         hind = hind.reshape(-1)
         hip = (np.arange(rows + 1, dtype=np.uint64) * npr).astype(np.uint32)
         hdat = rng.standard_normal(rows * npr)
         hx = rng.standard_normal(n)
-        src = "numpy uniform stand-in (no GPU for the generator: %s)" % type(e).__name__
+        whole = False
+        src = "numpy uniform stand-in (generator child failed: %s)" % (str(e)[:120],)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
     nnz = int(hip[-1])
     y = np.zeros(rows)
     for _ in range(args.warmup):
+        y[:] = 0
         O.mul_acc_mat_vec_csr(hip, hind, hdat, hx, y)
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        y[:] = 0
         O.mul_acc_mat_vec_csr(hip, hind, hdat, hx, y)
     dt = (time.perf_counter() - t0) / args.steps
     val = 2.0 * nnz / dt / 1e9
@@ -212,106 +288,28 @@ def run_reference(args):
             "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "n": n, "nnz_per_row": npr,
-                       "sample_nnz": nnz, "sample_rows": rows, "source": src},
+            "config": {"workload": args.workload, "n": n, "nnz": nnz if whole else None,
+                       "nnz_per_row": npr, "generator": gen, "index_bytes": 4,
+                       "whole_matrix": whole, "rows_per_step": rows, "nnz_per_step": nnz,
+                       "source": src},
             "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": 1, "kind": "port",
-                             "sample": "%d nnz per step; sprs SpMV/SpMM are single-threaded "
-                                       "(SURVEY F6), so 1 thread IS all the threads the "
-                                       "reference path can use; host has %d cores" %
+                             "sample": "the whole matrix (%d nnz) per step; sprs SpMV/SpMM are "
+                                       "single-threaded (SURVEY F6), so 1 thread IS all the "
+                                       "threads the reference path can use; host has %d cores" %
                                        (nnz, O.num_procs())},
             "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def pick_exchange_by_measurement(op, args, ctx, a, bounds, rank, world, n, dist, dev, x, mcast_cls):
-    """`--exchange auto` at 6+ GPUs: the exchange measured in round 1 (fused peer stores) runs
-    against the NVSwitch-multicast exchanges ON THIS BOX, untimed, before the benchmark proper:
-    each candidate must construct on every rank, reproduce the validated operator's y (checked
-    from a NaN-filled buffer after one step, so a row that has not landed by the barrier
-    fails it) and beat it by more than 2 % over 5 device-timed steps (max over ranks) to be
-    selected.  A candidate that is unavailable, raises or disagrees is dropped; the report of
-    what was tried goes into the JSON line (config.exchange_trial).  SPRS_B200_AUTO_TRIAL=0
-    switches the trial off (the round-1 choice is then used as is)."""
-    import torch
-
-    def agree(flag):
-        t = torch.tensor([1.0 if flag else 0.0], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        return bool(t.item() > 0.5)
-
-    def timed(o, steps=5):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        for _ in range(2):
-            o.step(x)
-        torch.cuda.synchronize()
-        dist.barrier()
-        e0.record()
-        for _ in range(steps):
-            o.step(x)
-        e1.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    report = {}
-    base_name = args.exchange
-    base_ms = timed(op)
-    report[base_name] = round(base_ms, 4)
-    y_ref = op.y.clone()
-    scale = float(y_ref.abs().max().item()) + 1e-300
-    best_op, best_name, best_ms = op, base_name, base_ms
-    supported = False
-    try:
-        import torch.distributed._symmetric_memory as symm
-        from torch._C._autograd import DeviceType
-        supported = bool(symm._SymmetricMemory.has_multicast_support(DeviceType.CUDA, dev.index))
-    except Exception as e:
-        report["probe"] = "no symmetric-memory multicast probe: %r" % (e,)
-    if not agree(supported):
-        report.setdefault("probe", "NVSwitch multicast not supported on every rank")
-        return op, base_name, report
-    for cand in ("mcast-push", "mcast"):
-        c_op, err = None, None
-        try:
-            c_op = mcast_cls(ctx, a.mirror, bounds, rank, world, n, dist, dev,
-                             mode=cand.partition("-")[2] or "fused", barrier=args.barrier)
-        except Exception as e:
-            err = repr(e)
-        if not agree(c_op is not None):
-            report[cand] = "unavailable: %s" % (err or "failed on another rank")
-            if c_op is not None:
-                c_op.close()
-            continue
-        ok, ms = False, None
-        try:
-            c_op.y.fill_(float("nan"))
-            torch.cuda.synchronize()
-            dist.barrier()
-            got = c_op.step(x)
-            torch.cuda.synchronize()
-            ok = bool(((got - y_ref).abs() <= 1e-9 * scale).all().item())
-            dist.barrier()
-        except Exception as e:
-            err = repr(e)
-        if not agree(ok):
-            report[cand] = "rejected: result differs from the validated exchange" if err is None \
-                else "rejected: %s" % err
-            c_op.close()
-            continue
-        ms = timed(c_op)
-        report[cand] = round(ms, 4)
-        if ms < 0.98 * best_ms:
-            if best_op is not op:
-                best_op.close()
-            best_op, best_name, best_ms = c_op, cand, ms
-        else:
-            c_op.close()
-    if best_op is not op and hasattr(op, "close"):
-        op.close()
-    report["selected"] = best_name
-    return best_op, best_name, report
+# ---- product arm -----------------------------------------------------------------------
+EXCHANGE_TEXT = {
+    "fused": "all-gather of y fused into the SpMV kernel: every finished row is stored into %s "
+             "by the kernel itself + device flag barrier in peer memory",
+    "push": "SpMV, then one put kernel copying this rank's y slice into %s (coalesced 16-byte "
+            "stores over NVLink) + device flag barrier in peer memory",
+    "nccl": "NCCL all_gather(y), unequal slices (torch.distributed)",
+}
 
 
 def main():
@@ -323,19 +321,17 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "overlap", "fused", "push", "stream", "chunked", "mcast", "mcast-push", "mcast-stream", "mcast-chunked", "nccl"],
-                    help="N>1 all-gather of y: 'overlap' = row block cut into chunks, each "
-                         "chunk's y slice pushed to the peers by DMA copies on a second stream "
-                         "while the next chunk computes; 'fused' = the SpMV kernel itself stores "
-                         "every finished row into the peers' buffers; 'nccl' = one NCCL "
-                         "all_gather after the kernel; 'auto' = push below 6 GPUs, fused from 6 "
-                         "up, where an untimed trial may replace it by a multicast exchange that "
-                         "reproduces its result and is faster (pick_exchange_by_measurement)")
-    ap.add_argument("--chunks", type=int, default=4)
-    ap.add_argument("--barrier", default="nccl", choices=["nccl", "symm"],
-                    help="mcast modes: barrier after the stores -- 1-element NCCL all_reduce, or "
-                         "the signal-pad barrier of the symmetric-memory handle")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "push", "nccl"],
+                    help="N>1 all-gather of y: 'push' = put kernel after the SpMV, 'fused' = stores "
+                         "from the SpMV kernel itself (both through the library's communicator: "
+                         "NVSwitch multicast address of y when available, else peer mappings), "
+                         "'nccl' = one NCCL all_gather; 'auto' = the measured default (DESIGN.md 5)")
+    ap.add_argument("--no-multicast", action="store_true",
+                    help="keep the symmetric buffers on CUDA IPC peer mappings")
+    ap.add_argument("--gen-to", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.gen_to:
+        return generate_to_dir(args.workload, args.gen_to)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -343,9 +339,8 @@ def main():
     import torch.distributed as dist
     import sprs_b200 as sp
     from sprs_b200 import generate as G
-    from sprs_b200.dist import (FusedAllGatherSpMV, OverlappedAllGatherSpMV, PushAllGatherSpMV,
-                                StreamAllGatherSpMV, ChunkedPushAllGatherSpMV, McastAllGatherSpMV,
-                                RowPartitionedSpMV, fit_row_cost, nnz_balanced_bounds)
+    from sprs_b200.dist import (Comm, CommHostSpMV, CommSpMV, RowPartitionedSpMV, fit_row_cost,
+                                nnz_balanced_bounds, rebalance_bounds)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -355,7 +350,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)  # plumbing: id broadcast, timing reductions
     ctx = sp.Context.default(local)
     kind, n, npr, gen = WORKLOADS[args.workload]
     if kind != "spmv":
@@ -363,11 +358,22 @@ def main():
     peaks, peak_src = measured_peaks()
     hbm_peak = float(peaks["hbm_gbs"])
 
+    def allmax(vals):
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
     # ---- inputs, generated in HBM (every rank builds the same matrix, keeps its block)
     t_gen = time.time()
     full = G.make_matrix(ctx, gen, n, npr, SEEDS[args.workload])
     nnz = full.nnz
     x = G.normal_vector(ctx, n)
+    comm = None
+    if world > 1:
+        ids = [Comm.unique_id(ctx) if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = Comm(ctx, ids[0], rank, world)
     bounds = nnz_balanced_bounds(full.indptr, world)
     r0, r1 = bounds[rank], bounds[rank + 1]
     row_cost = 0.0
@@ -384,10 +390,7 @@ def main():
             G.spmv(ctx, a, x, yt)
         ce1.record()
         torch.cuda.synchronize()
-        mine = torch.tensor([a.nnz, r1 - r0, ce0.elapsed_time(ce1) / 3e3], device=dev,
-                            dtype=torch.float64)
-        allm = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(allm, mine)
+        allm = comm.allgather_f64([a.nnz, r1 - r0, ce0.elapsed_time(ce1) / 3e3])
         row_cost = fit_row_cost([m.tolist() for m in allm])
         del a, yt
         bounds = nnz_balanced_bounds(full.indptr, world, row_cost=row_cost)
@@ -402,41 +405,24 @@ def main():
         except Exception as e:  # a reported baseline must never take the GPU number down
             cpu_base = {"error": repr(e)}
     t_gen = time.time() - t_gen
-    auto_exchange = args.exchange == "auto"
     if args.exchange == "auto":
-        # measured (profiles/r1_multi_gpu.md): the own put kernel is the fastest exchange at
-        # 2 and 4 GPUs (2.27 / 1.33 ms vs nccl 2.39 / 1.36, fused 2.43 / 1.38); its cost grows
-        # with the bytes pushed (~0.14 ms at 40 MB, ~0.22 ms at 60 MB), while at 8 GPUs the
-        # fused kernel measured 0.82 ms against 0.61 ms of pure compute -> fused from 6 GPUs up
-        args.exchange = "fused" if world >= 6 else "push"
-    fused = world > 1 and args.exchange in ("fused", "overlap", "push", "stream", "chunked",
-                                            "mcast", "mcast-push", "mcast-stream", "mcast-chunked")
+        # measured at 2/4/8 GPUs (profiles/r2_scale_probe.md): see DESIGN.md section 5
+        args.exchange = "push"
+    use_comm = world > 1 and args.exchange in ("fused", "push")
 
     def make_op(a_blk, bnds):
-        if world > 1 and args.exchange == "overlap":
-            o = OverlappedAllGatherSpMV(ctx, a_blk, bnds, rank, world, n, dist, dev,
-                                        chunks=args.chunks, row_cost=row_cost)
-        elif fused and args.exchange.startswith("mcast"):
-            o = McastAllGatherSpMV(ctx, a_blk.mirror, bnds, rank, world, n, dist, dev,
-                                   mode=args.exchange.partition("-")[2] or "fused",
-                                   barrier=args.barrier)
-        elif fused:
-            cls = {"push": PushAllGatherSpMV, "stream": StreamAllGatherSpMV,
-                   "chunked": ChunkedPushAllGatherSpMV}.get(
-                args.exchange, FusedAllGatherSpMV)
-            o = cls(ctx, a_blk.mirror, bnds, rank, world, n, dist, dev)
-        else:
-            yb = torch.zeros(n, device=dev, dtype=torch.float64)
-            o = RowPartitionedSpMV(bnds, rank, world, yb,
-                                   lambda xv, ys: G.spmv(ctx, a_blk, xv, ys),
-                                   dist=dist if world > 1 else None)
-        return o
+        if use_comm:
+            return CommSpMV(comm, a_blk.mirror, bnds, n, dev, exchange=args.exchange,
+                            multicast=not args.no_multicast)
+        yb = torch.zeros(n, device=dev, dtype=torch.float64)
+        return RowPartitionedSpMV(bnds, rank, world, yb,
+                                  lambda xv, ys: G.spmv(ctx, a_blk, xv, ys),
+                                  dist=dist if world > 1 else None)
 
     op = make_op(a, bounds)
     rebalanced = 0
     if world > 1:
-        # measured re-balancing with the REAL operator (the fused kernel's remote stores
-        # change the per-row cost): up to two rounds of equal-time re-cuts
+        # measured re-balancing with the REAL operator: up to two rounds of equal-time re-cuts
         for _ in range(2):
             for _ in range(2):
                 op.step(x)
@@ -451,13 +437,9 @@ def main():
                 op.exchange()
                 torch.cuda.synchronize()
                 tsum += ce0.elapsed_time(ce1)
-            mine = torch.tensor([tsum / 4], device=dev, dtype=torch.float64)
-            allt = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(allt, mine)
-            times = [float(t.item()) for t in allt]
+            times = [float(v[0]) for v in comm.allgather_f64([tsum / 4])]
             if max(times) <= 1.03 * (sum(times) / world):
                 break
-            from sprs_b200.dist import rebalance_bounds
             nb = rebalance_bounds(full.indptr, bounds, times, row_cost=row_cost)
             if nb == bounds:
                 break
@@ -470,22 +452,52 @@ def main():
             a = full.slice_rows(r0, r1)
             op = make_op(a, bounds)
             rebalanced += 1
+    multicast = bool(getattr(op, "multicast", False))
+
+    # ---- parity first, untimed: this rank's WHOLE y against the CPU oracle (every rank)
+    op.y.fill_(float("nan"))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    op.step(x)
+    torch.cuda.synchronize()
+    if comm is not None:
+        comm.check()
+    try:
+        p_ok, p_rows, p_worst = parity_vs_oracle(full, x, op.y)
+        p_err = None
+    except Exception as e:
+        p_ok, p_rows, p_worst, p_err = False, 0, float("inf"), repr(e)
+    p_ok_all, p_worst_all = allmax([0.0 if p_ok else 1.0, p_worst if np.isfinite(p_worst) else 1e300])
+    parity = {"ok": p_ok_all == 0.0, "rows_checked_per_rank": p_rows,
+              "max_error_over_gate": p_worst_all,
+              "gate": "|got - oracle| <= 1e-6 * sum|terms| per row; heaviest 100 rows + 10000 "
+                      "random rows of the whole (all-gathered) y, checked on every rank"}
+    if p_err:
+        parity["error"] = p_err
+    # the ceiling of this matrix (N=1): the same streams and gathers without the row logic
+    ceiling = None
+    if world == 1:
+        try:
+            import ctypes as C
+            ms_c, cov = C.c_double(), C.c_uint64()
+            ctx.check(ctx.lib.sprs_b200_diag_gather_ceiling(ctx.h, full.mirror.h,
+                                                            C.c_void_p(x.data_ptr()), 5,
+                                                            C.byref(ms_c), C.byref(cov)))
+            ceiling = {"ms": ms_c.value, "gnnz_s": cov.value / ms_c.value / 1e6,
+                       "frac_of_hbm": (12.0 * cov.value + 8.0 * n) / ms_c.value / 1e6 / hbm_peak,
+                       "kernel": "sprs_b200_diag_gather_ceiling (csrc/diag.cu): same index/value "
+                                 "stream and x gathers as the SpMV, one sum per lane, no rows"}
+        except Exception as e:
+            ceiling = {"error": repr(e)}
+    if world > 1:
         del full
         torch.cuda.empty_cache()
-    exchange_trial = None
-    trial_min = int(os.environ.get("SPRS_B200_AUTO_TRIAL_MIN_GPUS", "6"))
-    if auto_exchange and world >= trial_min and os.environ.get("SPRS_B200_AUTO_TRIAL", "1") != "0":
-        op, args.exchange, exchange_trial = pick_exchange_by_measurement(
-            op, args, ctx, a, bounds, rank, world, n, dist, dev, x, McastAllGatherSpMV)
     y = op.y
-    y_views = [y[bounds[g]:bounds[g + 1]] for g in range(world)]
     local_nnz = a.nnz
 
-    def step():
-        op.step(x)
-
     for _ in range(max(args.warmup, 3)):
-        step()
+        op.step(x)
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     use_sampler = rank == 0 and not os.environ.get("SPRS_BENCH_NO_SAMPLER")
@@ -503,15 +515,12 @@ def main():
     tw0 = time.time()
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record()
-    cpu_t = []
     for i in range(args.steps):
-        cpu_t.append(time.perf_counter())
         evs[i][0].record()
         op.compute(x)
         evs[i][1].record()
         op.exchange()
         evs[i][2].record()
-    cpu_t.append(time.perf_counter())
     e_stop.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -520,35 +529,43 @@ def main():
     tw1 = time.time()
     clocks = sampler.stop(tw0, tw1) if use_sampler else None
     launches = ctx.launches - launches0
+    if comm is not None:
+        comm.check()
     total_ms = e_start.elapsed_time(e_stop)
     kern_ms = [evs[i][0].elapsed_time(evs[i][1]) for i in range(args.steps)]
     coll_ms = [evs[i][1].elapsed_time(evs[i][2]) for i in range(args.steps)]
-    if os.environ.get("SPRS_BENCH_DEBUG"):
-        gaps = [evs[i][2].elapsed_time(evs[i + 1][0]) for i in range(args.steps - 1)]
-        print("[rank %d] kern %s\n[rank %d] coll %s\n[rank %d] gap  %s\n[rank %d] cpu_enqueue_ms %s" % (
-            rank, ["%.2f" % v for v in kern_ms], rank, ["%.2f" % v for v in coll_ms], rank,
-            ["%.2f" % v for v in gaps], rank,
-            ["%.2f" % ((cpu_t[i + 1] - cpu_t[i]) * 1e3) for i in range(args.steps)]),
-            file=sys.stderr, flush=True)
-    t = torch.tensor([total_ms, statistics.mean(kern_ms), statistics.mean(coll_ms)],
-                     device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, kern_ms_avg, coll_ms_avg = t.tolist()
+    my_kern = statistics.mean(kern_ms)
+    total_ms, kern_ms_avg, coll_ms_avg = allmax([total_ms, my_kern, statistics.mean(coll_ms)])
+    per_rank_kern = ([float(v[0]) for v in comm.allgather_f64([my_kern])] if comm is not None
+                     else [my_kern])
     ms_per_step = total_ms / args.steps
 
-    # ---- e2e: the reference-facing call with HOST buffers: `&A * &x` through the C ABI,
-    # x H2D from pinned memory and y D2H inside the timed region, every step.
+    # ---- e2e: the reference-facing call with HOST buffers, every step: x H2D from pinned
+    # memory and y D2H inside the timed region.  N=1: `&A * &x` through sprs_b200_mul_mat_vec.
+    # N>1: sprs_b200_mul_mat_vec_rowpart -- every rank moves only ITS slices of x and y.
     import ctypes as C
     rows_local = r1 - r0
-    hx = torch.empty(n, dtype=torch.float64).pin_memory()
-    hx.copy_(x)
-    hy = torch.empty(max(rows_local, 1), dtype=torch.float64).pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
+    if world == 1:
+        hx = torch.empty(n, dtype=torch.float64).pin_memory()
+        hx.copy_(x)
+        hy = torch.empty(max(rows_local, 1), dtype=torch.float64).pin_memory()
 
-    def e2e_step():
-        ctx.check(ctx.lib.sprs_b200_mul_mat_vec(ctx.h, a.mirror.h, C.c_void_p(hx.data_ptr()), n,
-                                                C.c_void_p(hy.data_ptr()), rows_local))
+        def e2e_step():
+            ctx.check(ctx.lib.sprs_b200_mul_mat_vec(ctx.h, a.mirror.h, C.c_void_p(hx.data_ptr()), n,
+                                                    C.c_void_p(hy.data_ptr()), rows_local))
+        e2e_api = "sprs_b200_mul_mat_vec (host x, y; A resident as a device mirror)"
+        hop = None
+    else:
+        hx = torch.empty(max(rows_local, 1), dtype=torch.float64).pin_memory()
+        hx[:rows_local].copy_(x[r0:r1])
+        hy = torch.empty(max(rows_local, 1), dtype=torch.float64).pin_memory()
+        hop = CommHostSpMV(comm, a.mirror, bounds, n, multicast=not args.no_multicast)
+
+        def e2e_step():
+            hop.step(hx.data_ptr(), hy.data_ptr())
+        e2e_api = ("sprs_b200_mul_mat_vec_rowpart (each rank uploads its own slice of x, x is "
+                   "all-gathered over NVLink, each rank downloads its own slice of y)")
     for _ in range(2):
         e2e_step()
     torch.cuda.synchronize()
@@ -559,34 +576,50 @@ def main():
         e2e_step()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    te = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te.item())
-    # parity spot-check of the e2e result against the device-resident result
-    ref_y = y_views[rank]
+    (e2e_ms,) = allmax([e2e_ms])
+    ref_y = y[r0:r1]
     got_y = hy[:rows_local].to(dev)
-    # same kernel, but the chunked exchange tiles sub-blocks separately: compare to rounding
     ok = bool(((got_y - ref_y).abs() <= 1e-9 * (ref_y.abs().max() + 1e-300)).all())
+    (e2e_bad,) = allmax([0.0 if ok else 1.0])
+    if hop is not None:
+        hop.close()
 
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra and args.workload == "spmv_rmat_10m":
-        try:
-            del a, full
+        del a, full, op, y
+        torch.cuda.empty_cache()
+        for name, fn in (("spmv_rand_1m", bench_small_spmv), ("spmm_rand_1m_k64", bench_other.extra_spmm),
+                         ("spgemm_rmat_500k", bench_other.extra_spgemm)):
+            try:
+                extra[name] = fn(ctx, G, hbm_peak, dev)
+            except Exception as e:
+                extra[name] = {"error": repr(e)}
             torch.cuda.empty_cache()
-            extra = bench_small_spmv(ctx, G, hbm_peak, dev)
-        except Exception as e:
-            extra = {"error": repr(e)}
 
     if rank == 0:
         flops = 2.0 * nnz
         alg_bytes = 12.0 * nnz + 8.0 * n
         gflops = flops / (ms_per_step * 1e-3) / 1e9
-        # roofline of the dominant kernel (spmv_tile_kernel; the carry fix-up kernel rides in
-        # the same event pair and is < 0.5 % of it): algorithmic bytes this rank's launch
-        # moves / its mean duration.  Rank 0's block; blocks are nnz-balanced.
+        # roofline of the dominant kernel (spmv_pipe_kernel; the carry fix-up kernel -- and at
+        # N > 1 the put kernel of the 'push' exchange -- ride in the same event pair):
+        # algorithmic bytes this rank's launch moves / its mean duration.
         local_bytes = 12.0 * local_nnz + 8.0 * rows_local
-        achieved = local_bytes / (kern_ms_avg * 1e-3) / 1e9
+        achieved = local_bytes / (per_rank_kern[0] * 1e-3) / 1e9
+        target = ("the NVSwitch multicast address of y (one store per row, replicated by the switch)"
+                  if multicast else "every peer's y (CUDA IPC / VMM peer mappings)")
+        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak,
+                "traffic": bench_other.ncu_traffic(args.workload, world),
+                "traffic_source": bench_other.ncu_traffic(args.workload, world, source=True),
+                "kernel": "spmv_pipe_kernel (+ spmv_fixup_kernel)",
+                "kernel_ms": per_rank_kern[0], "kernel_ms_per_rank": per_rank_kern,
+                "peak_source": peak_src,
+                "algorithmic_bytes": "12*nnz + 8*rows of this rank's block per launch",
+                "variant": os.environ.get("SPRS_B200_SPMV_VARIANT", "default 8,2 (nnz per lane per tile, CTAs/SM)")}
+        if ceiling is not None:
+            roof["gather_ceiling"] = ceiling
+            if "frac_of_hbm" in ceiling:
+                roof["frac_of_gather_ceiling"] = (achieved / hbm_peak) / ceiling["frac_of_hbm"]
         line = {
             "metric": "csr_spmv_f64_gflops", "value": gflops, "unit": "GFLOP/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -597,57 +630,24 @@ def main():
                        "partition": "contiguous row blocks balanced on nnz + %.2f*rows "
                                     "(row cost fitted from per-rank timings), then %d measured "
                                     "equal-time re-cut(s)" % (row_cost, rebalanced),
-                       "collective": ("none" if world == 1 else {
-                           "overlap": "all-gather of y overlapped with compute: %d row chunks, "
-                                      "each slice pushed to the peers by P2P DMA copies on a "
-                                      "second stream + 1-element NCCL all_reduce barrier "
-                                      "(roofline.kernel_ms then covers the whole step)"
-                                      % args.chunks,
-                           "fused": "all-gather of y fused into the SpMV kernel (peer stores "
-                                    "over NVLink) + 1-element NCCL all_reduce barrier",
-                           "push": "SpMV, then one push kernel storing this rank's y slice into "
-                                   "every peer buffer (coalesced NVLink stores) + 1-element "
-                                   "NCCL all_reduce barrier",
-                           "stream": "SpMV publishing its progress + concurrent put kernel "
-                                     "copying finished row chunks into the peer buffers "
-                                     "(pipelined all-gather over NVLink) + 1-element NCCL "
-                                     "all_reduce barrier",
-                           "chunked": "SpMV launched in 4 chunks of decreasing size; behind each "
-                                      "chunk's event a side stream pushes the rows it completed "
-                                      "into the peer buffers (own put kernel over NVLink) + "
-                                      "1-element NCCL all_reduce barrier",
-                           "mcast": "all-gather of y fused into the SpMV kernel through the "
-                                    "NVSwitch multicast address of y (one store per finished row, "
-                                    "replicated by the switch) + barrier (%s)" % args.barrier,
-                           "mcast-push": "SpMV, then one push kernel storing this rank's y slice "
-                                         "to the NVSwitch multicast address of y + barrier (%s)"
-                                         % args.barrier,
-                           "mcast-stream": "SpMV publishing its progress + concurrent put kernel "
-                                           "storing finished row chunks to the NVSwitch multicast "
-                                           "address of y + barrier (%s)" % args.barrier,
-                           "mcast-chunked": "SpMV in 4 chunks of decreasing size; behind each "
-                                            "chunk's event a side stream stores its rows to the "
-                                            "NVSwitch multicast address of y + barrier (%s)"
-                                            % args.barrier,
-                           "nccl": "NCCL all_gather(y), unequal slices"}[args.exchange]),
-                       "exchange_trial": exchange_trial,
+                       "collective": ("none" if world == 1 else
+                                      (EXCHANGE_TEXT[args.exchange] % target
+                                       if args.exchange != "nccl" else EXCHANGE_TEXT["nccl"])),
+                       "communicator": (None if comm is None else
+                                        "sprs_b200_comm (C ABI: shm rendezvous, %s symmetric buffers, "
+                                        "device flag barrier); torch.distributed only broadcasts the id"
+                                        % ("VMM + NVSwitch multicast" if multicast else "CUDA IPC")),
                        "l2_policy": "inputs (%.1f GB) exceed L2 (126 MB); no flush needed" %
                                     (alg_bytes / 1e9),
                        "gen_seconds": round(t_gen, 1)},
             "achieved_hbm_frac": (alg_bytes / (ms_per_step * 1e-3) / 1e9) / (hbm_peak * world),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak,
-                         "traffic": bench_other.ncu_traffic(args.workload, world),
-                         "traffic_source": bench_other.ncu_traffic(args.workload, world, source=True),
-                         "kernel": "spmv_warp_kernel (+ spmv_fixup_kernel)",
-                         "kernel_ms": kern_ms_avg, "peak_source": peak_src,
-                         "algorithmic_bytes": "12*nnz + 8*rows of this rank's block per launch",
-                         "variant": os.environ.get("SPRS_B200_SPMV_VARIANT", "default 384,1,8,3 (wt,stages,warps,ctas/SM)")},
+            "roofline": roof,
+            "parity_vs_oracle": parity,
             "collective_ms": coll_ms_avg,
             "e2e": {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s",
-                    "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * n * world,
-                    "d2h_bytes_per_step": 8 * n, "api": "sprs_b200_mul_mat_vec (host x, y; "
-                    "A resident as a device mirror)", "matches_device_result": ok},
+                    "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * n,
+                    "d2h_bytes_per_step": 8 * n, "api": e2e_api,
+                    "matches_device_result": e2e_bad == 0.0},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if cpu_base:
@@ -655,15 +655,17 @@ def main():
         if extra:
             line["extra"] = extra
         print(json.dumps(line))
-    if fused:
-        op.close()
     if world > 1:
+        if hasattr(op, "close"):
+            op.close()
+        comm.close()
         dist.destroy_process_group()
 
 
 def bench_small_spmv(ctx, G, hbm_peak, dev):
-    """BASELINE config 2 (1M x 1M sprs-rand, 32 nnz/row), reported as an extra line item.
-    392 MB of inputs > L2, so no flush is needed between iterations."""
+    """BASELINE config 2 (1M x 1M sprs-rand, 32 nnz/row), reported as an extra line item with
+    its own gather ceiling.  392 MB of inputs > L2, so no flush is needed between iterations."""
+    import ctypes as C
     import torch
     n = 1_000_000
     a = G.rand_csr(ctx, n, n, 32, seed=0x5EED0002)
@@ -681,8 +683,17 @@ def bench_small_spmv(ctx, G, hbm_peak, dev):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / k
     by = 12.0 * a.nnz + 8.0 * n
-    return {"spmv_rand_1m": {"nnz": a.nnz, "ms": ms, "gflops": 2.0 * a.nnz / ms / 1e6,
-                             "achieved_gbs": by / ms / 1e6, "frac": by / ms / 1e6 / hbm_peak}}
+    ok, rows, worst = parity_vs_oracle(a, x, y, n_random=20000, n_heavy=10)
+    out = {"nnz": a.nnz, "ms": ms, "gflops": 2.0 * a.nnz / ms / 1e6, "achieved_gbs": by / ms / 1e6,
+           "frac": by / ms / 1e6 / hbm_peak,
+           "parity_vs_oracle": {"ok": ok, "rows_checked": rows, "max_error_over_gate": worst}}
+    ms_c, cov = C.c_double(), C.c_uint64()
+    ctx.check(ctx.lib.sprs_b200_diag_gather_ceiling(ctx.h, a.mirror.h, C.c_void_p(x.data_ptr()), 20,
+                                                    C.byref(ms_c), C.byref(cov)))
+    cf = (12.0 * cov.value + 8.0 * n) / ms_c.value / 1e6 / hbm_peak
+    out["gather_ceiling"] = {"ms": ms_c.value, "frac_of_hbm": cf}
+    out["frac_of_gather_ceiling"] = out["frac"] / cf
+    return out
 
 
 if __name__ == "__main__":

@@ -115,8 +115,7 @@ def run(args, ctx, kind, n, npr, gen, seed):
                            "l2_policy": "inputs (1.4 GB) exceed L2; no flush needed"},
                 "roofline": {"bound": "hbm", "achieved": comp_bytes / ms / 1e6, "peak": hbm,
                              "unit": "GB/s", "frac": comp_bytes / ms / 1e6 / hbm,
-                             "traffic": (None if os.environ.get("SPRS_B200_SPMM_PANEL")
-                                         else ncu_traffic(args.workload, 1)),
+                             "traffic": ncu_traffic(args.workload, 1),
                              "kernel": "spmm_rowmaj_kernel", "peak_source": peak_src,
                              "algorithmic_bytes": "compulsory 12*nnz + 8*k*(cols+rows)"},
                 "e2e": {"value": flops / e2e_ms / 1e6, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
@@ -174,3 +173,95 @@ def run(args, ctx, kind, n, npr, gen, seed):
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = _cpu_spgemm(A, Bm, 20_000)
     print(json.dumps(line))
+
+
+def extra_spmm(ctx, G, hbm, dev):
+    """BASELINE config 3 as a compact entry of the default line's "extra" (the driver only runs
+    the default command): device-timed ms, GFLOP/s, fraction of the compulsory roofline, and a
+    bit-exactness check of sampled C rows against the oracle (csr_mulacc_dense_rowmaj)."""
+    import torch
+    from oracle import oracle as O
+    n, k = 1_000_000, 64
+    a = G.rand_csr(ctx, n, n, 32, seed=0x5EED0002)
+    b = torch.randn(n, k, device=dev, dtype=torch.float64)
+    c = torch.empty(n, k, device=dev, dtype=torch.float64)
+    for _ in range(3):
+        G.spmm_rowmaj(ctx, a, b, c)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 10
+    e0.record()
+    for _ in range(steps):
+        G.spmm_rowmaj(ctx, a, b, c)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    comp = 12.0 * a.nnz + 8.0 * k * (n + n)
+    # parity: the first 2000 rows, bit-exact (sequential unfused sums, prod.rs:189-214)
+    r1 = 2000
+    e = int(a.indptr[r1].item())
+    hip = a.indptr[:r1 + 1].cpu().numpy().view(np.uint32)
+    hind = a.indices[:e].cpu().numpy().view(np.uint32)
+    hdat = a.data[:e].cpu().numpy()
+    ref = np.zeros((r1, k))
+    O.csr_mulacc_dense_rowmaj(hip, hind, hdat, b.cpu().numpy(), ref)
+    return {"nnz": a.nnz, "k": k, "ms": ms, "gflops": 2.0 * a.nnz * k / ms / 1e6,
+            "frac_of_compulsory_roofline": comp / ms / 1e6 / hbm,
+            "traffic": ncu_traffic("spmm_rand_1m_k64", 1),
+            "parity_vs_oracle": {"bit_exact": bool(np.array_equal(c[:r1].cpu().numpy(), ref)),
+                                 "rows_checked": r1}}
+
+
+def extra_spgemm(ctx, G, hbm, dev):
+    """BASELINE config 4 as a compact entry of "extra": host-timed symbolic + numeric (both
+    synchronous C-ABI calls, C left on the device), and indptr / indices of a row block of the
+    product checked BIT-EXACT against the oracle (smmp.rs:81-189)."""
+    import torch
+    from oracle import oracle as O
+    n = 500_000
+    A = G.rmat_csr(ctx, n, 16, seed=0x5EED0004)
+    Bm = G.rmat_csr(ctx, n, 16, seed=0x5EED0004 ^ 0x1000)
+    lib = ctx.lib
+
+    def once(keep=False):
+        plan, nnz_c, cm = C.c_void_p(), C.c_uint64(), C.c_void_p()
+        ctx.check(lib.sprs_b200_spgemm_symbolic(ctx.h, A.mirror.h, Bm.mirror.h, C.byref(plan),
+                                                C.byref(nnz_c)))
+        ctx.check(lib.sprs_b200_spgemm_numeric_dev(ctx.h, plan, C.byref(cm)))
+        nprod = lib.sprs_b200_spgemm_nprod(plan) if keep else 0
+        lib.sprs_b200_spgemm_free(plan)
+        if keep:
+            return nnz_c.value, nprod, cm
+        lib.sprs_b200_csmat_free(cm)
+        return nnz_c.value, nprod, None
+    nnz_c, nprod, cm = once(keep=True)
+    # parity on rows [r0, r1) of C against the oracle's product of that row block of A with B
+    r0, r1 = 1000, 1400
+    d_ip, d_ind, d_dat, ipb = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int()
+    ctx.check(lib.sprs_b200_csmat_device_arrays(cm, C.byref(d_ip), C.byref(ipb), C.byref(d_ind),
+                                                C.byref(d_dat)))
+    cip = torch.as_tensor(G._DevArray(d_ip.value, n + 1, "<i4" if ipb.value == 4 else "<i8"),
+                          device=dev).to(torch.int64)
+    if ipb.value == 4:
+        cip &= 0xFFFFFFFF
+    s, e = int(cip[r0].item()), int(cip[r1].item())
+    got_ip = (cip[r0:r1 + 1] - s).cpu().numpy()
+    got_ind = torch.as_tensor(G._DevArray(d_ind.value + 4 * s, e - s, "<i4"),
+                              device=dev).cpu().numpy().view(np.uint32)
+    blk = A.slice_rows(r0, r1)
+    oip, oind, _ = O.mul_csr_csr((r1 - r0, n), blk.to_host(), (n, n), Bm.to_host(), threads=0)
+    parity = {"rows_checked": r1 - r0, "nnz_checked": int(e - s),
+              "indptr_bit_exact": bool(np.array_equal(got_ip, np.asarray(oip, dtype=np.int64))),
+              "indices_bit_exact": bool(np.array_equal(got_ind, np.asarray(oind, dtype=np.uint32)))}
+    lib.sprs_b200_csmat_free(cm)
+    del blk
+    once()
+    t0 = time.perf_counter()
+    steps = 3
+    for _ in range(steps):
+        once()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    alg = 12.0 * (A.nnz + nprod + nnz_c) + 8.0 * (n + 1)
+    return {"n_prod": nprod, "nnzC": nnz_c, "ms": ms, "gflops": 2.0 * nprod / ms / 1e6,
+            "frac_of_roofline": alg / ms / 1e6 / hbm, "parity_vs_oracle": parity,
+            "timing": "host clock around symbolic + numeric (synchronous calls), C left on the device"}

@@ -365,6 +365,15 @@ int sprs_b200_bicgstab_get(const sprs_b200_bicgstab* s, int which, double* out, 
 /* borrowed device pointer to vector `which` (valid until bicgstab_free) */
 int sprs_b200_bicgstab_get_dev(const sprs_b200_bicgstab* s, int which, const double** d_out);
 
+/* ---- measurement aid (bench.py roofline.gather_ceiling; not a product path): the SpMV's
+ * memory behaviour on THIS matrix with the row logic removed -- the same (index, value) stream
+ * and the same x gathers, one plain sum per lane, no rows, no y (csrc/diag.cu).  Any SpMV that
+ * gathers x through L1/L2 does at least this work: nnz_covered / ms_per_pass is the ceiling
+ * the product kernel is held against.  Blocking; `iters` timed passes after two warm-ups.   */
+int sprs_b200_diag_gather_ceiling(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat,
+                                  const double* d_x, int iters, double* ms_per_pass,
+                                  uint64_t* nnz_covered);
+
 /* ---- synthetic inputs, generated in HBM (sprs-rand/src/lib.rs:24-81
  * gives the uniform distribution; R-MAT is this repo's definition).  Each writes
  * `count` 64-bit keys (row<<32 | col) for candidate edges [first, first+count);

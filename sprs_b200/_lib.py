@@ -102,6 +102,8 @@ PROTOTYPES = {
     "sprs_b200_bicgstab_stats": (_int, [_vp, C.POINTER(_u64), C.POINTER(C.c_double)]),
     "sprs_b200_bicgstab_get": (_int, [_vp, _int, _dp, _u64]),
     "sprs_b200_bicgstab_get_dev": (_int, [_vp, _int, C.POINTER(_vp)]),
+    "sprs_b200_diag_gather_ceiling": (_int, [_vp, _vp, _dp, _int, C.POINTER(C.c_double),
+                                             C.POINTER(_u64)]),
     "sprs_b200_gen_rmat_keys": (_int, [_vp, _u64, _int, _u64, _u64, C.c_double, C.c_double,
                                        C.c_double, _u64, _u64, _vp, _vp]),
     "sprs_b200_gen_uniform_keys": (_int, [_vp, _u64, _u64, _u64, _u64, _u64, _vp, _vp]),
@@ -111,7 +113,7 @@ PROTOTYPES = {
 }
 
 _NOT_EMULATED = ("sprs_b200_comm_", "sprs_b200_symm_", "sprs_b200_partition_rows",
-                 "sprs_b200_spmv_rowpart", "sprs_b200_mul_mat_vec_rowpart")
+                 "sprs_b200_spmv_rowpart", "sprs_b200_mul_mat_vec_rowpart", "sprs_b200_diag_")
 _lib = None
 
 

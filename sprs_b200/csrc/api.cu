@@ -11,8 +11,14 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace {
+
+__global__ void make_policies_kernel(uint64_t* out) {
+    out[0] = policy_evict_first();
+    out[1] = policy_evict_last();
+}
 
 thread_local std::string g_create_error;
 
@@ -219,6 +225,24 @@ int sprs_b200_ctx_create(int device, sprs_b200_ctx** out) {
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->l2_bytes = (size_t)prop.l2CacheSize;
+    {
+        uint64_t* d_pol = nullptr;
+        uint64_t h_pol[2] = {0, 0};
+        if ((e = cudaMalloc((void**)&d_pol, 16)) == cudaSuccess) {
+            make_policies_kernel<<<1, 1, 0, ctx->stream>>>(d_pol);
+            e = cudaMemcpyAsync(h_pol, d_pol, 16, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            cudaFree(d_pol);
+        }
+        if (e != cudaSuccess) {
+            g_create_error = std::string("ctx_create (cache policies): ") + cudaGetErrorString(e);
+            cudaStreamDestroy(ctx->stream);
+            delete ctx;
+            return SPRS_B200_ERR_CUDA;
+        }
+        ctx->pol_evict_first = h_pol[0];
+        ctx->pol_evict_last = h_pol[1];
+    }
     *out = ctx;
     return SPRS_B200_OK;
 }

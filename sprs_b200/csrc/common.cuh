@@ -21,6 +21,9 @@ struct sprs_b200_ctx {
     cudaStream_t stream = nullptr;  // private stream of the host-buffer entry points
     std::string last_error;
     uint64_t launches = 0;
+    // L2 cache-policy words (createpolicy results), produced once per ctx: kernels take them as
+    // parameters so that they live in uniform registers
+    uint64_t pol_evict_first = 0, pol_evict_last = 0;
     // pinned host staging + device scratch for the host-buffer entry points
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;

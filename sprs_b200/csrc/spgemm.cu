@@ -61,24 +61,14 @@ constexpr int S_SLOTS = 256;
 constexpr uint32_t SYM_M_SLOTS = 16384, NUM_M_SLOTS = 8192;
 constexpr uint64_t BITMAP_SMEM_MAX_COLS = 200ull * 1024 * 8;  // 200 KB of bits
 
-// Round-2 candidate tuning, opt-in until it has been timed on hardware (SPRS_B200_SPGEMM_V2=1;
-// profiles/r1_launches_spgemm_breakdown.txt and tools/spgemm_rmat_stats.py are the evidence
-// behind it).  What it changes, results unchanged:
-//   * routing: the hash bins shrink to the rows they are cheap for -- with a shared-memory
-//     bitmap the symbolic phase sends rows with n_prod > B.cols/256 to the bitmap kernel, and
-//     the numeric phase sends rows with nnz(C_i) > 16 * n_panels to the panel kernel (config 4:
-//     sym_med + num_med were 20 % of the time for 2 % of the products);
-//   * short A rows: groups of G warps share one B row (the CTA-per-row kernels otherwise keep
-//     nwarps - nnz(A_i) warps idle: half of config 4's large rows have <= 8 A non-zeros);
-//   * panel kernel: 1024 threads (32 warps of latency hiding instead of 8 at one CTA per SM),
-//     two chunks of every B row in flight per warp, panels nothing landed in are skipped.
-bool spgemm_v2() {
-    static const bool v = [] {
-        const char* e = getenv("SPRS_B200_SPGEMM_V2");
-        return e && atoi(e) != 0;
-    }();
-    return v;
-}
+// Routing and kernel shapes measured in round 2 (profiles/r2_spgemm_notes.md): the hash bins
+// serve only the rows they are cheap for -- with a shared-memory bitmap the symbolic phase sends
+// rows with n_prod > B.cols/256 to the bitmap kernel, the numeric phase rows with
+// nnz(C_i) > 16 * n_panels to the panel kernel; groups of G warps share one B row when the A row
+// is short (half of config 4's large rows have <= 8 A non-zeros); the CTA-per-row kernels run
+// 1024 threads and keep several 32-entry chunks of B in flight per warp: they are bound by the
+// L2 round trip of the B stream, not by the shared-memory atomics (launch list: 1.5 products per
+// clock per SM with one chunk in flight).
 
 // Warps that share one B row in the CTA-per-row kernels: the largest power of two G with
 // G * na <= nwarps (1 when grouping is off or the A row has at least nwarps/2 non-zeros).
@@ -220,40 +210,74 @@ __global__ void __launch_bounds__(NT)
 // SMEM_BM: the bitmap's address space is a template parameter, not a run-time pointer choice
 // (with the choice at run time the compiler has to emit generic ATOM.E.OR instead of ATOMS.OR
 // for the shared-memory bitmap; cuobjdump of the first version).
+constexpr int SYM_L_NT = 1024;  // one CTA per SM (the bitmap takes the shared memory)
 template <bool SMEM_BM>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(SYM_L_NT)
     sym_large_kernel(const uint32_t* __restrict__ a_ip, const uint32_t* __restrict__ a_idx,
                      const uint32_t* __restrict__ b_ip, const uint32_t* __restrict__ b_idx,
                      const uint32_t* __restrict__ list, uint32_t n_list, uint32_t words,
                      uint32_t* __restrict__ g_bitmaps /* used when !SMEM_BM */,
-                     uint32_t* __restrict__ cnt, int grouping) {
+                     uint32_t* __restrict__ cnt, int grouping, uint32_t* __restrict__ row_counter) {
+    constexpr int NTH = SYM_L_NT, NW = NTH / 32;
     extern __shared__ uint32_t dyn_u32[];
     uint32_t* bm = SMEM_BM ? dyn_u32 : g_bitmaps + (uint64_t)blockIdx.x * words;
     __shared__ uint32_t total;
+    __shared__ uint32_t next_li;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t li = blockIdx.x; li < n_list; li += gridDim.x) {
-        const uint32_t r = list[li];
-        for (uint32_t i = threadIdx.x; i < words; i += NT) bm[i] = 0;
-        if (threadIdx.x == 0) total = 0;
+    for (uint32_t i = threadIdx.x; i < words; i += NTH) bm[i] = 0;  // re-zeroed by the count pass
+    for (;;) {
+        // rows are handed out dynamically: work per row spans three orders of magnitude
+        if (threadIdx.x == 0) {
+            next_li = atomicAdd(row_counter, 1u);
+            total = 0;
+        }
         __syncthreads();
+        const uint32_t li = next_li;
+        if (li >= n_list) break;
+        const uint32_t r = list[li];
         const uint32_t a0 = a_ip[r], a1 = a_ip[r + 1];
-        const int G = warps_per_brow(a1 - a0, WARPS, grouping);
-        const int grp = warp / G, wg = warp % G, ngrp = WARPS / G;
-        for (uint32_t k = a0 + grp; k < a1; k += ngrp) {
+        const int G = warps_per_brow(a1 - a0, NW, grouping);
+        const int grp = warp / G, wg = warp % G, ngrp = NW / G;
+        // the row range of the NEXT A non-zero is fetched while the current B row streams
+        uint32_t k = a0 + grp, s = 0, e = 0;
+        if (k < a1) {
             const uint32_t br = a_idx[k];
-            for (uint32_t p = b_ip[br] + wg * 32 + lane, pe = b_ip[br + 1]; p < pe; p += 32 * G) {
-                const uint32_t c = b_idx[p];
-                atomicOr(&bm[c >> 5], 1u << (c & 31));
+            s = b_ip[br];
+            e = b_ip[br + 1];
+        }
+        while (k < a1) {
+            const uint32_t kn = k + ngrp;
+            uint32_t sn = 0, en = 0;
+            if (kn < a1) {
+                const uint32_t brn = a_idx[kn];
+                sn = b_ip[brn];
+                en = b_ip[brn + 1];
             }
+            for (uint32_t p = s + (uint32_t)wg * 128 + lane; p < e; p += 128u * G) {
+                uint32_t c[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) c[u] = (p + 32 * u < e) ? b_idx[p + 32 * u] : EMPTY;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (c[u] != EMPTY) atomicOr(&bm[c[u] >> 5], 1u << (c[u] & 31));
+            }
+            k = kn;
+            s = sn;
+            e = en;
         }
         __syncthreads();
         uint32_t mine = 0;
-        for (uint32_t i = threadIdx.x; i < words; i += NT) mine += __popc(bm[i]);
+        for (uint32_t i = threadIdx.x; i < words; i += NTH) {
+            mine += __popc(bm[i]);
+            bm[i] = 0;
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
         if (lane == 0 && mine) atomicAdd(&total, mine);
         __syncthreads();
         if (threadIdx.x == 0) cnt[r] = total;
+        // next_li / total are rewritten only after the barrier at the top of the loop... which
+        // thread 0 reaches after this store; the other threads read next_li before it
         __syncthreads();
     }
 }
@@ -455,118 +479,133 @@ __global__ void __launch_bounds__(1024)
 
 // ---- numeric, large rows with a moderate A row (<= PANEL_MAX_A non-zeros): dense f64
 // accumulation in SHARED memory, one column panel of PANEL_W columns at a time.  Per A
-// non-zero a cursor (shared memory) remembers how far its (sorted) B row has been consumed,
-// so every B entry is read once and lands in the panel that owns its column; panels are
-// extracted in order, so the row comes out sorted.  No global atomics: the first version's
-// dense accumulators in global memory (1.2 GB for 296 CTAs) made this phase 77 % of the
-// whole SpGEMM (profiles/r1_launches_spgemm_breakdown.txt).
-constexpr uint32_t PANEL_W = 20480;       // columns per panel: 160 KB of f64 accumulators
-constexpr uint32_t PANEL_MAX_A = 4096;    // cursors: 16 KB
-constexpr size_t PANEL_SMEM = PANEL_W * 8 + PANEL_W / 8 + PANEL_MAX_A * 4;
+// non-zero a cursor remembers how far its (sorted) B row has been consumed, so every B entry is
+// read once and lands in the panel that owns its column; panels are extracted in order, so the
+// row comes out sorted.  No global atomics (round 1's dense accumulators in global memory were
+// 77 % of the whole SpGEMM).  What bounds it is the L2 round trip of the B stream, so:
+//   * everything a segment needs -- cursor, end of the B row, A's value -- sits in shared memory
+//     (filled once per row): one dependent global load per chunk instead of three;
+//   * a warp works on TWO A non-zeros at a time, index and value chunks of both in flight;
+//   * 1024 threads (32 warps of latency hiding at one CTA per SM), rows handed out dynamically,
+//     panels nothing landed in are skipped.
+constexpr uint32_t PANEL_W = 16384;       // columns per panel: 128 KB of f64 accumulators
+constexpr uint32_t PANEL_MAX_A = 4096;    // per-A-non-zero state: 16 B each = 64 KB
+constexpr size_t PANEL_SMEM = (size_t)PANEL_W * 8 + PANEL_W / 8 + (size_t)PANEL_MAX_A * 16;
+constexpr int PANEL_NT = 1024;
 
-// NTH threads per CTA (one CTA per SM: the panel takes the shared memory).  TUNED = the
-// round-2 candidate (spgemm_v2): warp groups for short A rows, two chunks of a B row in flight
-// per warp, untouched panels skipped; <256, false> is the kernel validated in round 1.
-template <int NTH, bool TUNED>
-__global__ void __launch_bounds__(NTH)
+__global__ void __launch_bounds__(PANEL_NT)
     num_panel_kernel(const uint32_t* __restrict__ a_ip, const uint32_t* __restrict__ a_idx,
                      const double* __restrict__ a_val, const uint32_t* __restrict__ b_ip,
                      const uint32_t* __restrict__ b_idx, const double* __restrict__ b_val,
                      const uint64_t* __restrict__ c_ip, const uint32_t* __restrict__ list,
                      uint32_t n_list, uint32_t cols, uint32_t* __restrict__ c_idx,
                      double* __restrict__ c_val, uint32_t* __restrict__ row_counter) {
-    constexpr int NWARPS = NTH / 32;
+    constexpr int NTH = PANEL_NT, NWARPS = NTH / 32;
     extern __shared__ __align__(16) unsigned char dyn_raw[];
     double* acc = (double*)dyn_raw;                                  // PANEL_W
-    uint32_t* bm = (uint32_t*)(dyn_raw + (size_t)PANEL_W * 8);        // PANEL_W / 32 words
+    double* aval = acc + PANEL_W;                                     // PANEL_MAX_A
+    uint32_t* bm = (uint32_t*)(aval + PANEL_MAX_A);                   // PANEL_W / 32 words
     uint32_t* cursor = bm + PANEL_W / 32;                             // PANEL_MAX_A
+    uint32_t* bend = cursor + PANEL_MAX_A;                            // PANEL_MAX_A
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t chunk_total;
-    __shared__ uint32_t panel_mark;  // TUNED: sequence number of the last panel something landed in
+    __shared__ uint32_t panel_mark;  // sequence number of the last panel something landed in
+    __shared__ uint32_t next_li;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t i = threadIdx.x; i < PANEL_W; i += NTH) acc[i] = 0.0;   // stays zero between rows
     for (uint32_t i = threadIdx.x; i < PANEL_W / 32; i += NTH) bm[i] = 0;
     if (threadIdx.x == 0) panel_mark = 0;
     __syncthreads();
     uint32_t seq = 0;  // panels visited by this CTA so far (uniform)
-    __shared__ uint32_t next_li;
-    // TUNED: rows are handed out dynamically (work per row spans three orders of magnitude and
-    // the list starts with the heaviest rows of an R-MAT matrix); otherwise round-robin
-    for (uint32_t li = blockIdx.x;; li += gridDim.x) {
-        if (TUNED) {
-            if (threadIdx.x == 0) next_li = atomicAdd(row_counter, 1u);
-            __syncthreads();
-            li = next_li;  // the next write is behind the barrier after the cursor set-up
-        }
+    for (;;) {
+        if (threadIdx.x == 0) next_li = atomicAdd(row_counter, 1u);
+        __syncthreads();
+        const uint32_t li = next_li;  // the next write is behind the barrier after the set-up
         if (li >= n_list) break;
         const uint32_t r = list[li];
         const uint32_t a0 = a_ip[r], na = a_ip[r + 1] - a0;
-        for (uint32_t kk = threadIdx.x; kk < na; kk += NTH) cursor[kk] = b_ip[a_idx[a0 + kk]];
+        for (uint32_t kk = threadIdx.x; kk < na; kk += NTH) {
+            const uint32_t br = a_idx[a0 + kk];
+            cursor[kk] = b_ip[br];
+            bend[kk] = b_ip[br + 1];
+            aval[kk] = a_val[a0 + kk];
+        }
         __syncthreads();
         // G warps share one B row when the A row is short (G > 1 implies na <= NWARPS / 2, so
-        // every group then sees exactly one A non-zero per panel)
-        const int G = warps_per_brow(na, NWARPS, TUNED ? 1 : 0);
+        // every group then sees at most one A non-zero per panel)
+        const int G = warps_per_brow(na, NWARPS, 1);
         const int grp = warp / G, wg = warp % G, ngrp = NWARPS / G;
         uint64_t out = c_ip[r];
         for (uint32_t p0 = 0; p0 < cols; p0 += PANEL_W) {
             const uint32_t p1 = (cols - p0 > PANEL_W) ? p0 + PANEL_W : cols;
             ++seq;
             uint32_t grp_taken = 0;  // G > 1: entries of the group's B row this warp consumed
-            for (uint32_t kk = grp; kk < na; kk += ngrp) {
-                const uint32_t br = a_idx[a0 + kk];
-                const double av = a_val[a0 + kk];
-                const uint32_t end = b_ip[br + 1];
-                const uint32_t base = cursor[kk];
-                uint32_t pos = base + (uint32_t)wg * 32;  // this warp's chunks: pos, pos + 32 G, ...
-                uint32_t taken = 0;
+            bool landed = false;
+            // two A non-zeros (kk, kk + ngrp) per pass, their chunks interleaved
+            for (uint32_t kk = grp; kk < na; kk += 2 * ngrp) {
+                const uint32_t kb = kk + ngrp;
+                const bool has_b = kb < na;
+                const uint32_t base_a = cursor[kk], end_a = bend[kk];
+                const uint32_t base_b = has_b ? cursor[kb] : 0u, end_b = has_b ? bend[kb] : 0u;
+                const double av_a = aval[kk], av_b = has_b ? aval[kb] : 0.0;
                 // columns ascend, so the entries below p1 are a prefix of [base, end): a chunk
                 // inside the prefix is taken whole, the chunk holding its end partly, later
-                // chunks not at all -- the warps' counts add up to the prefix length
-                while (pos < end) {
-                    const uint32_t pa = pos + lane;
-                    const uint32_t ca = pa < end ? b_idx[pa] : 0xffffffffu;
-                    uint32_t cb = 0xffffffffu;
+                // chunks not at all -- with G warps the warps' counts add up to the prefix length
+                uint32_t pos_a = base_a + (uint32_t)wg * 32, pos_b = base_b + (uint32_t)wg * 32;
+                uint32_t taken_a = 0, taken_b = 0;
+                bool live_a = pos_a < end_a, live_b = has_b && pos_b < end_b;
+                while (live_a || live_b) {
+                    uint32_t ca = EMPTY, cb = EMPTY;
                     double va = 0.0, vb = 0.0;
-                    if (TUNED) {  // second chunk and both value loads in flight with the first
-                        const uint32_t pb = pos + 32u * G + lane;
-                        cb = pb < end ? b_idx[pb] : 0xffffffffu;
-                        if (pa < end) va = b_val[pa];
-                        if (pb < end) vb = b_val[pb];
+                    const uint32_t pa = pos_a + lane, pb = pos_b + lane;
+                    if (live_a && pa < end_a) {
+                        ca = b_idx[pa];
+                        va = b_val[pa];
                     }
-                    const bool take_a = ca < p1;
-                    if (take_a) {
-                        if (!TUNED) va = b_val[pa];
-                        atomicAdd(&acc[ca - p0], __dmul_rn(av, va));
-                        atomicOr(&bm[(ca - p0) >> 5], 1u << ((ca - p0) & 31));
+                    if (live_b && pb < end_b) {
+                        cb = b_idx[pb];
+                        vb = b_val[pb];
                     }
-                    const uint32_t na_t = __popc(__ballot_sync(0xffffffffu, take_a));
-                    taken += na_t;
-                    if (na_t < 32) break;
-                    if (TUNED) {
-                        const bool take_b = cb < p1;
-                        if (take_b) {
-                            atomicAdd(&acc[cb - p0], __dmul_rn(av, vb));
+                    if (live_a) {
+                        const bool take = ca < p1;
+                        if (take) {
+                            atomicAdd(&acc[ca - p0], __dmul_rn(av_a, va));
+                            atomicOr(&bm[(ca - p0) >> 5], 1u << ((ca - p0) & 31));
+                        }
+                        const uint32_t n = __popc(__ballot_sync(0xffffffffu, take));
+                        taken_a += n;
+                        pos_a += 32u * G;
+                        live_a = n == 32 && pos_a < end_a;
+                    }
+                    if (live_b) {
+                        const bool take = cb < p1;
+                        if (take) {
+                            atomicAdd(&acc[cb - p0], __dmul_rn(av_b, vb));
                             atomicOr(&bm[(cb - p0) >> 5], 1u << ((cb - p0) & 31));
                         }
-                        const uint32_t nb_t = __popc(__ballot_sync(0xffffffffu, take_b));
-                        taken += nb_t;
-                        if (nb_t < 32) break;
-                        pos += 64u * G;
-                    } else {
-                        pos += 32;
+                        const uint32_t n = __popc(__ballot_sync(0xffffffffu, take));
+                        taken_b += n;
+                        pos_b += 32u * G;
+                        live_b = n == 32 && pos_b < end_b;
                     }
                 }
-                if (TUNED && taken && lane == 0) panel_mark = seq;  // same value from every writer
+                landed |= (taken_a | taken_b) != 0;
                 if (G == 1) {
-                    if (lane == 0) cursor[kk] = base + taken;
+                    if (lane == 0) {
+                        cursor[kk] = base_a + taken_a;
+                        if (has_b) cursor[kb] = base_b + taken_b;
+                    }
                 } else {
-                    grp_taken = taken;  // added after the barrier: the group's other warps read `base`
+                    grp_taken = taken_a;  // added after the barrier: the group's other warps read `base`
                 }
             }
+            if (landed && lane == 0) panel_mark = seq;  // same value from every writer
             __syncthreads();
             if (G > 1 && grp < (int)na && grp_taken && lane == 0) atomicAdd(&cursor[grp], grp_taken);
-            if (TUNED && panel_mark != seq) continue;  // nothing landed here (uniform: read after the barrier;
-                                                       // the next write to panel_mark is behind the next barrier)
+            if (panel_mark != seq) {  // nothing landed here (uniform: read after the barrier)
+                __syncthreads();      // cursor updates above / panel_mark before the next panel
+                continue;
+            }
             // ordered extraction of this panel (also re-zeroes what it touched)
             const uint32_t words = (p1 - p0 + 31) / 32;
             for (uint32_t w0 = 0; w0 < words; w0 += NTH) {
@@ -688,14 +727,11 @@ int run_numeric(sprs_b200_ctx* ctx, sprs_b200_spgemm* p, uint32_t* d_cidx, doubl
     const auto* b = p->b;
     const uint32_t *a_ip = (const uint32_t*)a->d_indptr, *b_ip = (const uint32_t*)b->d_indptr;
     SPRS_CUDA(ctx, cudaMemsetAsync(p->d_counters, 0, 8 * sizeof(uint32_t), s));
-    const bool v2 = spgemm_v2();
-    // v2: rows with more than 16 entries per column panel are cheaper in the panel kernel (no
+    // rows with more than 16 entries per column panel are cheaper in the panel kernel (no
     // probing, no sort; fixed cost ~ n_panels) than in the CTA hash map
-    uint32_t num_m_max = NUM_M_MAX;
-    if (v2) {
-        const uint64_t n_panels = (p->cols + PANEL_W - 1) / PANEL_W;
-        num_m_max = (uint32_t)std::min<uint64_t>(NUM_M_MAX, std::max<uint64_t>(NUM_S_MAX, 16 * n_panels));
-    }
+    const uint64_t n_panels = (p->cols + PANEL_W - 1) / PANEL_W;
+    const uint32_t num_m_max =
+        (uint32_t)std::min<uint64_t>(NUM_M_MAX, std::max<uint64_t>(NUM_S_MAX, 16 * n_panels));
     bin_rows_kernel<uint32_t><<<grid_for(rows), 256, 0, s>>>(p->d_cnt, rows, NUM_S_MAX, num_m_max,
                                                             p->d_lists, p->d_counters, nullptr);
     ctx->launches += 1;
@@ -717,7 +753,7 @@ int run_numeric(sprs_b200_ctx* ctx, sprs_b200_spgemm* p, uint32_t* d_cidx, doubl
         const unsigned g = std::min<unsigned>(h_cnt[1], cap);
         num_med_kernel<<<g, NT, smem, s>>>(a_ip, a->d_indices, a->d_data, b_ip, b->d_indices,
                                            b->d_data, p->d_cptr, p->d_cnt, l1, h_cnt[1], d_cidx,
-                                           d_cval, v2 ? 1 : 0);
+                                           d_cval, 1);
         ctx->launches += 1;
     }
     if (h_cnt[2]) {
@@ -734,13 +770,13 @@ int run_numeric(sprs_b200_ctx* ctx, sprs_b200_spgemm* p, uint32_t* d_cidx, doubl
         int st = cudaStreamSynchronize(s) == cudaSuccess ? SPRS_B200_OK : SPRS_B200_ERR_CUDA;
         const uint32_t n_panel = h2[3], n_hub = h2[4];
         if (st == SPRS_B200_OK && n_panel) {
-            auto kern = v2 ? num_panel_kernel<1024, true> : num_panel_kernel<NT, false>;
+            auto kern = num_panel_kernel;
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)PANEL_SMEM) != cudaSuccess)
                 st = SPRS_B200_ERR_CUDA;
             else {
                 const unsigned g = std::min<unsigned>(n_panel, (unsigned)ctx->sm_count);
-                kern<<<g, v2 ? 1024 : NT, PANEL_SMEM, s>>>(a_ip, a->d_indices, a->d_data, b_ip,
+                kern<<<g, PANEL_NT, PANEL_SMEM, s>>>(a_ip, a->d_indices, a->d_data, b_ip,
                                                            b->d_indices, b->d_data, p->d_cptr,
                                                            panel_list, n_panel, (uint32_t)p->cols,
                                                            d_cidx, d_cval, p->d_counters + 5);
@@ -811,11 +847,10 @@ int sprs_b200_spgemm_symbolic(sprs_b200_ctx* ctx, const sprs_b200_csmat* a,
         nprod_kernel<<<std::min<unsigned>((rows + WARPS - 1) / WARPS, cap * 4), NT, 0, s>>>(
             a_ip, a->d_indices, b_ip, rows, p->d_nprod);
         cudaMemsetAsync(p->d_counters, 0, 8 * sizeof(uint32_t), s);
-        const bool v2 = spgemm_v2();
-        // v2: with the bitmap in shared memory (no probing, fixed cost ~ cols / 32 words) the
+            // with the bitmap in shared memory (no probing, fixed cost ~ cols / 32 words) the
         // hash set only pays below ~cols/256 products
         uint32_t sym_m_max = SYM_M_MAX;
-        if (v2 && p->cols <= BITMAP_SMEM_MAX_COLS)
+        if (p->cols <= BITMAP_SMEM_MAX_COLS)
             sym_m_max = (uint32_t)std::min<uint64_t>(SYM_M_MAX, std::max<uint64_t>(SYM_S_MAX, p->cols / 256));
         bin_rows_kernel<uint64_t><<<grid_for(rows), 256, 0, s>>>(
             p->d_nprod, rows, SYM_S_MAX, sym_m_max, p->d_lists, p->d_counters, p->d_cnt);
@@ -841,7 +876,7 @@ int sprs_b200_spgemm_symbolic(sprs_b200_ctx* ctx, const sprs_b200_csmat* a,
                                  (int)smem);
             sym_med_kernel<<<std::min<unsigned>(h_cnt[1], cap), NT, smem, s>>>(
                 a_ip, a->d_indices, b_ip, b->d_indices, p->d_nprod, l1, h_cnt[1], p->d_cnt,
-                v2 ? 1 : 0);
+                1);
             ctx->launches += 1;
         }
         if (h_cnt[2]) {
@@ -851,8 +886,9 @@ int sprs_b200_spgemm_symbolic(sprs_b200_ctx* ctx, const sprs_b200_csmat* a,
             if (w.smem)
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)w.smem);
-            kern<<<w.grid, NT, w.smem, s>>>(a_ip, a->d_indices, b_ip, b->d_indices, l2, h_cnt[2],
-                                            w.words, w.bitmaps, p->d_cnt, v2 ? 1 : 0);
+            kern<<<w.grid, SYM_L_NT, w.smem, s>>>(a_ip, a->d_indices, b_ip, b->d_indices, l2,
+                                                  h_cnt[2], w.words, w.bitmaps, p->d_cnt, 1,
+                                                  p->d_counters + 5);
             ctx->launches += 1;
             cudaStreamSynchronize(s);
             free_large(w);

@@ -157,87 +157,124 @@ __device__ __forceinline__ void reduce_rows_warp(const TileCtx& tc, const P* __r
     }
 }
 
+// What the row emitters need, by value (they are real functions, not inlined: the hot loop stays
+// small enough for the instruction cache).
+struct RowSink {
+    double* y;                  // this GPU's y (target 0)
+    const SpmvTargets* yt;      // MULTI only: the kernel parameter itself (constant bank)
+    double* carry_slot;
+    uint32_t r1;                // first row NOT owned by the tile (== its carry row when < rows)
+    int accumulate;
+};
+template <bool MULTI>
+__device__ __forceinline__ void sink_row(const RowSink& k, uint64_t r, double sum) {
+    if (r < k.r1) {
+        const double v = k.accumulate ? __dadd_rn(k.y[r], sum) : sum;
+        k.y[r] = v;
+        if (MULTI) {
+#pragma unroll
+            for (int q = 1; q < SPMV_MAX_TARGETS; ++q)
+                if (q < k.yt->n) k.yt->p[q][r] = v;
+        }
+    } else {
+        *k.carry_slot = sum;  // row continues in a later tile: spmv_fixup_kernel adds it
+    }
+}
+
 // Register path, second half: up to four finished rows sit as per-lane partials in s0..s3
 // (row_base + 0..3).  One multi-value butterfly reduces them together: xor 16 halves the live
 // values (lanes with bit 4 clear keep rows 0,1, the others rows 2,3), xor 8 halves again, xor
 // 4/2/1 finish: 6 double shuffles for 4 rows instead of 20.  Lane 8*j ends up with row j.
 template <bool MULTI>
-__device__ __forceinline__ void flush_slots(const TileCtx& tc, double s0, double s1, double s2,
-                                            double s3, uint64_t row_base, int n, int lane) {
+__device__ __noinline__ void flush_slots(RowSink k, double s0, double s1, double s2, double s3,
+                                         uint32_t row_base, int n, int lane) {
     constexpr unsigned FULL = 0xffffffffu;
-    double v;
-    if (n > 2) {
-        const bool up16 = lane & 16;
-        const double a0 = __dadd_rn(up16 ? s2 : s0, __shfl_xor_sync(FULL, up16 ? s0 : s2, 16));
-        const double a1 = __dadd_rn(up16 ? s3 : s1, __shfl_xor_sync(FULL, up16 ? s1 : s3, 16));
-        const bool up8 = lane & 8;
-        v = __dadd_rn(up8 ? a1 : a0, __shfl_xor_sync(FULL, up8 ? a0 : a1, 8));
-    } else {  // one or two rows: row 0 in the lanes with bit 3 clear, row 1 in the others
-        const bool up8 = lane & 8;
-        const double a0 = __dadd_rn(s0, __shfl_xor_sync(FULL, s0, 16));
-        const double a1 = __dadd_rn(s1, __shfl_xor_sync(FULL, s1, 16));
-        v = __dadd_rn(up8 ? a1 : a0, __shfl_xor_sync(FULL, up8 ? a0 : a1, 8));
-    }
+    const bool up16 = lane & 16, up8 = lane & 8;
+    const double a0 = __dadd_rn(up16 ? s2 : s0, __shfl_xor_sync(FULL, up16 ? s0 : s2, 16));
+    const double a1 = __dadd_rn(up16 ? s3 : s1, __shfl_xor_sync(FULL, up16 ? s1 : s3, 16));
+    double v = __dadd_rn(up8 ? a1 : a0, __shfl_xor_sync(FULL, up8 ? a0 : a1, 8));
     v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 4));
     v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 2));
     v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 1));
-    // n > 2: row = 2*bit4 + bit3 = lane >> 3;  n <= 2: row = bit3 (both 16-lane halves agree)
-    const int row = n > 2 ? (lane >> 3) : ((lane >> 3) & 1);
-    if ((lane & 7) == 0 && lane < 32 && row < n && (n > 2 || lane < 16))
-        emit_row<MULTI>(tc, row_base + row, v);
+    const int row = lane >> 3;  // 2*bit4 + bit3
+    if ((lane & 7) == 0 && row < n) sink_row<MULTI>(k, (uint64_t)row_base + row, v);
 }
 
-// Register path: the tile's EPL products per lane (element e = lane + 32*i) are folded into
-// row sums without leaving the registers.  `bl`: lane L holds the tile-local position of
-// indptr[r0 + L] clamped to [0, WT] (WT beyond the last boundary); row r0+q ends at bl[q+1].
-// nrc rows end inside the tile (r0 .. r0+nrc-1); what is left after the last end belongs to
-// row r0+nrc, which continues in a later tile (carry) when has_tail.  Control flow is
-// warp-uniform throughout (boundaries are warp-wide data).
+// Register path: the tile's EPL products per lane (element e = lane + 32*i, i.e. register i is
+// the "slab" of 32 consecutive non-zeros 32*i .. 32*i+31) are folded into row sums without
+// leaving the registers.  ends: lane L in 1..nrc holds the tile-local END of row r0+L-1, in
+// [0, WT]; nrc rows end inside the tile, what is left after the last end belongs to row r0+nrc
+// (the tile's carry) when has_tail.  All control flow is warp-uniform AND known to be: the
+// slab mask comes from a warp reduction (REDUX), row counts from ballots, so the branches cost
+// no divergence bookkeeping.  A slab without a row end costs one add.
 template <int EPL, bool MULTI>
-__device__ __forceinline__ void reduce_rows_slots(const TileCtx& tc, const double (&p)[EPL], int bl,
-                                                  uint32_t r0, int nrc, bool has_tail, int lane) {
+__device__ __forceinline__ void reduce_rows_slots(const RowSink& k, const double (&p)[EPL],
+                                                  int end_local, uint32_t r0, int nrc, bool has_tail,
+                                                  int lane) {
     constexpr unsigned FULL = 0xffffffffu;
-    constexpr int NONE = 0x7fffffff;
+    const bool is_end = lane >= 1 && lane <= nrc;
+    // slab that holds the row's last element (end 0 = an empty row at the very start: slab 0)
+    const int sb = end_local > 0 ? (end_local - 1) >> 5 : 0;
+    const int q = end_local - 32 * sb;  // lanes < q of slab sb belong to the row (0 .. 32)
+    const unsigned slabs = __reduce_or_sync(FULL, is_end ? 1u << sb : 0u);
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, acc = 0.0;
-    int j = 0, ridx = 0;
-    uint64_t row_base = r0;
-    int nb = nrc > 0 ? __shfl_sync(FULL, bl, 1) : NONE;  // tile-local end of row r0 + ridx
-#define SPMV_PARK(val)                                                            \
-    do {                                                                          \
-        const double v_ = (val);                                                  \
-        s0 = j == 0 ? v_ : s0;                                                    \
-        s1 = j == 1 ? v_ : s1;                                                    \
-        s2 = j == 2 ? v_ : s2;                                                    \
-        s3 = j == 3 ? v_ : s3;                                                    \
-        ++j;                                                                      \
-        if (j == 4) {                                                             \
-            flush_slots<MULTI>(tc, s0, s1, s2, s3, row_base, 4, lane);            \
-            row_base += 4;                                                        \
-            j = 0;                                                                \
-        }                                                                         \
+    int j = 0;
+    uint32_t row_base = r0;
+#define SPMV_PARK(val)                                                  \
+    do {                                                                \
+        const double v_ = (val);                                        \
+        if (j == 0) s0 = v_;                                            \
+        else if (j == 1) s1 = v_;                                       \
+        else if (j == 2) s2 = v_;                                       \
+        else s3 = v_;                                                   \
+        if (++j == 4) {                                                 \
+            flush_slots<MULTI>(k, s0, s1, s2, s3, row_base, 4, lane);   \
+            row_base += 4;                                              \
+            j = 0;                                                      \
+        }                                                               \
     } while (0)
 #pragma unroll
     for (int i = 0; i < EPL; ++i) {
         double pi = p[i];
-        const int e0 = 32 * i;
-        while (nb < e0 + 32) {  // row r0+ridx ends inside this slab, before lane q
-            const bool mine = lane < nb - e0;
-            SPMV_PARK(__dadd_rn(acc, mine ? pi : 0.0));
-            pi = mine ? 0.0 : pi;
-            acc = 0.0;
-            ++ridx;
-            nb = ridx < nrc ? __shfl_sync(FULL, bl, ridx + 1) : NONE;
+        if ((slabs >> i) & 1u) {  // rows end inside this slab: consecutive boundary lanes
+            const unsigned m = __ballot_sync(FULL, is_end && sb == i);
+            const int first = __ffs(m) - 1, cnt = __popc(m);
+            for (int c = 0; c < cnt; ++c) {
+                const bool mine = lane < __shfl_sync(FULL, q, first + c);
+                SPMV_PARK(__dadd_rn(acc, mine ? pi : 0.0));
+                pi = mine ? 0.0 : pi;
+                acc = 0.0;
+            }
         }
         acc = __dadd_rn(acc, pi);
     }
-    while (ridx < nrc) {  // rows ending exactly at the tile end (and empty rows after them)
-        SPMV_PARK(acc);
-        acc = 0.0;
-        ++ridx;
-    }
-    if (has_tail) SPMV_PARK(acc);  // row r0+nrc >= r1: emit_row files it as the tile's carry
-    if (j > 0) flush_slots<MULTI>(tc, s0, s1, s2, s3, row_base, j, lane);
+    if (has_tail) SPMV_PARK(acc);  // row r0+nrc >= r1: sink_row files it as the tile's carry
+    if (j > 0) flush_slots<MULTI>(k, s0, j > 1 ? s1 : 0.0, j > 2 ? s2 : 0.0, 0.0, row_base, j, lane);
 #undef SPMV_PARK
+}
+
+// Shared-memory path (tiles with many rows, and the ragged last tile): products are in the
+// warp's buffer; rows are reduced by lane groups sized to the tile's mean row length.
+template <typename P, bool MULTI>
+__device__ __noinline__ void reduce_rows_smem(RowSink k, const P* __restrict__ indptr,
+                                              const double* sprod, uint64_t k0, uint64_t k1,
+                                              uint32_t r0, uint32_t rows, uint64_t b_first, int lane) {
+    TileCtx tc;
+    tc.k0 = k0;
+    tc.k1 = k1;
+    tc.r1 = k.r1;
+    tc.y = k.y;
+    tc.yt = k.yt;
+    tc.carry_slot = k.carry_slot;
+    tc.accumulate = k.accumulate;
+    const uint64_t r_last = k.r1 < rows ? (uint64_t)k.r1 : (uint64_t)k.r1 - 1;
+    const uint64_t cnt = k1 - k0, nr = r_last - r0 + 1;
+    if (cnt <= 6 * nr)
+        reduce_rows_warp<P, 1, MULTI>(tc, indptr, sprod, r0, r_last, b_first, lane);
+    else if (cnt <= 12 * nr)
+        reduce_rows_warp<P, 2, MULTI>(tc, indptr, sprod, r0, r_last, b_first, lane);
+    else
+        reduce_rows_warp<P, 4, MULTI>(tc, indptr, sprod, r0, r_last, b_first, lane);
 }
 
 template <typename P, int EPL, int NWARPS, int MINB, bool MULTI>
@@ -245,138 +282,128 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
     spmv_pipe_kernel(const P* __restrict__ indptr, const uint32_t* __restrict__ indices,
                      const double* __restrict__ data, const uint32_t* __restrict__ tile_row,
                      const double* __restrict__ x, const __grid_constant__ SpmvTargets yt,
-                     double* __restrict__ carry, uint64_t nnz, uint32_t rows, uint64_t t_begin,
-                     uint64_t t_end /* this launch covers tiles [t_begin, t_end) */, int accumulate) {
+                     double* __restrict__ carry, uint64_t nnz, uint32_t rows, uint32_t t_begin,
+                     uint32_t t_end /* this launch covers tiles [t_begin, t_end) */, int accumulate,
+                     uint64_t pol_stream /* L2 evict_first */, uint64_t polx /* L2 evict_last */) {
     constexpr int WT = EPL * 32;
+    using OFF = P;  // element offsets: 32 bits wide when the indptr is (nnz < 2^32)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* sprod = (double*)smem_raw + (size_t)warp * WT;  // many-row tiles only
-    const uint64_t GW = (uint64_t)gridDim.x * NWARPS;
-    uint64_t t = t_begin + (uint64_t)blockIdx.x * NWARPS + warp;
-    if (t >= t_end) return;
-    const uint64_t pol_stream = policy_evict_first();
-    const uint64_t polx = policy_evict_last();
+    const uint32_t GW = gridDim.x * NWARPS;
+    uint32_t t = t_begin + blockIdx.x * NWARPS + warp;
+    // tiles below n_full are whole: the hot loop never guards a load.  The ragged tail (at most
+    // one tile, index n_full) is handled after the loop by the warp the deal gives it to.
+    const uint32_t n_full = (uint32_t)(nnz / WT);
+    const uint32_t t_hot_end = t_end < n_full ? t_end : n_full;
+    // (the two L2 policies are kernel PARAMETERS: values the compiler knows to be warp-uniform
+    // go into uniform registers once; as per-thread createpolicy results every hinted load
+    // re-materialised its descriptor -- 32 extra instructions per tile)
+    RowSink sink;
+    sink.y = yt.p[0];
+    sink.yt = &yt;
+    sink.accumulate = accumulate;
 
-    // operands of a tile: guarded loads only for the (single) ragged last tile of the matrix
-    uint32_t c[EPL];
-    double xn[EPL], vn[EPL];
-    auto load_idx = [&](uint64_t tt) {
-        const uint64_t k0 = tt * (uint64_t)WT;
-        if (k0 + WT <= nnz) {
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) c[i] = ldg_stream_u32(indices + k0 + lane + 32 * i, pol_stream);
-        } else {
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) {
-                const uint64_t e = k0 + lane + 32 * i;
-                c[i] = e < nnz ? indices[e] : 0u;
-            }
+    if (t < t_hot_end) {
+        uint32_t c[EPL];
+        double xn[EPL], vn[EPL];
+        // prologue: tile t fully issued, tile t+GW's indices and row range on their way
+        uint32_t tn = t + GW;
+        uint32_t r0 = tile_row[t], r1 = tile_row[t + 1];
+        uint32_t r0n = 0, r1n = 0;
+        if (tn < t_hot_end) {
+            r0n = tile_row[tn];
+            r1n = tile_row[tn + 1];
         }
-    };
-    auto load_ops = [&](uint64_t tt) {  // gathers of x (indices in c) and the values
-        const uint64_t k0 = tt * (uint64_t)WT;
-        if (k0 + WT <= nnz) {
+        {
+            const uint32_t* ip = indices + (OFF)t * WT + lane;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) c[i] = ldg_stream_u32(ip + 32 * i, pol_stream);
+        }
+        // lane L: indptr[r0 + L] (L <= rows ending in the tile, +1 when a row continues)
+        P b_first = (r0 + lane <= (r1 < rows ? r1 + 1 : r1)) ? indptr[(size_t)r0 + lane] : (P)0;
+        {
+            const double* dp = data + (OFF)t * WT + lane;
 #pragma unroll
             for (int i = 0; i < EPL; ++i) xn[i] = ldg_f64_hint(x + c[i], polx);
 #pragma unroll
-            for (int i = 0; i < EPL; ++i) vn[i] = ldg_stream_f64(data + k0 + lane + 32 * i, pol_stream);
-        } else {
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) {
-                const uint64_t e = k0 + lane + 32 * i;
-                xn[i] = e < nnz ? ldg_f64_hint(x + c[i], polx) : 0.0;
-                vn[i] = e < nnz ? data[e] : 0.0;
-            }
+            for (int i = 0; i < EPL; ++i) vn[i] = ldg_stream_f64(dp + 32 * i, pol_stream);
         }
-    };
-    auto load_bounds = [&](uint32_t ra, uint32_t rb) -> uint64_t {  // lane L: indptr[ra + L]
-        const uint64_t rl = (rb < rows) ? (uint64_t)rb : (uint64_t)rb - 1;
-        const uint64_t rr = (uint64_t)ra + lane;
-        return rr <= rl + 1 ? (uint64_t)indptr[rr] : 0;
-    };
-
-    // prologue: tile t fully issued, tile t+GW's indices and row range on their way
-    uint64_t tn = t + GW;
-    uint32_t r0 = tile_row[t], r1 = tile_row[t + 1];
-    uint32_t r0n = 0, r1n = 0;
-    if (tn < t_end) {
-        r0n = tile_row[tn];
-        r1n = tile_row[tn + 1];
-    }
-    load_idx(t);
-    uint64_t b_first = load_bounds(r0, r1);
-    load_ops(t);
-    if (tn < t_end) load_idx(tn);
-
-    for (;;) {
-        const uint64_t k0 = t * (uint64_t)WT;
-        const uint64_t k1 = (k0 + WT < nnz) ? k0 + WT : nnz;
-        // products of tile t (its gathers and values were issued one iteration ago)
-        double p[EPL];
-        if (k1 - k0 == WT) {
+        if (tn < t_hot_end) {
+            const uint32_t* ip = indices + (OFF)tn * WT + lane;
+#pragma unroll
+            for (int i = 0; i < EPL; ++i) c[i] = ldg_stream_u32(ip + 32 * i, pol_stream);
+        }
+        for (;;) {
+            // products of tile t (its gathers and values were issued one iteration ago)
+            double p[EPL];
 #pragma unroll
             for (int i = 0; i < EPL; ++i) p[i] = __dmul_rn(vn[i], xn[i]);
-        } else {
+            // tile t+GW: gathers + values in flight while tile t is reduced; then the indices of
+            // the tile after that, its row range, and the row boundaries of tile t+GW
+            const uint32_t tnn = tn + GW;
+            uint32_t r0nn = 0, r1nn = 0;
+            P b_next = 0;
+            if (tn < t_hot_end) {
+                const double* dp = data + (OFF)tn * WT + lane;
 #pragma unroll
-            for (int i = 0; i < EPL; ++i)
-                p[i] = (k0 + lane + 32 * i < nnz) ? __dmul_rn(vn[i], xn[i]) : 0.0;
-        }
-        // tile t+GW: gathers + values in flight while tile t is reduced; then the indices of
-        // the tile after that, its row range, and the row boundaries of tile t+GW
-        const uint64_t tnn = tn + GW;
-        uint32_t r0nn = 0, r1nn = 0;
-        uint64_t b_next = 0;
-        if (tn < t_end) {
-            load_ops(tn);
-            b_next = load_bounds(r0n, r1n);
-            if (tnn < t_end) {
-                load_idx(tnn);
-                r0nn = tile_row[tnn];
-                r1nn = tile_row[tnn + 1];
-            }
-        }
-
-        TileCtx tc;
-        tc.k0 = k0;
-        tc.k1 = k1;
-        tc.r1 = r1;
-        tc.y = yt.p[0];
-        tc.yt = &yt;
-        tc.carry_slot = carry + t;
-        tc.accumulate = accumulate;
-        const uint32_t nrc = r1 - r0;  // rows that END in this tile
-        const bool has_tail = r1 < rows;
-        // mean row length of the tile: <= 6 keeps the one-lane-per-row path (storage order,
-        // bit-identical to the reference) even for a ragged tile with few rows
-        const uint64_t r_last = has_tail ? (uint64_t)r1 : (uint64_t)r1 - 1;
-        const uint32_t avg = (uint32_t)((k1 - k0) / (r_last - r0 + 1));
-        if (nrc <= (uint32_t)SPMV_REG_ROWS && avg > 6) {
-            int bl = WT;
-            if (lane <= (int)nrc) {
-                const uint64_t bb = b_first > k0 ? b_first - k0 : 0;
-                bl = bb < (uint64_t)WT ? (int)bb : WT;
-            }
-            reduce_rows_slots<EPL, MULTI>(tc, p, bl, r0, (int)nrc, has_tail, lane);
-        } else {
+                for (int i = 0; i < EPL; ++i) xn[i] = ldg_f64_hint(x + c[i], polx);
 #pragma unroll
-            for (int i = 0; i < EPL; ++i) sprod[lane + 32 * i] = p[i];
-            __syncwarp();
-            if (avg <= 6)
-                reduce_rows_warp<P, 1, MULTI>(tc, indptr, sprod, r0, r_last, b_first, lane);
-            else if (avg <= 12)
-                reduce_rows_warp<P, 2, MULTI>(tc, indptr, sprod, r0, r_last, b_first, lane);
-            else
-                reduce_rows_warp<P, 4, MULTI>(tc, indptr, sprod, r0, r_last, b_first, lane);
-            __syncwarp();
+                for (int i = 0; i < EPL; ++i) vn[i] = ldg_stream_f64(dp + 32 * i, pol_stream);
+                b_next = (r0n + lane <= (r1n < rows ? r1n + 1 : r1n)) ? indptr[(size_t)r0n + lane] : (P)0;
+                if (tnn < t_hot_end) {
+                    const uint32_t* ip = indices + (OFF)tnn * WT + lane;
+#pragma unroll
+                    for (int i = 0; i < EPL; ++i) c[i] = ldg_stream_u32(ip + 32 * i, pol_stream);
+                    r0nn = tile_row[tnn];
+                    r1nn = tile_row[tnn + 1];
+                }
+            }
+            const OFF k0 = (OFF)t * WT;
+            sink.carry_slot = carry + t;
+            sink.r1 = r1;
+            const uint32_t nrc = r1 - r0;  // rows that END in this tile
+            const bool has_tail = r1 < rows;
+            // mean row length <= 6 keeps the one-lane-per-row path (storage order: the
+            // reference's bits); more than 24 row ends do not fit the boundary lanes
+            if (nrc <= (uint32_t)SPMV_REG_ROWS && (uint32_t)WT > 6u * (nrc + (has_tail ? 1u : 0u))) {
+                int end_local = 0;  // lane L in 1..nrc: end of row r0+L-1, clamped to the tile
+                if (lane <= (int)nrc) {
+                    const P bb = b_first > k0 ? (P)(b_first - k0) : (P)0;
+                    end_local = bb < (P)WT ? (int)bb : WT;
+                }
+                reduce_rows_slots<EPL, MULTI>(sink, p, end_local, r0, (int)nrc, has_tail, lane);
+            } else {
+#pragma unroll
+                for (int i = 0; i < EPL; ++i) sprod[lane + 32 * i] = p[i];
+                __syncwarp();
+                reduce_rows_smem<P, MULTI>(sink, indptr, sprod, (uint64_t)k0, (uint64_t)k0 + WT, r0,
+                                           rows, (uint64_t)b_first, lane);
+                __syncwarp();
+            }
+            t = tn;
+            if (tn >= t_hot_end) break;
+            tn = tnn;
+            r0 = r0n;
+            r1 = r1n;
+            r0n = r0nn;
+            r1n = r1nn;
+            b_first = b_next;
         }
-        if (tn >= t_end) break;
-        t = tn;
-        tn = tnn;
-        r0 = r0n;
-        r1 = r1n;
-        r0n = r0nn;
-        r1n = r1nn;
-        b_first = b_next;
+    }
+    // the ragged tail tile (or the single empty tile of a matrix without non-zeros)
+    if (t == n_full && t < t_end) {
+        const uint64_t k0 = (uint64_t)t * WT;
+        const uint32_t r0 = tile_row[t], r1 = tile_row[t + 1];
+        for (uint64_t e = k0 + lane; e < nnz; e += 32)
+            sprod[e - k0] = __dmul_rn(data[e], ldg_f64_hint(x + indices[e], polx));
+        __syncwarp();
+        sink.carry_slot = carry + t;
+        sink.r1 = r1;
+        const uint64_t rl = r1 < rows ? (uint64_t)r1 : (uint64_t)r1 - 1;
+        const uint64_t rr = (uint64_t)r0 + lane;
+        const uint64_t b_first = rr <= rl + 1 ? (uint64_t)indptr[rr] : 0;
+        reduce_rows_smem<P, MULTI>(sink, indptr, sprod, k0, nnz, r0, rows, b_first, lane);
     }
 }
 
@@ -476,6 +503,8 @@ template <typename P, int EPL, int CTAS>
 int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
                    const SpmvTargets& yt, int accumulate, uint64_t t0, uint64_t t1,
                    cudaStream_t s) {
+    if (m->n_tiles >= 0xffffffffull)
+        SPRS_FAIL(ctx, SPRS_B200_ERR_UNSUPPORTED, "spmv: more than 2^32 tiles");
     // CTAS resident CTAs per SM is also the kernel's __launch_bounds__ minBlocks: it sets the
     // register budget of the pipelined operand buffers.
     const bool multi = yt.n > 1;
@@ -502,8 +531,9 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
     if (grid > need) grid = need;
     kern<<<(unsigned)grid, SPMV_NWARPS * 32, smem, s>>>((const P*)m->d_indptr, m->d_indices,
                                                         m->d_data, m->d_tile_row, d_x, yt,
-                                                        m->d_carry, m->nnz, (uint32_t)m->rows, t0,
-                                                        t1, accumulate);
+                                                        m->d_carry, m->nnz, (uint32_t)m->rows,
+                                                        (uint32_t)t0, (uint32_t)t1, accumulate,
+                                                        ctx->pol_evict_first, ctx->pol_evict_last);
     return SPRS_B200_OK;
 }
 

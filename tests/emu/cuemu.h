@@ -26,6 +26,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __align__(n) alignas(n)
@@ -232,6 +233,11 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     return cuemu::warp_ballot(mask, pred != 0);
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline unsigned __reduce_or_sync(unsigned mask, unsigned v) {  // full-warp masks only
+    for (int o = 16; o > 0; o >>= 1)
+        v |= cuemu::from_bits<unsigned>(cuemu::warp_exchange(mask, cuemu::to_bits(v), cuemu::lane_id() ^ o));
+    return v;
+}
 static inline int __all_sync(unsigned mask, int pred) {
     return cuemu::warp_ballot(mask, pred == 0) == 0;
 }

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "..", "..", "sprs_b200", "csrc")
 FILES = ["api.cu", "spmv.cu", "spmm.cu", "spgemm.cu", "transpose.cu", "gen.cu", "peer.cu",
          "solver.cu", "csvec.cu", "common.cuh", "scan.cuh", "ptx.cuh"]
-# comm.cu (process rendezvous, CUDA IPC / VMM, device barrier) is not emulated: the multi-rank
+# diag.cu (event-timed measurement aid) and comm.cu (process rendezvous, CUDA IPC / VMM, device barrier) is not emulated: the multi-rank
 # path is covered on hardware by tests/cpp/test_comm_ranks.cpp and tests/test_gpu_comm.py
 
 
