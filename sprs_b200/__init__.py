@@ -12,4 +12,4 @@ from .sparse import (CSC, CSR, Context, CsMat, CsVec, DeviceCsMat, SprsPanic, Th
 __all__ = ["CSC", "CSR", "Context", "CsMat", "CsVec", "DeviceCsMat", "SprsPanic",
            "ThirdPartyError", "csmat_mul_csmat", "prod", "smmp", "_lib", "io", "linalg"]
 __version__ = "0.1.0"
-SPMV_TILE = 256  # nnz per SpMV warp tile (default variant in csrc/spmv.cu); tests use it to find rows cut by a tile
+SPMV_TILE = 1024  # nnz per SpMV warp tile (default variant in csrc/spmv.cu); tests use it to find rows cut by a tile

@@ -71,94 +71,7 @@ __global__ void tile_row_kernel(const P* __restrict__ indptr, uint32_t rows, uin
     tile_row[t] = lo;
 }
 
-constexpr int SPMV_REG_ROWS = 24;  // tiles completing <= this many rows reduce in registers
-
-struct TileCtx {
-    uint64_t k0, k1;
-    uint32_t r1;  // first row NOT owned (== carry row when < rows)
-    double* y;    // this GPU's y (target 0)
-    const SpmvTargets* yt;  // MULTI only: the kernel parameter itself (constant bank)
-    double* carry_slot;
-    int accumulate;
-};
-
-// y[r] is written to every target buffer: target 0 is this GPU's own y; targets 1.. are the
-// peer GPUs' y buffers (CUDA IPC / VMM mappings) or the NVSwitch multicast address of y (fused
-// SpMV + all-gather over NVLink: the result of a row leaves for the peers the moment it is
-// reduced, overlapped with the rest of the kernel, instead of a separate collective afterwards).
-template <bool MULTI>
-__device__ __forceinline__ void emit_row(const TileCtx& tc, uint64_t r, double sum) {
-    if (r < tc.r1) {
-        const double v = tc.accumulate ? __dadd_rn(tc.y[r], sum) : sum;
-        tc.y[r] = v;
-        if (MULTI) {
-#pragma unroll
-            for (int q = 1; q < SPMV_MAX_TARGETS; ++q)
-                if (q < tc.yt->n) tc.yt->p[q][r] = v;
-        }
-    } else {
-        *tc.carry_slot = sum;  // row continues in a later tile: spmv_fixup_kernel adds it
-    }
-}
-
-// Shared-memory path: reduce rows [r0, r_last] of one warp tile with groups of G lanes per
-// row.  Row boundaries come 31 rows at a time: lane L holds indptr[rbase + L].
-template <typename P, int G, bool MULTI>
-__device__ __forceinline__ void reduce_rows_warp(const TileCtx& tc, const P* __restrict__ indptr,
-                                                 const double* sprod, uint32_t r0,
-                                                 uint64_t r_last, uint64_t b_first, int lane) {
-    constexpr int NG = 32 / G;
-    const int gid = lane / G, gl = lane % G;
-    uint64_t b = b_first;  // boundaries of the first chunk were prefetched by the caller
-    for (uint64_t rbase = r0; rbase <= r_last; rbase += 31) {
-        if (rbase != r0) {
-            const uint64_t rr = rbase + lane;
-            b = rr <= r_last + 1 ? (uint64_t)indptr[rr] : 0;
-        }
-        const int nrows = (r_last - rbase + 1) < 31 ? (int)(r_last - rbase + 1) : 31;
-        for (int j0 = 0; j0 < nrows; j0 += NG) {
-            const int j = j0 + gid;
-            const bool valid = j < nrows;
-            const int js = valid ? j : 0;
-            uint64_t s = __shfl_sync(0xffffffffu, b, js);
-            uint64_t e = __shfl_sync(0xffffffffu, b, js + 1);
-            int ls = 0, le = 0;
-            s = s > tc.k0 ? s : tc.k0;
-            e = e < tc.k1 ? e : tc.k1;
-            if (valid && e > s) {
-                ls = (int)(s - tc.k0);
-                le = (int)(e - tc.k0);
-            }
-            const bool is_long = (G < 32) && (le - ls) > 16 * G;
-            double acc = 0.0;
-            if (!is_long)
-                for (int q = ls + gl; q < le; q += G) acc = __dadd_rn(acc, sprod[q]);
-#pragma unroll
-            for (int o = G / 2; o > 0; o >>= 1)
-                acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-            if (gl == 0 && valid && !is_long) emit_row<MULTI>(tc, rbase + j, acc);
-            if (G < 32) {  // rows too long for their group: the whole warp takes them
-                unsigned pending = __ballot_sync(0xffffffffu, gl == 0 && valid && is_long);
-                while (pending) {
-                    const int src = __ffs(pending) - 1;
-                    pending &= pending - 1;
-                    const int qs = __shfl_sync(0xffffffffu, ls, src);
-                    const int qe = __shfl_sync(0xffffffffu, le, src);
-                    const int jj = __shfl_sync(0xffffffffu, j, src);
-                    double a2 = 0.0;
-                    for (int q = qs + lane; q < qe; q += 32) a2 = __dadd_rn(a2, sprod[q]);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1)
-                        a2 = __dadd_rn(a2, __shfl_xor_sync(0xffffffffu, a2, o));
-                    if (lane == 0) emit_row<MULTI>(tc, rbase + jj, a2);
-                }
-            }
-        }
-    }
-}
-
-// What the row emitters need, by value (they are real functions, not inlined: the hot loop stays
-// small enough for the instruction cache).
+// What the row emitters need.
 struct RowSink {
     double* y;                  // this GPU's y (target 0)
     const SpmvTargets* yt;      // MULTI only: the kernel parameter itself (constant bank)
@@ -166,6 +79,10 @@ struct RowSink {
     uint32_t r1;                // first row NOT owned by the tile (== its carry row when < rows)
     int accumulate;
 };
+// y[r] is written to every target buffer: target 0 is this GPU's own y; targets 1.. are the
+// peer GPUs' y buffers (CUDA IPC / VMM mappings) or the NVSwitch multicast address of y (fused
+// SpMV + all-gather over NVLink: the result of a row leaves for the peers the moment it is
+// reduced, overlapped with the rest of the kernel, instead of a separate collective afterwards).
 template <bool MULTI>
 __device__ __forceinline__ void sink_row(const RowSink& k, uint64_t r, double sum) {
     if (r < k.r1) {
@@ -181,229 +98,160 @@ __device__ __forceinline__ void sink_row(const RowSink& k, uint64_t r, double su
     }
 }
 
-// Register path, second half: up to four finished rows sit as per-lane partials in s0..s3
-// (row_base + 0..3).  One multi-value butterfly reduces them together: xor 16 halves the live
-// values (lanes with bit 4 clear keep rows 0,1, the others rows 2,3), xor 8 halves again, xor
-// 4/2/1 finish: 6 double shuffles for 4 rows instead of 20.  Lane 8*j ends up with row j.
-template <bool MULTI>
-__device__ __noinline__ void flush_slots(RowSink k, double s0, double s1, double s2, double s3,
-                                         uint32_t row_base, int n, int lane) {
+// Rows [r0, r_last] of one warp tile [k0, k1), G lanes per row (32/G rows at a time): every
+// group walks ITS row's part of the tile with stride G, straight from global memory -- index,
+// value (coalesced inside the group, L1::no_allocate, L2 evict_first) and the x gather (L2
+// evict_last), U of each in flight per lane -- adds its products in storage order, and one
+// G-lane butterfly finishes the row.  Nothing is staged and nothing but the row sum crosses
+// lanes: ~0.5 instructions per non-zero, against ~1.5 for reducing products staged in shared
+// memory or registers (profiles/r2_spmv_notes.md).  G = 1: one lane sums a whole row in
+// storage order, i.e. the reference's bits.  Row boundaries come 31 rows at a time: lane L
+// holds indptr[rbase + L].
+template <typename P, int G, bool MULTI>
+__device__ __forceinline__ void rows_direct(const RowSink& k, const P* __restrict__ indptr,
+                                            const uint32_t* __restrict__ indices,
+                                            const double* __restrict__ data,
+                                            const double* __restrict__ x, P k0, P k1,
+                                            uint32_t r0, uint32_t r_last, P b_first,
+                                            uint64_t pol_stream, uint64_t polx, int lane) {
+    constexpr int NG = 32 / G;
+    constexpr int U = 4;  // loads in flight per lane and kind
     constexpr unsigned FULL = 0xffffffffu;
-    const bool up16 = lane & 16, up8 = lane & 8;
-    const double a0 = __dadd_rn(up16 ? s2 : s0, __shfl_xor_sync(FULL, up16 ? s0 : s2, 16));
-    const double a1 = __dadd_rn(up16 ? s3 : s1, __shfl_xor_sync(FULL, up16 ? s1 : s3, 16));
-    double v = __dadd_rn(up8 ? a1 : a0, __shfl_xor_sync(FULL, up8 ? a0 : a1, 8));
-    v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 4));
-    v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 2));
-    v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 1));
-    const int row = lane >> 3;  // 2*bit4 + bit3
-    if ((lane & 7) == 0 && row < n) sink_row<MULTI>(k, (uint64_t)row_base + row, v);
-}
-
-// Register path: the tile's EPL products per lane (element e = lane + 32*i, i.e. register i is
-// the "slab" of 32 consecutive non-zeros 32*i .. 32*i+31) are folded into row sums without
-// leaving the registers.  ends: lane L in 1..nrc holds the tile-local END of row r0+L-1, in
-// [0, WT]; nrc rows end inside the tile, what is left after the last end belongs to row r0+nrc
-// (the tile's carry) when has_tail.  All control flow is warp-uniform AND known to be: the
-// slab mask comes from a warp reduction (REDUX), row counts from ballots, so the branches cost
-// no divergence bookkeeping.  A slab without a row end costs one add.
-template <int EPL, bool MULTI>
-__device__ __forceinline__ void reduce_rows_slots(const RowSink& k, const double (&p)[EPL],
-                                                  int end_local, uint32_t r0, int nrc, bool has_tail,
-                                                  int lane) {
-    constexpr unsigned FULL = 0xffffffffu;
-    const bool is_end = lane >= 1 && lane <= nrc;
-    // slab that holds the row's last element (end 0 = an empty row at the very start: slab 0)
-    const int sb = end_local > 0 ? (end_local - 1) >> 5 : 0;
-    const int q = end_local - 32 * sb;  // lanes < q of slab sb belong to the row (0 .. 32)
-    const unsigned slabs = __reduce_or_sync(FULL, is_end ? 1u << sb : 0u);
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, acc = 0.0;
-    int j = 0;
-    uint32_t row_base = r0;
-#define SPMV_PARK(val)                                                  \
-    do {                                                                \
-        const double v_ = (val);                                        \
-        if (j == 0) s0 = v_;                                            \
-        else if (j == 1) s1 = v_;                                       \
-        else if (j == 2) s2 = v_;                                       \
-        else s3 = v_;                                                   \
-        if (++j == 4) {                                                 \
-            flush_slots<MULTI>(k, s0, s1, s2, s3, row_base, 4, lane);   \
-            row_base += 4;                                              \
-            j = 0;                                                      \
-        }                                                               \
-    } while (0)
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-        double pi = p[i];
-        if ((slabs >> i) & 1u) {  // rows end inside this slab: consecutive boundary lanes
-            const unsigned m = __ballot_sync(FULL, is_end && sb == i);
-            const int first = __ffs(m) - 1, cnt = __popc(m);
-            for (int c = 0; c < cnt; ++c) {
-                const bool mine = lane < __shfl_sync(FULL, q, first + c);
-                SPMV_PARK(__dadd_rn(acc, mine ? pi : 0.0));
-                pi = mine ? 0.0 : pi;
-                acc = 0.0;
-            }
+    const int gid = lane / G, gl = lane % G;
+    // (offsets are as wide as the indptr: 32 bits unless nnz >= 2^32; row indices are 32-bit)
+    P b = b_first;  // boundaries of the first chunk were prefetched by the caller
+    for (uint32_t rbase = r0;; rbase += 31) {
+        if (rbase != r0) {
+            const uint32_t rr = rbase + lane;  // r_last + 1 <= rows < 2^32: no wrap for rr <= r_last + 1
+            b = (rr >= rbase && rr <= r_last + 1) ? indptr[rr] : (P)0;
         }
-        acc = __dadd_rn(acc, pi);
+        const int nrows = (r_last - rbase + 1) < 31 ? (int)(r_last - rbase + 1) : 31;
+        for (int j0 = 0; j0 < nrows; j0 += NG) {
+            const int j = j0 + gid;
+            const bool valid = j < nrows;
+            const int js = valid ? j : 0;
+            P s = __shfl_sync(FULL, b, js);
+            P e = __shfl_sync(FULL, b, js + 1);
+            s = s > k0 ? s : k0;
+            e = e < k1 ? e : k1;
+            if (!valid || e < s) e = s;
+            // a row much longer than its group would serialise the warp behind G lanes: such
+            // rows (a hub row inside a tile of short rows) are taken by the whole warp below
+            const bool is_long = (G < 32) && (e - s) > (P)(16 * G * U);
+            double acc = 0.0;
+            for (P q = s + gl; q < (is_long ? s : e); q += (P)(G * U)) {
+                uint32_t c[U];
+                double v[U], xv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    c[u] = q + (P)(u * G) < e ? ldg_stream_u32(indices + q + (P)(u * G), pol_stream) : 0u;
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    v[u] = q + (P)(u * G) < e ? ldg_stream_f64(data + q + (P)(u * G), pol_stream) : 0.0;
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    xv[u] = q + (P)(u * G) < e ? ldg_f64_hint(x + c[u], polx) : 0.0;
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (q + (P)(u * G) < e) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(FULL, acc, o));
+            if (G < 32) {
+                unsigned pending = __ballot_sync(FULL, gl == 0 && is_long);
+                while (pending) {
+                    const int src = __ffs(pending) - 1;
+                    pending &= pending - 1;
+                    const P qs = __shfl_sync(FULL, s, src), qe = __shfl_sync(FULL, e, src);
+                    const int jj = __shfl_sync(FULL, j, src);
+                    double a2 = 0.0;
+                    for (P q = qs + lane; q < qe; q += (P)(32 * U)) {
+                        uint32_t c[U];
+                        double v[U], xv[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            c[u] = q + (P)(u * 32) < qe ? ldg_stream_u32(indices + q + (P)(u * 32), pol_stream) : 0u;
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            v[u] = q + (P)(u * 32) < qe ? ldg_stream_f64(data + q + (P)(u * 32), pol_stream) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            xv[u] = q + (P)(u * 32) < qe ? ldg_f64_hint(x + c[u], polx) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            if (q + (P)(u * 32) < qe) a2 = __dadd_rn(a2, __dmul_rn(v[u], xv[u]));
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) a2 = __dadd_rn(a2, __shfl_xor_sync(FULL, a2, o));
+                    if (lane == 0) sink_row<MULTI>(k, (uint64_t)rbase + jj, a2);
+                }
+            }
+            if (gl == 0 && valid && !is_long) sink_row<MULTI>(k, (uint64_t)rbase + j, acc);
+        }
+        if (r_last - rbase < 31) break;  // (also ends the loop when rbase + 31 would wrap)
     }
-    if (has_tail) SPMV_PARK(acc);  // row r0+nrc >= r1: sink_row files it as the tile's carry
-    if (j > 0) flush_slots<MULTI>(k, s0, j > 1 ? s1 : 0.0, j > 2 ? s2 : 0.0, 0.0, row_base, j, lane);
-#undef SPMV_PARK
 }
 
-// Shared-memory path (tiles with many rows, and the ragged last tile): products are in the
-// warp's buffer; rows are reduced by lane groups sized to the tile's mean row length.
-template <typename P, bool MULTI>
-__device__ __noinline__ void reduce_rows_smem(RowSink k, const P* __restrict__ indptr,
-                                              const double* sprod, uint64_t k0, uint64_t k1,
-                                              uint32_t r0, uint32_t rows, uint64_t b_first, int lane) {
-    TileCtx tc;
-    tc.k0 = k0;
-    tc.k1 = k1;
-    tc.r1 = k.r1;
-    tc.y = k.y;
-    tc.yt = k.yt;
-    tc.carry_slot = k.carry_slot;
-    tc.accumulate = k.accumulate;
-    const uint64_t r_last = k.r1 < rows ? (uint64_t)k.r1 : (uint64_t)k.r1 - 1;
-    const uint64_t cnt = k1 - k0, nr = r_last - r0 + 1;
-    if (cnt <= 6 * nr)
-        reduce_rows_warp<P, 1, MULTI>(tc, indptr, sprod, r0, r_last, b_first, lane);
-    else if (cnt <= 12 * nr)
-        reduce_rows_warp<P, 2, MULTI>(tc, indptr, sprod, r0, r_last, b_first, lane);
-    else
-        reduce_rows_warp<P, 4, MULTI>(tc, indptr, sprod, r0, r_last, b_first, lane);
-}
-
-template <typename P, int EPL, int NWARPS, int MINB, bool MULTI>
+template <typename P, int WT, int NWARPS, int MINB, bool MULTI>
 __global__ void __launch_bounds__(NWARPS * 32, MINB)
-    spmv_pipe_kernel(const P* __restrict__ indptr, const uint32_t* __restrict__ indices,
+    spmv_rows_kernel(const P* __restrict__ indptr, const uint32_t* __restrict__ indices,
                      const double* __restrict__ data, const uint32_t* __restrict__ tile_row,
                      const double* __restrict__ x, const __grid_constant__ SpmvTargets yt,
                      double* __restrict__ carry, uint64_t nnz, uint32_t rows, uint32_t t_begin,
                      uint32_t t_end /* this launch covers tiles [t_begin, t_end) */, int accumulate,
                      uint64_t pol_stream /* L2 evict_first */, uint64_t polx /* L2 evict_last */) {
-    constexpr int WT = EPL * 32;
-    using OFF = P;  // element offsets: 32 bits wide when the indptr is (nnz < 2^32)
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // (the two L2 policies are kernel PARAMETERS: warp-uniform by construction, so they live in
+    // uniform registers; as per-thread createpolicy results every hinted load re-materialised
+    // its descriptor)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* sprod = (double*)smem_raw + (size_t)warp * WT;  // many-row tiles only
     const uint32_t GW = gridDim.x * NWARPS;
-    uint32_t t = t_begin + blockIdx.x * NWARPS + warp;
-    // tiles below n_full are whole: the hot loop never guards a load.  The ragged tail (at most
-    // one tile, index n_full) is handled after the loop by the warp the deal gives it to.
-    const uint32_t n_full = (uint32_t)(nnz / WT);
-    const uint32_t t_hot_end = t_end < n_full ? t_end : n_full;
-    // (the two L2 policies are kernel PARAMETERS: values the compiler knows to be warp-uniform
-    // go into uniform registers once; as per-thread createpolicy results every hinted load
-    // re-materialised its descriptor -- 32 extra instructions per tile)
     RowSink sink;
     sink.y = yt.p[0];
     sink.yt = &yt;
     sink.accumulate = accumulate;
-
-    if (t < t_hot_end) {
-        uint32_t c[EPL];
-        double xn[EPL], vn[EPL];
-        // prologue: tile t fully issued, tile t+GW's indices and row range on their way
-        uint32_t tn = t + GW;
-        uint32_t r0 = tile_row[t], r1 = tile_row[t + 1];
+    uint32_t t = t_begin + blockIdx.x * NWARPS + warp;
+    if (t >= t_end) return;
+    // row range and the first 32 row boundaries of a tile are fetched ONE TILE AHEAD
+    uint32_t r0 = tile_row[t], r1 = tile_row[t + 1];
+    // lane L: indptr[r0 + L] while r0 + L <= r_last + 1 (r_last + 1 <= rows: always in range)
+    P b_first = (uint64_t)r0 + lane <= (r1 < rows ? (uint64_t)r1 + 1 : (uint64_t)r1)
+                    ? indptr[(size_t)r0 + lane] : (P)0;
+    for (;;) {
+        const uint32_t tn = t + GW;
         uint32_t r0n = 0, r1n = 0;
-        if (tn < t_hot_end) {
+        if (tn < t_end) {
             r0n = tile_row[tn];
             r1n = tile_row[tn + 1];
         }
-        {
-            const uint32_t* ip = indices + (OFF)t * WT + lane;
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) c[i] = ldg_stream_u32(ip + 32 * i, pol_stream);
-        }
-        // lane L: indptr[r0 + L] (L <= rows ending in the tile, +1 when a row continues)
-        P b_first = (r0 + lane <= (r1 < rows ? r1 + 1 : r1)) ? indptr[(size_t)r0 + lane] : (P)0;
-        {
-            const double* dp = data + (OFF)t * WT + lane;
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) xn[i] = ldg_f64_hint(x + c[i], polx);
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) vn[i] = ldg_stream_f64(dp + 32 * i, pol_stream);
-        }
-        if (tn < t_hot_end) {
-            const uint32_t* ip = indices + (OFF)tn * WT + lane;
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) c[i] = ldg_stream_u32(ip + 32 * i, pol_stream);
-        }
-        for (;;) {
-            // products of tile t (its gathers and values were issued one iteration ago)
-            double p[EPL];
-#pragma unroll
-            for (int i = 0; i < EPL; ++i) p[i] = __dmul_rn(vn[i], xn[i]);
-            // tile t+GW: gathers + values in flight while tile t is reduced; then the indices of
-            // the tile after that, its row range, and the row boundaries of tile t+GW
-            const uint32_t tnn = tn + GW;
-            uint32_t r0nn = 0, r1nn = 0;
-            P b_next = 0;
-            if (tn < t_hot_end) {
-                const double* dp = data + (OFF)tn * WT + lane;
-#pragma unroll
-                for (int i = 0; i < EPL; ++i) xn[i] = ldg_f64_hint(x + c[i], polx);
-#pragma unroll
-                for (int i = 0; i < EPL; ++i) vn[i] = ldg_stream_f64(dp + 32 * i, pol_stream);
-                b_next = (r0n + lane <= (r1n < rows ? r1n + 1 : r1n)) ? indptr[(size_t)r0n + lane] : (P)0;
-                if (tnn < t_hot_end) {
-                    const uint32_t* ip = indices + (OFF)tnn * WT + lane;
-#pragma unroll
-                    for (int i = 0; i < EPL; ++i) c[i] = ldg_stream_u32(ip + 32 * i, pol_stream);
-                    r0nn = tile_row[tnn];
-                    r1nn = tile_row[tnn + 1];
-                }
-            }
-            const OFF k0 = (OFF)t * WT;
-            sink.carry_slot = carry + t;
-            sink.r1 = r1;
-            const uint32_t nrc = r1 - r0;  // rows that END in this tile
-            const bool has_tail = r1 < rows;
-            // mean row length <= 6 keeps the one-lane-per-row path (storage order: the
-            // reference's bits); more than 24 row ends do not fit the boundary lanes
-            if (nrc <= (uint32_t)SPMV_REG_ROWS && (uint32_t)WT > 6u * (nrc + (has_tail ? 1u : 0u))) {
-                int end_local = 0;  // lane L in 1..nrc: end of row r0+L-1, clamped to the tile
-                if (lane <= (int)nrc) {
-                    const P bb = b_first > k0 ? (P)(b_first - k0) : (P)0;
-                    end_local = bb < (P)WT ? (int)bb : WT;
-                }
-                reduce_rows_slots<EPL, MULTI>(sink, p, end_local, r0, (int)nrc, has_tail, lane);
-            } else {
-#pragma unroll
-                for (int i = 0; i < EPL; ++i) sprod[lane + 32 * i] = p[i];
-                __syncwarp();
-                reduce_rows_smem<P, MULTI>(sink, indptr, sprod, (uint64_t)k0, (uint64_t)k0 + WT, r0,
-                                           rows, (uint64_t)b_first, lane);
-                __syncwarp();
-            }
-            t = tn;
-            if (tn >= t_hot_end) break;
-            tn = tnn;
-            r0 = r0n;
-            r1 = r1n;
-            r0n = r0nn;
-            r1n = r1nn;
-            b_first = b_next;
-        }
-    }
-    // the ragged tail tile (or the single empty tile of a matrix without non-zeros)
-    if (t == n_full && t < t_end) {
-        const uint64_t k0 = (uint64_t)t * WT;
-        const uint32_t r0 = tile_row[t], r1 = tile_row[t + 1];
-        for (uint64_t e = k0 + lane; e < nnz; e += 32)
-            sprod[e - k0] = __dmul_rn(data[e], ldg_f64_hint(x + indices[e], polx));
-        __syncwarp();
+        const uint64_t k0w = (uint64_t)t * WT;
+        const P k0 = (P)k0w, k1 = (P)(k0w + WT < nnz ? k0w + WT : nnz);
         sink.carry_slot = carry + t;
         sink.r1 = r1;
-        const uint64_t rl = r1 < rows ? (uint64_t)r1 : (uint64_t)r1 - 1;
-        const uint64_t rr = (uint64_t)r0 + lane;
-        const uint64_t b_first = rr <= rl + 1 ? (uint64_t)indptr[rr] : 0;
-        reduce_rows_smem<P, MULTI>(sink, indptr, sprod, k0, nnz, r0, rows, b_first, lane);
+        const uint32_t r_last = r1 < rows ? r1 : r1 - 1;
+        const uint64_t cnt = k1 - k0, nr = (uint64_t)(r_last - r0) + 1;  // mean row length = cnt / nr
+#define SPMV_ROWS(G)                                                                            \
+    rows_direct<P, G, MULTI>(sink, indptr, indices, data, x, k0, k1, r0, r_last, b_first,       \
+                             pol_stream, polx, lane)
+        if (cnt <= 6 * nr)
+            SPMV_ROWS(1);
+        else if (cnt <= 12 * nr)
+            SPMV_ROWS(2);
+        else if (cnt <= 24 * nr)
+            SPMV_ROWS(4);
+        else if (cnt <= 48 * nr)
+            SPMV_ROWS(8);
+        else if (cnt <= 96 * nr)
+            SPMV_ROWS(16);
+        else
+            SPMV_ROWS(32);
+#undef SPMV_ROWS
+        if (tn >= t_end) break;
+        const P b_next = (uint64_t)r0n + lane <= (r1n < rows ? (uint64_t)r1n + 1 : (uint64_t)r1n)
+                             ? indptr[(size_t)r0n + lane] : (P)0;
+        t = tn;
+        r0 = r0n;
+        r1 = r1n;
+        b_first = b_next;
     }
 }
 
@@ -480,14 +328,14 @@ __global__ void spmv_fixup_range_kernel(const uint32_t* __restrict__ tile_row, c
 
 // ---- launch configuration ---------------------------------------------------------
 struct SpmvVariant {
-    int epl, ctas_per_sm;
+    int wt, ctas_per_sm;
 };
 // default picked from the round-2 sweeps (profiles/r2_spmv_notes.md);
-// SPRS_B200_SPMV_VARIANT="epl,ctas" overrides it for tuning runs (read once per process: the
-// tile size 32*epl is baked into every mirror's tile_row).
+// SPRS_B200_SPMV_VARIANT="wt,ctas" overrides it for tuning runs (read once per process: the
+// tile size is baked into every mirror's tile_row).
 SpmvVariant spmv_variant() {
     static SpmvVariant v = [] {
-        SpmvVariant d{8, 2};
+        SpmvVariant d{1024, 6};
         if (const char* e = getenv("SPRS_B200_SPMV_VARIANT")) {
             int a, b;
             if (sscanf(e, "%d,%d", &a, &b) == 2) d = SpmvVariant{a, b};
@@ -499,29 +347,24 @@ SpmvVariant spmv_variant() {
 
 constexpr int SPMV_NWARPS = 8;
 
-template <typename P, int EPL, int CTAS>
+template <typename P, int WT, int CTAS>
 int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
                    const SpmvTargets& yt, int accumulate, uint64_t t0, uint64_t t1,
                    cudaStream_t s) {
     if (m->n_tiles >= 0xffffffffull)
         SPRS_FAIL(ctx, SPRS_B200_ERR_UNSUPPORTED, "spmv: more than 2^32 tiles");
     // CTAS resident CTAs per SM is also the kernel's __launch_bounds__ minBlocks: it sets the
-    // register budget of the pipelined operand buffers.
+    // register budget (the kernel hides latency with warps, not with registers).
     const bool multi = yt.n > 1;
-    auto kern = multi ? spmv_pipe_kernel<P, EPL, SPMV_NWARPS, CTAS, true>
-                      : spmv_pipe_kernel<P, EPL, SPMV_NWARPS, CTAS, false>;
-    const size_t smem = (size_t)SPMV_NWARPS * EPL * 32 * 8;
+    auto kern = multi ? spmv_rows_kernel<P, WT, SPMV_NWARPS, CTAS, true>
+                      : spmv_rows_kernel<P, WT, SPMV_NWARPS, CTAS, false>;
     static bool configured_flags[64][2] = {};  // function attributes are per device
     bool& configured = configured_flags[ctx->device & 63][multi ? 1 : 0];
     if (!configured) {
-        SPRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
-        // Shared-memory carve-out = exactly what CTAS resident CTAs need, everything else stays
-        // L1: every in-flight gather holds an L1 line, so the gather rate is bounded by
-        // L1 lines / L2 latency (lab carve sweep: 0 % 303, 50 % 275, 100 % 106 Gnnz/s).
-        int carve = (int)(((smem + 1024) * CTAS * 100 + 228 * 1024 - 1) / (228 * 1024));
+        // no shared memory at all: the whole unified array is L1 for the gathers (every
+        // in-flight gather holds an L1 line; lab carve sweep: 0 % 303, 50 % 275, 100 % 106 Gnnz/s)
+        int carve = 0;
         if (const char* e = getenv("SPRS_B200_SPMV_CARVEOUT")) carve = atoi(e);
-        if (carve > 100) carve = 100;
         SPRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                             carve));
         configured = true;
@@ -529,11 +372,11 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
     uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
     const uint64_t need = (t1 - t0 + SPMV_NWARPS - 1) / SPMV_NWARPS;
     if (grid > need) grid = need;
-    kern<<<(unsigned)grid, SPMV_NWARPS * 32, smem, s>>>((const P*)m->d_indptr, m->d_indices,
-                                                        m->d_data, m->d_tile_row, d_x, yt,
-                                                        m->d_carry, m->nnz, (uint32_t)m->rows,
-                                                        (uint32_t)t0, (uint32_t)t1, accumulate,
-                                                        ctx->pol_evict_first, ctx->pol_evict_last);
+    kern<<<(unsigned)grid, SPMV_NWARPS * 32, 0, s>>>((const P*)m->d_indptr, m->d_indices,
+                                                     m->d_data, m->d_tile_row, d_x, yt, m->d_carry,
+                                                     m->nnz, (uint32_t)m->rows, (uint32_t)t0,
+                                                     (uint32_t)t1, accumulate, ctx->pol_evict_first,
+                                                     ctx->pol_evict_last);
     return SPRS_B200_OK;
 }
 
@@ -542,15 +385,15 @@ int launch_dispatch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* 
                     const SpmvTargets& yt, int accumulate, uint64_t t0, uint64_t t1,
                     cudaStream_t s) {
     const SpmvVariant v = spmv_variant();
-#define SPMV_CASE(E, CT)                                                          \
-    if (v.epl == E && v.ctas_per_sm == CT)                                        \
-        return launch_variant<P, E, CT>(ctx, m, d_x, yt, accumulate, t0, t1, s);
-    SPMV_CASE(8, 2)
-    SPMV_CASE(6, 3)
-    SPMV_CASE(10, 2)
-    SPMV_CASE(12, 2)
+#define SPMV_CASE(W, CT)                                                          \
+    if (v.wt == W && v.ctas_per_sm == CT)                                         \
+        return launch_variant<P, W, CT>(ctx, m, d_x, yt, accumulate, t0, t1, s);
+    SPMV_CASE(1024, 6)
+    SPMV_CASE(1024, 5)
+    SPMV_CASE(1024, 4)
+    SPMV_CASE(512, 6)
 #undef SPMV_CASE
-    SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "unknown SPRS_B200_SPMV_VARIANT (epl,ctas)");
+    SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "unknown SPRS_B200_SPMV_VARIANT (wt,ctas)");
 }
 
 int check_spmv_args(sprs_b200_ctx* ctx, const sprs_b200_csmat* m) {
@@ -562,7 +405,7 @@ int check_spmv_args(sprs_b200_ctx* ctx, const sprs_b200_csmat* m) {
 
 }  // namespace
 
-int spmv_tile_nnz() { return 32 * spmv_variant().epl; }
+int spmv_tile_nnz() { return spmv_variant().wt; }
 
 int spmv_prepare(sprs_b200_ctx* ctx, sprs_b200_csmat* m, cudaStream_t s) {
     if (m->storage != SPRS_B200_CSR) return SPRS_B200_OK;  // CSC mirrors are converted first

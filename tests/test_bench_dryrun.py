@@ -23,7 +23,9 @@ class _FakeEvent:
 
 
 class _FakeMirror:
-    h = None
+    @property
+    def h(self):
+        return self
 
 
 class _FakeCsr:
@@ -48,7 +50,18 @@ class _FakeLib:
         self.ctx = ctx
 
     def sprs_b200_mul_mat_vec(self, h, mh, xp, n, yp, rows):
+        # y = A x into the caller's (fake-pinned) host buffer, like the real call
+        from sprs_b200.dist import tensor_view
+        a = mh.owner if hasattr(mh, "owner") else None
         self.ctx.launches += 2
+        if a is not None:
+            x = tensor_view(xp.value, n, "cpu")
+            tensor_view(yp.value, rows, "cpu").copy_(torch.from_numpy(a.m @ x.numpy()))
+        return 0
+
+    def sprs_b200_diag_gather_ceiling(self, h, mh, xp, iters, ms_ref, cov_ref):
+        ms_ref._obj.value = 0.5
+        cov_ref._obj.value = 1000
         return 0
 
 
@@ -127,6 +140,10 @@ def test_bench_n1_contract_keys(fake_gpu, monkeypatch, capsys):
     assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] > 0
     assert line["gpu_launches"] == 2 * 3
     assert "spmv_rand_1m" in line["extra"]
+    par = line["parity_vs_oracle"]
+    assert par["ok"] and par["max_error_over_gate"] <= 1.0 and par["rows_checked_per_rank"] > 1000
+    assert line["e2e"]["matches_device_result"]
+    assert line["roofline"]["gather_ceiling"]["gnnz_s"] > 0 and "frac_of_gather_ceiling" in line["roofline"]
 
 
 def test_bench_flags(fake_gpu, monkeypatch, capsys):
@@ -135,17 +152,19 @@ def test_bench_flags(fake_gpu, monkeypatch, capsys):
     assert line["warmup"] >= 3  # W >= 3 whatever the flag says
 
 
-# ---- tools/scale_modes.py (all exchange modes in one multi-GPU launch): control-flow dry run
-def _scale_modes_worker(rank, world, port, q):
+
+# ---- N > 1 control flow on two gloo ranks with the GPU pieces faked: the library's
+#      communicator is replaced by a gloo-backed stand-in with the same Python face
+#      (sprs_b200.dist.Comm / CommSpMV / CommHostSpMV), so that bench.py's and
+#      tools/scale_modes.py's multi-rank Python (partition calibration, re-cuts, oracle parity on
+#      every rank, the e2e slices, the JSON lines) runs where no GPU is attached.
+def _install_fakes(rank, world, port):
     import os
-    import socket  # noqa: F401
     ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
-                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
-    import io
-    import contextlib
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank), SPRS_BENCH_NO_SAMPLER="1")
     import torch.distributed as dist
     import sprs_b200
     from sprs_b200 import dist as D
@@ -156,6 +175,7 @@ def _scale_modes_worker(rank, world, port, q):
     torch.cuda.synchronize = lambda *a: None
     torch.cuda.empty_cache = lambda: None
     torch.cuda.Event = _FakeEvent
+    torch.Tensor.pin_memory = lambda self: self
     real_init = dist.init_process_group
     dist.init_process_group = lambda backend, **k: real_init("gloo")
     ctx = _FakeCtx()
@@ -167,29 +187,134 @@ def _scale_modes_worker(rank, world, port, q):
                                    data_rvs=rng.standard_normal))
 
     def spmv(c, a, x, y, accumulate=False):
+        c.launches += 2
         y.copy_(torch.from_numpy(a.m @ x.numpy()))
         return y
 
     G.make_matrix, G.spmv = make_matrix, spmv
     G.normal_vector = lambda c, n, seed=1: torch.from_numpy(np.random.default_rng(seed).standard_normal(n))
 
-    class FakePeerOp(D.RowPartitionedSpMV):  # stands in for every peer-buffer exchange class
-        def __init__(self, c, mirror, bounds, rank, world, n, dist_, device, **kw):
-            if kw.get("mode") == "chunked" and kw.get("barrier") == "symm":
-                raise RuntimeError("pretend this combination is unavailable")  # the skip path
-            blk = mirror.owner
-            super().__init__(bounds, rank, world, torch.zeros(n, dtype=torch.float64),
-                             lambda xv, ys: spmv(c, blk, xv, ys), dist=dist_)
+    class FakeComm:
+        multicast = False
+
+        @staticmethod
+        def unique_id(c=None):
+            return b"dryrun".ljust(64, b"\0")
+
+        def __init__(self, c, comm_id, rank_, world_):
+            assert len(comm_id) == 64
+            self.ctx, self.rank, self.world = c, rank_, world_
+
+        def allgather(self, record):
+            out = [None] * self.world
+            dist.all_gather_object(out, record)
+            return out
+
+        def allgather_f64(self, values):
+            rec = np.asarray(values, dtype=np.float64).tobytes()
+            return np.stack([np.frombuffer(r, dtype=np.float64) for r in self.allgather(rec)])
+
+        def barrier_host(self):
+            dist.barrier()
+
+        def barrier_dev(self, stream=None):
+            dist.barrier()
+
+        def check(self, stream=None):
+            pass
 
         def close(self):
             pass
 
-    for name in ("PushAllGatherSpMV", "FusedAllGatherSpMV", "StreamAllGatherSpMV",
-                 "ChunkedPushAllGatherSpMV", "McastAllGatherSpMV"):
-        setattr(D, name, FakePeerOp)
+    class FakeCommSpMV(D.RowPartitionedSpMV):
+        def __init__(self, comm, mirror, bounds, n, device, exchange="auto", multicast=True):
+            assert exchange in D.EXCHANGES
+            blk = mirror.owner
+            self.multicast = False
+            super().__init__(bounds, comm.rank, comm.world, torch.zeros(n, dtype=torch.float64),
+                             lambda xv, ys: spmv(comm.ctx, blk, xv, ys), dist=dist)
+
+        def close(self):
+            pass
+
+    class _FakeX:
+        multicast_ptr = 0
+
+    class FakeCommHostSpMV:
+        def __init__(self, comm, mirror, bounds, n, multicast=True):
+            self.comm, self.blk, self.bounds, self.n, self.x = comm, mirror.owner, bounds, n, _FakeX()
+
+        def step(self, x_ptr, y_ptr):
+            r0, r1 = self.bounds[self.comm.rank], self.bounds[self.comm.rank + 1]
+            xs = D.tensor_view(x_ptr, max(r1 - r0, 1), "cpu")[:r1 - r0]
+            parts = [None] * self.comm.world
+            dist.all_gather_object(parts, xs.numpy().copy())
+            xf = np.concatenate(parts)
+            D.tensor_view(y_ptr, max(r1 - r0, 1), "cpu")[:r1 - r0].copy_(torch.from_numpy(self.blk.m @ xf))
+
+        def close(self):
+            pass
+
+    D.Comm, D.CommSpMV, D.CommHostSpMV = FakeComm, FakeCommSpMV, FakeCommHostSpMV
+    return ctx
+
+
+def _bench_n2_worker(rank, world, port, q, exchange):
+    import contextlib
+    import io
+    _install_fakes(rank, world, port)
+    import bench
+    bench.WORKLOADS["spmv_rmat_10m"] = ("spmv", 3000, 10, "rmat")
+    sys.argv = ["bench.py", "--gpus", "2", "--steps", "2", "--warmup", "3", "--no-cpu-baseline",
+                "--no-extra", "--exchange", exchange]
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        bench.main()
+    q.put((rank, buf.getvalue()))
+
+
+def _spawn2(target, extra=()):
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=target, args=(r, 2, port, q) + tuple(extra)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return res
+
+
+@pytest.mark.parametrize("exchange", ["auto", "nccl"])
+def test_bench_n2_control_flow_gloo(exchange):
+    res = _spawn2(_bench_n2_worker, (exchange,))
+    lines = [l for l in res[0].splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and res[1].strip() == ""       # rank 0 alone reports
+    line = json.loads(lines[0])
+    for k in REQUIRED:
+        assert k in line, k
+    assert line["n_gpus"] == 2 and line["scaling"] == "strong"
+    par = line["parity_vs_oracle"]
+    assert par["ok"] and par["rows_checked_per_rank"] > 1500 and par["max_error_over_gate"] <= 1.0
+    e2e = line["e2e"]
+    assert e2e["matches_device_result"] and e2e["h2d_bytes_per_step"] == 8 * 3000 == e2e["d2h_bytes_per_step"]
+    assert len(line["roofline"]["kernel_ms_per_rank"]) == 2
+    assert ("NCCL" in line["config"]["collective"]) == (exchange == "nccl")
+
+
+def _scale_modes_worker(rank, world, port, q):
+    import contextlib
+    import io
+    _install_fakes(rank, world, port)
     import scale_modes
     sys.argv = ["scale_modes.py", "--n", "3000", "--npr", "10", "--steps", "2", "--warmup", "1",
-                "--modes", "push fused nccl mcast-push mcast-chunked stream"]
+                "--modes", "nccl push fused push+mc"]
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         scale_modes.main()
@@ -197,146 +322,13 @@ def _scale_modes_worker(rank, world, port, q):
 
 
 def test_scale_modes_control_flow_gloo_world2():
-    import socket
-    import torch.multiprocessing as mp
-    with socket.socket() as sk:
-        sk.bind(("127.0.0.1", 0))
-        port = sk.getsockname()[1]
-    mpc = mp.get_context("spawn")
-    q = mpc.Queue()
-    procs = [mpc.Process(target=_scale_modes_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = dict(q.get(timeout=240) for _ in procs)
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = _spawn2(_scale_modes_worker)
     lines = [json.loads(l) for l in res[0].splitlines() if l.startswith("{")]
-    assert res[1].strip() == ""                      # rank 0 alone reports
-    modes = [(d["mode"], d["barrier"]) for d in lines if "mode" in d]
-    assert modes == [("push", "nccl"), ("fused", "nccl"), ("nccl", "nccl"), ("mcast-push", "nccl"),
-                     ("mcast-push", "symm"), ("mcast-chunked", "nccl"), ("mcast-chunked", "symm"),
-                     ("stream", "nccl")]
-    done = [d for d in lines if "ms_per_step" in d]
-    assert len(done) == 7 and all(d["correct"] and d["speedup_vs_n1"] > 0 for d in done)
-    assert [d for d in lines if "skipped" in d][0]["mode"] == "mcast-chunked"
+    assert res[1].strip() == ""
+    modes = [d["mode"] for d in lines if "mode" in d]
+    assert modes == ["nccl", "push", "fused", "push+mc"]
+    done = [d for d in lines if "ms_per_step" in d and "mode" in d]
+    assert len(done) == 3 and all(d["correct"] and d["speedup_vs_n1"] > 0 for d in done)
+    assert [d for d in lines if "skipped" in d][0]["mode"] == "push+mc"   # the stand-in has no multicast
     assert any("partition_round" in d for d in lines) and any("setup_seconds" in d for d in lines)
-
-
-# ---- bench.py N > 1 control flow (partition calibration, re-cuts, the exchange trial of
-#      `--exchange auto`, the JSON line) on two gloo ranks with the GPU pieces faked
-def _bench_n2_worker(rank, world, port, q):
-    import os
-    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    sys.path.insert(0, ROOT)
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
-                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank), SPRS_BENCH_NO_SAMPLER="1",
-                      SPRS_B200_AUTO_TRIAL_MIN_GPUS="2")
-    import contextlib
-    import io
-    import torch.distributed as dist
-    import torch.distributed._symmetric_memory as symm
-    import sprs_b200
-    from sprs_b200 import dist as D
-    from sprs_b200 import generate as G
-    real_device = torch.device
-    torch.device = lambda *a, **k: real_device("cpu")
-    torch.cuda.set_device = lambda d: None
-    torch.cuda.synchronize = lambda *a: None
-    torch.cuda.empty_cache = lambda: None
-    torch.Tensor.pin_memory = lambda self: self
-
-    class Event(_FakeEvent):
-        ms = 1.0
-
-        def elapsed_time(self, other):
-            return Event.ms
-
-    torch.cuda.Event = Event
-    real_init = dist.init_process_group
-    dist.init_process_group = lambda backend, **k: real_init("gloo")
-    symm._SymmetricMemory.has_multicast_support = staticmethod(lambda *a: True)
-    ctx = _FakeCtx()
-    sprs_b200.Context.default = classmethod(lambda cls, device=None: ctx)
-
-    def make_matrix(c, gen, n, npr, seed):
-        rng = np.random.default_rng(seed % (1 << 32))
-        return _FakeCsr(sps.random(n, n, density=npr / n, format="csr", random_state=rng,
-                                   data_rvs=rng.standard_normal))
-
-    def spmv(c, a, x, y, accumulate=False):
-        y.copy_(torch.from_numpy(a.m @ x.numpy()))
-        return y
-
-    G.make_matrix, G.spmv = make_matrix, spmv
-    G.normal_vector = lambda c, n, seed=1: torch.from_numpy(np.random.default_rng(seed).standard_normal(n))
-    closed = []
-
-    class FakePeerOp(D.RowPartitionedSpMV):
-        speed = 1.0
-
-        def __init__(self, c, mirror, bounds, rank_, world_, n, dist_, device, mode=None, barrier=None):
-            self.tag = mode
-            if mode == "fused":          # pretend plain `mcast` computes something else
-                self.wrong = True
-            blk = mirror.owner
-            super().__init__(bounds, rank_, world_, torch.zeros(n, dtype=torch.float64),
-                             lambda xv, ys: spmv(c, blk, xv, ys), dist=dist_)
-
-        def step(self, xv):
-            Event.ms = 0.5 if self.tag == "push" else 1.0   # only mcast-push is "faster"
-            out = super().step(xv)
-            if getattr(self, "wrong", False):
-                out[0] += 1.0
-            return out
-
-        def close(self):
-            closed.append(self.tag)
-
-    class Plain(FakePeerOp):             # the non-mcast peer classes take no mode/barrier
-        def __init__(self, c, mirror, bounds, rank_, world_, n, dist_, device):
-            super().__init__(c, mirror, bounds, rank_, world_, n, dist_, device)
-
-    for name in ("PushAllGatherSpMV", "FusedAllGatherSpMV", "StreamAllGatherSpMV",
-                 "ChunkedPushAllGatherSpMV"):
-        setattr(D, name, Plain)
-    D.McastAllGatherSpMV = FakePeerOp
-    import bench
-    bench.WORKLOADS["spmv_rmat_10m"] = ("spmv", 3000, 10, "rmat")
-    sys.argv = ["bench.py", "--gpus", "2", "--steps", "2", "--warmup", "3", "--no-cpu-baseline",
-                "--no-extra"]
-    buf = io.StringIO()
-    with contextlib.redirect_stdout(buf):
-        bench.main()
-    q.put((rank, buf.getvalue(), closed))
-
-
-def test_bench_n2_auto_exchange_trial_gloo():
-    import socket
-    import torch.multiprocessing as mp
-    with socket.socket() as sk:
-        sk.bind(("127.0.0.1", 0))
-        port = sk.getsockname()[1]
-    mpc = mp.get_context("spawn")
-    q = mpc.Queue()
-    procs = [mpc.Process(target=_bench_n2_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = {r: (out, closed) for r, out, closed in (q.get(timeout=240) for _ in procs)}
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    lines = [l for l in res[0][0].splitlines() if l.startswith("{")]
-    assert len(lines) == 1 and res[1][0].strip() == ""
-    line = json.loads(lines[0])
-    for k in REQUIRED:
-        assert k in line, k
-    assert line["n_gpus"] == 2 and line["scaling"] == "strong"
-    trial = line["config"]["exchange_trial"]
-    # the validated exchange (push at 2 GPUs) was timed, mcast-push beat it and was selected,
-    # plain mcast was rejected because its result differed
-    # (the fake event reports 1.0 / 0.5 ms for the 5 timed steps)
-    assert trial["push"] == 0.2 and trial["mcast-push"] == 0.1 and trial["selected"] == "mcast-push"
-    assert trial["mcast"].startswith("rejected")
-    assert "multicast" in line["config"]["collective"]
-    assert "fused" in res[0][1] and None in res[0][1]      # the loser and the base op were closed
+    assert sum(1 for d in lines if "e2e_host_slices" in d and d.get("correct")) == 2

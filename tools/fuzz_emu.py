@@ -41,7 +41,8 @@ def setup(schedule):
 
 BOUNDARY_LENS = [0, 0, 0, 1, 1, 2, 3, 5, 6, 7, 8, 9, 10, 11, 12, 13, 16, 24, 31, 32, 33, 47, 48, 49,
                  63, 64, 65, 95, 96, 97, 127, 128, 129, 191, 192, 193, 255, 256, 257, 319, 320,
-                 321, 383, 384, 385, 511, 512, 513, 767, 768, 769, 1151, 1152, 1153]
+                 321, 383, 384, 385, 511, 512, 513, 767, 768, 769, 1023, 1024, 1025, 1151, 1152, 1153, 2047,
+                 2048, 2049]
 
 
 def row_lengths(rng, rows, cols):
@@ -177,7 +178,7 @@ def one_case(sp, O, seed):
     e = gate(got, ref, bound, "spmv")
     if e:
         errs.append(e)
-    elif lens.max() <= 6 and int(ip[-1]) < 256:
+    elif lens.max() <= 6 and int(ip[-1]) < 1024:
         # `&A * &x` (y starts at 0), one partial tile of short rows: one lane sums each row in
         # storage order -> the reference's bits (cut rows and y0 != 0 only agree to rounding)
         ref0 = np.zeros(rows)

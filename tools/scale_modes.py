@@ -1,15 +1,14 @@
-"""All exchange modes of the row-partitioned SpMV in ONE launch (N GPUs are charged N-fold: one
-matrix generation, one rendezvous and one partition calibration for every mode instead of one
-per mode).  Same workload, partition and timing rules as bench.py (BASELINE config 5, CUDA
-events, barrier on both sides, max over ranks); the safest modes run first and every result is
-printed as soon as it exists, so a trap in a never-run mode loses only what follows it.
+"""All exchange modes of the row-partitioned SpMV in ONE multi-GPU launch (8 GPUs are charged
+8-fold): the matrix, the rendezvous and the measured partition are shared, every mode is checked
+against the single-GPU product of the same matrix (computed on every rank) and timed with CUDA
+events, max over ranks.  One JSON line per mode on rank 0.
 
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \\
-      --master-port 29611 tools/scale_modes.py --steps 20 \\
-      --modes "push fused nccl mcast-push mcast mcast-chunked chunked mcast-stream stream"
+  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/scale_modes.py \
+      [--n 10000000 --npr 100 --steps 20 --warmup 5 --modes "nccl push fused push+mc fused+mc"]
 
-Prints one JSON line per (mode, barrier); `speedup_vs` divides --n1-ms (the measured 1-GPU
-step, default round 1's 4.18 ms) by the step time.  Not a bench arm: bench.py stays the contract.
+Modes: nccl = NCCL all_gather after the kernel; push / fused = the library's communicator over
+CUDA IPC peer mappings; "+mc" = the same through the NVSwitch multicast address of y.  The
+multicast modes run last (they are the ones that can fail hard on an unsupported box).
 """
 import argparse
 import json
@@ -23,166 +22,170 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    # the modes whose put kernel waits on the SpMV (they can trap) go last
-    ap.add_argument("--modes", default="push fused nccl mcast-push mcast mcast-chunked chunked "
-                                       "mcast-stream stream")
-    ap.add_argument("--barriers", default="nccl symm", help="tried for the mcast modes")
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--n", type=int, default=10_000_000)
     ap.add_argument("--npr", type=int, default=100)
-    ap.add_argument("--n1-ms", type=float, default=4.18)
-    ap.add_argument("--recuts", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--modes", default="nccl push fused push+mc fused+mc")
     args = ap.parse_args()
 
     import torch
     import torch.distributed as dist
     import sprs_b200 as sp
     from sprs_b200 import generate as G
-    from sprs_b200.dist import (ChunkedPushAllGatherSpMV, FusedAllGatherSpMV, McastAllGatherSpMV,
-                                PushAllGatherSpMV, RowPartitionedSpMV, StreamAllGatherSpMV,
-                                fit_row_cost, nnz_balanced_bounds, rebalance_bounds)
-    world, rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
+    from sprs_b200.dist import (Comm, CommHostSpMV, CommSpMV, RowPartitionedSpMV, fit_row_cost,
+                                nnz_balanced_bounds, rebalance_bounds)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ctx = sp.Context.default(local)
-    t0 = time.time()
-    full = G.make_matrix(ctx, "rmat", args.n, args.npr, 0x5EED0005)
-    n, nnz = args.n, full.nnz
-    x = G.normal_vector(ctx, n)
+    n = args.n
 
     def say(d):
         if rank == 0:
             print(json.dumps(d), flush=True)
 
-    def max_over_ranks(v):
-        t = torch.tensor([v], device=dev, dtype=torch.float64)
+    def allmax(vals):
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return t.tolist()
 
-    def all_ok(flag):
-        t = torch.tensor([1.0 if flag else 0.0], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        return bool(t.item() > 0.5)
-
-    def make(mode, barrier, blk, bnds):
-        if mode == "nccl":
-            yb = torch.zeros(n, device=dev, dtype=torch.float64)
-            return RowPartitionedSpMV(bnds, rank, world, yb, lambda xv, ys: G.spmv(ctx, blk, xv, ys),
-                                      dist=dist)
-        if mode.startswith("mcast"):
-            return McastAllGatherSpMV(ctx, blk.mirror, bnds, rank, world, n, dist, dev,
-                                      mode=mode.partition("-")[2] or "fused", barrier=barrier)
-        cls = {"push": PushAllGatherSpMV, "fused": FusedAllGatherSpMV,
-               "stream": StreamAllGatherSpMV, "chunked": ChunkedPushAllGatherSpMV}[mode]
-        return cls(ctx, blk.mirror, bnds, rank, world, n, dist, dev)
-
-    def timed(op, steps, split=False):
-        """(ms per step, compute-only ms per step), max over ranks."""
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        dist.barrier()
-        if not split:
-            e0.record()
-            for _ in range(steps):
-                op.step(x)
-            e1.record()
-            torch.cuda.synchronize()
-            dist.barrier()
-            return max_over_ranks(e0.elapsed_time(e1) / steps), None
-        tsum = 0.0
-        for _ in range(steps):
-            torch.cuda.synchronize()
-            dist.barrier()
-            e0.record()
-            op.compute(x)
-            e1.record()
-            op.exchange()
-            torch.cuda.synchronize()
-            tsum += e0.elapsed_time(e1)
-        return None, tsum / steps
-
-    # ---- partition: row cost fitted from the plain kernel, then equal-time re-cuts measured
-    #      with the push operator (validated in round 1); every mode then runs on the same cut
-    bounds = nnz_balanced_bounds(full.indptr, world)
-    blk = full.slice_rows(bounds[rank], bounds[rank + 1])
-    yt = torch.empty(max(blk.rows, 1), device=dev, dtype=torch.float64)
-    for _ in range(2):
-        G.spmv(ctx, blk, x, yt)
+    t0 = time.time()
+    full = G.make_matrix(ctx, "rmat", n, args.npr, 0x5EED0005)
+    x = G.normal_vector(ctx, n)
+    y_ref = torch.empty(n, device=dev, dtype=torch.float64)
+    G.spmv(ctx, full, x, y_ref)
+    # single-GPU time of the same matrix on this box (the denominator of the speed-up)
+    for _ in range(3):
+        G.spmv(ctx, full, x, y_ref)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(3):
-        G.spmv(ctx, blk, x, yt)
+    for _ in range(10):
+        G.spmv(ctx, full, x, y_ref)
     e1.record()
     torch.cuda.synchronize()
-    mine = torch.tensor([blk.nnz, blk.rows, e0.elapsed_time(e1) / 3e3], device=dev,
-                        dtype=torch.float64)
-    allm = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(allm, mine)
+    (n1_ms,) = allmax([e0.elapsed_time(e1) / 10])
+    scale = float(y_ref.abs().max().item()) + 1e-300
+    ids = [Comm.unique_id(ctx) if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    comm = Comm(ctx, ids[0], rank, world)
+    say({"setup_seconds": round(time.time() - t0, 1), "n1_ms_this_box": n1_ms, "world": world,
+         "multicast_supported": comm.multicast, "nnz": full.nnz})
+
+    # ---- partition: nnz balance, fitted row cost, then measured equal-time re-cuts (plain SpMV)
+    bounds = nnz_balanced_bounds(full.indptr, world)
+    row_cost = 0.0
+
+    def block_time(b):
+        a = full.slice_rows(b[rank], b[rank + 1])
+        yt = torch.empty(max(b[rank + 1] - b[rank], 1), device=dev, dtype=torch.float64)
+        for _ in range(2):
+            G.spmv(ctx, a, x, yt)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(4):
+            G.spmv(ctx, a, x, yt)
+        c1.record()
+        torch.cuda.synchronize()
+        return a, c0.elapsed_time(c1) / 4
+
+    a, ms = block_time(bounds)
+    allm = comm.allgather_f64([a.nnz, bounds[rank + 1] - bounds[rank], ms / 1e3])
     row_cost = fit_row_cost([m.tolist() for m in allm])
-    del blk, yt
     bounds = nnz_balanced_bounds(full.indptr, world, row_cost=row_cost)
-    best = None
-    for cut in range(args.recuts + 1):
-        blk = full.slice_rows(bounds[rank], bounds[rank + 1])
-        op = make("push", "nccl", blk, bounds)
-        for _ in range(3):
-            op.step(x)
-        _, comp = timed(op, 4, split=True)
-        tm = torch.tensor([comp], device=dev, dtype=torch.float64)
-        allt = [torch.empty_like(tm) for _ in range(world)]
-        dist.all_gather(allt, tm)
-        times = [float(t.item()) for t in allt]
-        op.close()
-        del op, blk
+    for rnd in range(3):
+        del a
         torch.cuda.empty_cache()
-        if best is None or max(times) < best[0]:
-            best = (max(times), list(bounds))
-        say({"partition_round": cut, "row_cost": row_cost, "compute_ms_max": max(times),
-             "compute_ms_mean": sum(times) / world})
-        if cut == args.recuts or max(times) <= 1.015 * sum(times) / world:
+        a, ms = block_time(bounds)
+        times = [float(v[0]) for v in comm.allgather_f64([ms])]
+        say({"partition_round": rnd, "row_cost": round(row_cost, 2), "block_ms": [round(t, 4) for t in times]})
+        if max(times) <= 1.02 * (sum(times) / world):
             break
         nb = rebalance_bounds(full.indptr, bounds, times, row_cost=row_cost)
         if nb == bounds:
             break
         bounds = nb
-    bounds = best[1]
-    blk = full.slice_rows(bounds[rank], bounds[rank + 1])
-    ref = torch.empty(n, device=dev, dtype=torch.float64)
-    G.spmv(ctx, full, x, ref)
-    scale = float(ref.abs().max().item())
-    del full
-    torch.cuda.empty_cache()
-    say({"setup_seconds": round(time.time() - t0, 1), "nnz": nnz, "world": world, "bounds": bounds})
+    r0, r1 = bounds[rank], bounds[rank + 1]
+
+    def run_mode(mode):
+        name, _, mc = mode.partition("+")
+        if name == "nccl":
+            yb = torch.zeros(n, device=dev, dtype=torch.float64)
+            op = RowPartitionedSpMV(bounds, rank, world, yb, lambda xv, ys: G.spmv(ctx, a, xv, ys), dist=dist)
+        else:
+            op = CommSpMV(comm, a.mirror, bounds, n, dev, exchange=name, multicast=(mc == "mc"))
+            if mc == "mc" and not op.multicast:
+                op.close()
+                return {"mode": mode, "skipped": "no multicast binding on this box"}
+        op.y.fill_(float("nan"))
+        torch.cuda.synchronize()
+        dist.barrier()
+        op.step(x)
+        torch.cuda.synchronize()
+        comm.check()
+        ok = bool(((op.y - y_ref).abs() <= 1e-9 * scale).all().item())
+        (bad,) = allmax([0.0 if ok else 1.0])
+        for _ in range(args.warmup):
+            op.step(x)
+        torch.cuda.synchronize()
+        dist.barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+                torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(args.steps):
+            evs[i][0].record()
+            op.compute(x)
+            evs[i][1].record()
+            op.exchange()
+            evs[i][2].record()
+        s1.record()
+        torch.cuda.synchronize()
+        comm.check()
+        kern = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+        coll = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+        total, kmax, cmax = allmax([s0.elapsed_time(s1) / args.steps, kern, coll])
+        per_rank = [round(float(v[0]), 4) for v in comm.allgather_f64([kern])]
+        if hasattr(op, "close"):
+            op.close()
+        return {"mode": mode, "correct": bad == 0.0, "ms_per_step": total, "compute_ms_max": kmax,
+                "barrier_or_collective_ms_max": cmax, "compute_ms_per_rank": per_rank,
+                "speedup_vs_n1": n1_ms / total, "efficiency": n1_ms / total / world}
 
     for mode in args.modes.split():
-        for barrier in (args.barriers.split() if mode.startswith("mcast") else ["nccl"]):
-            op, err = None, None
-            try:
-                op = make(mode, barrier, blk, bounds)
-            except Exception as e:  # e.g. no multicast support: every rank must agree to skip
-                err = repr(e)
-            if not all_ok(op is not None):
-                say({"mode": mode, "barrier": barrier, "skipped": err or "failed on another rank"})
-                if op is not None and hasattr(op, "close"):
-                    op.close()
-                continue
-            for _ in range(args.warmup):
-                op.step(x)
+        try:
+            res = run_mode(mode)
+        except Exception as e:  # one mode failing must not hide the others' numbers
+            res = {"mode": mode, "error": repr(e)[:300]}
+        say(res)
+
+    # ---- host-vector form (e2e): every rank moves only its own slices
+    for mc in (False, True):
+        try:
+            hop = CommHostSpMV(comm, a.mirror, bounds, n, multicast=mc)
+            hx = torch.empty(max(r1 - r0, 1), dtype=torch.float64).pin_memory()
+            hx[:r1 - r0].copy_(x[r0:r1])
+            hy = torch.empty(max(r1 - r0, 1), dtype=torch.float64).pin_memory()
+            for _ in range(2):
+                hop.step(hx.data_ptr(), hy.data_ptr())
+            dist.barrier()
+            t1 = time.perf_counter()
+            for _ in range(5):
+                hop.step(hx.data_ptr(), hy.data_ptr())
             torch.cuda.synchronize()
-            good = bool(((op.y - ref).abs() <= 1e-9 * scale).all().item())
-            ms, _ = timed(op, args.steps)
-            _, comp = timed(op, 5, split=True)
-            comp = max_over_ranks(comp)
-            say({"mode": mode, "barrier": barrier, "ms_per_step": ms, "compute_ms": comp,
-                 "gflops": 2.0 * nnz / ms / 1e6, "speedup_vs_n1": args.n1_ms / ms,
-                 "correct": all_ok(good)})
-            if hasattr(op, "close"):
-                op.close()
-            del op
-            torch.cuda.empty_cache()
+            (ms,) = allmax([(time.perf_counter() - t1) * 1e3 / 5])
+            ok = bool(((hy[:r1 - r0].to(dev) - y_ref[r0:r1]).abs() <= 1e-9 * scale).all().item())
+            (bad,) = allmax([0.0 if ok else 1.0])
+            say({"e2e_host_slices": "multicast" if mc and hop.x.multicast_ptr else "ipc",
+                 "ms_per_step": ms, "correct": bad == 0.0})
+            hop.close()
+        except Exception as e:
+            say({"e2e_host_slices": "multicast" if mc else "ipc", "error": repr(e)[:300]})
+    comm.close()
     dist.destroy_process_group()
 
 
