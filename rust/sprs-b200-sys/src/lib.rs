@@ -8,6 +8,8 @@ use std::os::raw::{c_char, c_double, c_int, c_void};
 #[repr(C)] pub struct sprs_b200_ctx { _private: [u8; 0] }
 #[repr(C)] pub struct sprs_b200_csmat { _private: [u8; 0] }
 #[repr(C)] pub struct sprs_b200_spgemm { _private: [u8; 0] }
+#[repr(C)] pub struct sprs_b200_comm { _private: [u8; 0] }
+#[repr(C)] pub struct sprs_b200_symm { _private: [u8; 0] }
 #[repr(C)] pub struct sprs_b200_bicgstab { _private: [u8; 0] }
 
 pub const SPRS_B200_CSR: c_int = 0;
@@ -150,10 +152,46 @@ extern "C" {
         ctx: *mut sprs_b200_ctx, mat: *const sprs_b200_csmat, d_x: *const c_double,
         row_offset: u64, n_targets: c_int, d_y_bufs: *const *mut c_double, accumulate: c_int,
         stream: *mut c_void) -> c_int;
-    pub fn sprs_b200_spmv_stream_push_dev(
-        ctx: *mut sprs_b200_ctx, mat: *mut sprs_b200_csmat, d_x: *const c_double, row_offset: u64,
-        n_targets: c_int, d_y_bufs: *const *mut c_double, accumulate: c_int, put_ctas: c_int,
+    pub fn sprs_b200_copy_to_device(
+        ctx: *mut sprs_b200_ctx, d_dst: *mut c_void, h_src: *const c_void, bytes: u64,
         stream: *mut c_void) -> c_int;
+    pub fn sprs_b200_copy_to_host(
+        ctx: *mut sprs_b200_ctx, h_dst: *mut c_void, d_src: *const c_void, bytes: u64,
+        stream: *mut c_void) -> c_int;
+    // ---- multi-GPU communicator (one node; ranks = processes or threads; include/sprs_b200.h)
+    pub fn sprs_b200_comm_unique_id(id: *mut c_char) -> c_int;
+    pub fn sprs_b200_comm_init_rank(
+        ctx: *mut sprs_b200_ctx, id: *const c_char, rank: c_int, world: c_int,
+        out: *mut *mut sprs_b200_comm) -> c_int;
+    pub fn sprs_b200_comm_free(comm: *mut sprs_b200_comm) -> c_int;
+    pub fn sprs_b200_comm_rank(comm: *const sprs_b200_comm) -> c_int;
+    pub fn sprs_b200_comm_world(comm: *const sprs_b200_comm) -> c_int;
+    pub fn sprs_b200_comm_multicast_supported(comm: *const sprs_b200_comm) -> c_int;
+    pub fn sprs_b200_comm_allgather_host(
+        comm: *mut sprs_b200_comm, mine: *const c_void, bytes: u64, all: *mut c_void) -> c_int;
+    pub fn sprs_b200_comm_barrier_host(comm: *mut sprs_b200_comm) -> c_int;
+    pub fn sprs_b200_comm_barrier_dev(comm: *mut sprs_b200_comm, stream: *mut c_void) -> c_int;
+    pub fn sprs_b200_comm_check(comm: *mut sprs_b200_comm, stream: *mut c_void) -> c_int;
+    pub fn sprs_b200_symm_alloc(
+        comm: *mut sprs_b200_comm, bytes: u64, want_multicast: c_int,
+        out: *mut *mut sprs_b200_symm) -> c_int;
+    pub fn sprs_b200_symm_free(buf: *mut sprs_b200_symm) -> c_int;
+    pub fn sprs_b200_symm_ptr(buf: *const sprs_b200_symm, rank: c_int) -> *mut c_void;
+    pub fn sprs_b200_symm_multicast_ptr(buf: *const sprs_b200_symm) -> *mut c_void;
+    pub fn sprs_b200_symm_bytes(buf: *const sprs_b200_symm) -> u64;
+    pub fn sprs_b200_partition_rows(
+        indptr: *const c_void, indptr_bytes: c_int, rows: u64, nparts: c_int, row_cost: c_double,
+        bounds: *mut u64) -> c_int;
+    pub fn sprs_b200_spmv_rowpart(
+        comm: *mut sprs_b200_comm, mat: *const sprs_b200_csmat, d_x: *const c_double,
+        y: *mut sprs_b200_symm, row_offset: u64, exchange: c_int, stream: *mut c_void) -> c_int;
+    pub fn sprs_b200_mul_mat_vec_rowpart(
+        comm: *mut sprs_b200_comm, mat: *const sprs_b200_csmat, x: *mut sprs_b200_symm,
+        x_slice: *const c_double, col_offset: u64, col_count: u64, y_slice: *mut c_double,
+        y_len: u64) -> c_int;
+    pub fn sprs_b200_diag_gather_ceiling(
+        ctx: *mut sprs_b200_ctx, mat: *const sprs_b200_csmat, d_x: *const c_double, iters: c_int,
+        ms_per_pass: *mut c_double, nnz_covered: *mut u64) -> c_int;
     pub fn sprs_b200_spmv_chunked_push_dev(
         ctx: *mut sprs_b200_ctx, mat: *const sprs_b200_csmat, d_x: *const c_double,
         row_offset: u64, n_targets: c_int, d_y_bufs: *const *mut c_double, accumulate: c_int,

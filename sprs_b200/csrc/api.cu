@@ -243,6 +243,15 @@ int sprs_b200_ctx_create(int device, sprs_b200_ctx** out) {
         ctx->pol_evict_first = h_pol[0];
         ctx->pol_evict_last = h_pol[1];
     }
+    {   // the stream-ordered allocator keeps what the SpGEMM frees (a 42 GB product is
+        // re-allocated by the next call: cudaMalloc / cudaFree of it cost ~100 ms per product)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     *out = ctx;
     return SPRS_B200_OK;
 }
@@ -262,6 +271,11 @@ int sprs_b200_ctx_destroy(sprs_b200_ctx* ctx) {
     if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        cudaGetLastError();
+    }
     delete ctx;
     return SPRS_B200_OK;
 }
@@ -393,7 +407,12 @@ int sprs_b200_csmat_from_device(sprs_b200_ctx* ctx, int storage, uint64_t rows, 
 int sprs_b200_csmat_free(sprs_b200_csmat* m) {
     if (!m) return SPRS_B200_OK;
     if (m->ctx) cudaSetDevice(m->ctx->device);
-    if (m->owns) {
+    if (m->owns && m->pooled && m->ctx) {  // back to the pool, ordered on the ctx stream
+        cudaDeviceSynchronize();  // (readers on other streams -- a caller's views of C -- are done)
+        if (m->d_indptr) cudaFreeAsync(m->d_indptr, m->ctx->stream);
+        if (m->d_indices) cudaFreeAsync(m->d_indices, m->ctx->stream);
+        if (m->d_data) cudaFreeAsync(m->d_data, m->ctx->stream);
+    } else if (m->owns) {
         if (m->d_indptr) cudaFree(m->d_indptr);
         if (m->d_indices) cudaFree(m->d_indices);
         if (m->d_data) cudaFree(m->d_data);
@@ -662,7 +681,13 @@ static int spmv_host(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, int want_st
             const char* v = getenv("SPRS_B200_E2E_CHUNKS");
             return v ? atoi(v) : SPRS_E2E_DEFAULT_CHUNKS;
         }();
-        if (chunks > 1 && y_len >= 4096 && csr->n_tiles >= (uint64_t)chunks * 1024) {
+        // (a chunk is worth its launch only with >= ~1000 tiles; SPRS_B200_E2E_MIN_TILES is a TEST
+        // hook that lets small matrices take the chunked path)
+        static const uint64_t min_tiles = [] {
+            const char* v = getenv("SPRS_B200_E2E_MIN_TILES");
+            return v ? (uint64_t)atoll(v) : (uint64_t)1024;
+        }();
+        if (chunks > 1 && y_len >= 4096 && csr->n_tiles >= (uint64_t)chunks * min_tiles) {
             if ((st = spmv_host_chunked(ctx, csr, (const double*)d_x, (double*)d_y, y, accumulate,
                                         chunks, s)) != SPRS_B200_OK)
                 break;

@@ -49,6 +49,7 @@ struct sprs_b200_csmat {
     uint32_t* d_indices = nullptr; // nnz entries
     double* d_data = nullptr;      // nnz entries
     bool owns = true;              // false for from_device adoption
+    bool pooled = false;           // arrays came from cudaMallocAsync (SpGEMM results)
     // SpMV partition (built lazily, see spmv.cu): tile_row[t] = first outer index whose
     // end lies beyond nnz position t*TILE; n_tiles+1 entries.  carry: n_tiles doubles.
     uint32_t* d_tile_row = nullptr;

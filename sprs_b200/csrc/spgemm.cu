@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(1024)
 //     panels nothing landed in are skipped.
 constexpr uint32_t PANEL_W = 16384;       // columns per panel: 128 KB of f64 accumulators
 constexpr uint32_t PANEL_MAX_A = 4096;    // per-A-non-zero state: 16 B each = 64 KB
-constexpr size_t PANEL_SMEM = (size_t)PANEL_W * 8 + PANEL_W / 8 + (size_t)PANEL_MAX_A * 16;
+constexpr size_t PANEL_SMEM = (size_t)PANEL_W * 8 + PANEL_W / 8 + (size_t)PANEL_MAX_A * 20;
 constexpr int PANEL_NT = 1024;
 
 __global__ void __launch_bounds__(PANEL_NT)
@@ -507,6 +507,8 @@ __global__ void __launch_bounds__(PANEL_NT)
     uint32_t* bm = (uint32_t*)(aval + PANEL_MAX_A);                   // PANEL_W / 32 words
     uint32_t* cursor = bm + PANEL_W / 32;                             // PANEL_MAX_A
     uint32_t* bend = cursor + PANEL_MAX_A;                            // PANEL_MAX_A
+    uint32_t* nextcol = bend + PANEL_MAX_A;  // column at the cursor (0 = not known yet): a B row
+                                             // with nothing in a panel costs one LDS there
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t chunk_total;
     __shared__ uint32_t panel_mark;  // sequence number of the last panel something landed in
@@ -529,6 +531,7 @@ __global__ void __launch_bounds__(PANEL_NT)
             cursor[kk] = b_ip[br];
             bend[kk] = b_ip[br + 1];
             aval[kk] = a_val[a0 + kk];
+            nextcol[kk] = 0;
         }
         __syncthreads();
         // G warps share one B row when the A row is short (G > 1 implies na <= NWARPS / 2, so
@@ -545,6 +548,10 @@ __global__ void __launch_bounds__(PANEL_NT)
             for (uint32_t kk = grp; kk < na; kk += 2 * ngrp) {
                 const uint32_t kb = kk + ngrp;
                 const bool has_b = kb < na;
+                // (G == 1 only: the first column beyond the cursor is known from the last visit)
+                const bool skip_a = G == 1 && nextcol[kk] >= p1;
+                const bool skip_b = !has_b || (G == 1 && nextcol[kb] >= p1);
+                if (skip_a && skip_b) continue;
                 const uint32_t base_a = cursor[kk], end_a = bend[kk];
                 const uint32_t base_b = has_b ? cursor[kb] : 0u, end_b = has_b ? bend[kb] : 0u;
                 const double av_a = aval[kk], av_b = has_b ? aval[kb] : 0.0;
@@ -553,7 +560,8 @@ __global__ void __launch_bounds__(PANEL_NT)
                 // chunks not at all -- with G warps the warps' counts add up to the prefix length
                 uint32_t pos_a = base_a + (uint32_t)wg * 32, pos_b = base_b + (uint32_t)wg * 32;
                 uint32_t taken_a = 0, taken_b = 0;
-                bool live_a = pos_a < end_a, live_b = has_b && pos_b < end_b;
+                uint32_t next_a = EMPTY, next_b = EMPTY;  // first column NOT taken (EMPTY: row used up)
+                bool live_a = !skip_a && pos_a < end_a, live_b = !skip_b && pos_b < end_b;
                 while (live_a || live_b) {
                     uint32_t ca = EMPTY, cb = EMPTY;
                     double va = 0.0, vb = 0.0;
@@ -576,6 +584,7 @@ __global__ void __launch_bounds__(PANEL_NT)
                         taken_a += n;
                         pos_a += 32u * G;
                         live_a = n == 32 && pos_a < end_a;
+                        if (n < 32) next_a = __shfl_sync(0xffffffffu, ca, n);
                     }
                     if (live_b) {
                         const bool take = cb < p1;
@@ -587,13 +596,20 @@ __global__ void __launch_bounds__(PANEL_NT)
                         taken_b += n;
                         pos_b += 32u * G;
                         live_b = n == 32 && pos_b < end_b;
+                        if (n < 32) next_b = __shfl_sync(0xffffffffu, cb, n);
                     }
                 }
                 landed |= (taken_a | taken_b) != 0;
                 if (G == 1) {
                     if (lane == 0) {
-                        cursor[kk] = base_a + taken_a;
-                        if (has_b) cursor[kb] = base_b + taken_b;
+                        if (!skip_a) {
+                            cursor[kk] = base_a + taken_a;
+                            nextcol[kk] = next_a;  // (a chunk that ended exactly at `end`: EMPTY)
+                        }
+                        if (!skip_b) {
+                            cursor[kb] = base_b + taken_b;
+                            nextcol[kb] = next_b;
+                        }
                     }
                 } else {
                     grp_taken = taken_a;  // added after the barrier: the group's other warps read `base`
@@ -729,9 +745,10 @@ int run_numeric(sprs_b200_ctx* ctx, sprs_b200_spgemm* p, uint32_t* d_cidx, doubl
     SPRS_CUDA(ctx, cudaMemsetAsync(p->d_counters, 0, 8 * sizeof(uint32_t), s));
     // rows with more than 16 entries per column panel are cheaper in the panel kernel (no
     // probing, no sort; fixed cost ~ n_panels) than in the CTA hash map
-    const uint64_t n_panels = (p->cols + PANEL_W - 1) / PANEL_W;
-    const uint32_t num_m_max =
-        (uint32_t)std::min<uint64_t>(NUM_M_MAX, std::max<uint64_t>(NUM_S_MAX, 16 * n_panels));
+    // (measured: a row costs the panel kernel ~900 instructions per warp and panel whatever it
+    // holds -- 71 G instructions for config 4 when rows from 500 entries up went there; the CTA
+    // hash map is an order of magnitude cheaper up to its 4096 entries)
+    const uint32_t num_m_max = NUM_M_MAX;
     bin_rows_kernel<uint32_t><<<grid_for(rows), 256, 0, s>>>(p->d_cnt, rows, NUM_S_MAX, num_m_max,
                                                             p->d_lists, p->d_counters, nullptr);
     ctx->launches += 1;
@@ -760,7 +777,7 @@ int run_numeric(sprs_b200_ctx* ctx, sprs_b200_spgemm* p, uint32_t* d_cidx, doubl
         // lists[0 .. rows) and [rows .. 2 rows) are free again once small / medium have been
         // LAUNCHED?  No -- they are still being read; use fresh scratch for the split lists.
         uint32_t* split = nullptr;
-        SPRS_CUDA(ctx, cudaMalloc((void**)&split, 2ull * h_cnt[2] * sizeof(uint32_t)));
+        SPRS_CUDA(ctx, cudaMallocAsync((void**)&split, 2ull * h_cnt[2] * sizeof(uint32_t), s));
         uint32_t *panel_list = split, *hub_list = split + h_cnt[2];
         split_large_kernel<<<grid_for(h_cnt[2]), 256, 0, s>>>(a_ip, l2, h_cnt[2], PANEL_MAX_A,
                                                              panel_list, hub_list, p->d_counters);
@@ -802,7 +819,7 @@ int run_numeric(sprs_b200_ctx* ctx, sprs_b200_spgemm* p, uint32_t* d_cidx, doubl
             free_large(w);
         }
         if (cudaStreamSynchronize(s) != cudaSuccess) st = SPRS_B200_ERR_CUDA;
-        cudaFree(split);
+        cudaFreeAsync(split, s);
         if (st != SPRS_B200_OK) SPRS_FAIL(ctx, st, "spgemm numeric (large rows) failed");
     }
     SPRS_CUDA(ctx, cudaGetLastError());
@@ -831,11 +848,12 @@ int sprs_b200_spgemm_symbolic(sprs_b200_ctx* ctx, const sprs_b200_csmat* a,
     const uint32_t rows = (uint32_t)p->rows;
     int st = SPRS_B200_OK;
     do {
-        if (cudaMalloc((void**)&p->d_nprod, (p->rows + 1) * 8) != cudaSuccess ||
-            cudaMalloc((void**)&p->d_cnt, (p->rows + 1) * 4) != cudaSuccess ||
-            cudaMalloc((void**)&p->d_cptr, (p->rows + 1) * 8) != cudaSuccess ||
-            cudaMalloc((void**)&p->d_lists, (3 * p->rows + 1) * 4) != cudaSuccess ||
-            cudaMalloc((void**)&p->d_counters, 8 * 4) != cudaSuccess) {
+        // (stream-ordered allocations: the pool keeps the memory across calls, api.cu)
+        if (cudaMallocAsync((void**)&p->d_nprod, (p->rows + 1) * 8, s) != cudaSuccess ||
+            cudaMallocAsync((void**)&p->d_cnt, (p->rows + 1) * 4, s) != cudaSuccess ||
+            cudaMallocAsync((void**)&p->d_cptr, (p->rows + 1) * 8, s) != cudaSuccess ||
+            cudaMallocAsync((void**)&p->d_lists, (3 * p->rows + 1) * 4, s) != cudaSuccess ||
+            cudaMallocAsync((void**)&p->d_counters, 8 * 4, s) != cudaSuccess) {
             sprs_b200_set_error(ctx, "spgemm: cudaMalloc failed");
             st = SPRS_B200_ERR_CUDA;
             break;
@@ -928,11 +946,12 @@ int sprs_b200_spgemm_numeric_dev(sprs_b200_ctx* ctx, sprs_b200_spgemm* p, sprs_b
     m->outer = p->rows;
     m->inner = p->cols;
     m->indptr_bytes = p->nnz_c >= 0xffffffffull ? 8 : 4;
+    m->pooled = true;
     int st = SPRS_B200_OK;
     do {
-        if (cudaMalloc(&m->d_indptr, (m->rows + 1) * (size_t)m->indptr_bytes + 16) != cudaSuccess ||
-            cudaMalloc((void**)&m->d_indices, m->nnz * 4 + 16) != cudaSuccess ||
-            cudaMalloc((void**)&m->d_data, m->nnz * 8 + 16) != cudaSuccess) {
+        if (cudaMallocAsync(&m->d_indptr, (m->rows + 1) * (size_t)m->indptr_bytes + 16, s) != cudaSuccess ||
+            cudaMallocAsync((void**)&m->d_indices, m->nnz * 4 + 16, s) != cudaSuccess ||
+            cudaMallocAsync((void**)&m->d_data, m->nnz * 8 + 16, s) != cudaSuccess) {
             sprs_b200_set_error(ctx, "spgemm numeric: cudaMalloc of C failed");
             st = SPRS_B200_ERR_CUDA;
             break;
@@ -987,11 +1006,12 @@ uint64_t sprs_b200_spgemm_nprod(const sprs_b200_spgemm* p) {
 int sprs_b200_spgemm_free(sprs_b200_spgemm* p) {
     if (!p) return SPRS_B200_OK;
     if (p->ctx) cudaSetDevice(p->ctx->device);
-    if (p->d_nprod) cudaFree(p->d_nprod);
-    if (p->d_cnt) cudaFree(p->d_cnt);
-    if (p->d_cptr) cudaFree(p->d_cptr);
-    if (p->d_lists) cudaFree(p->d_lists);
-    if (p->d_counters) cudaFree(p->d_counters);
+    cudaStream_t s = p->ctx ? p->ctx->stream : nullptr;
+    if (p->d_nprod) cudaFreeAsync(p->d_nprod, s);
+    if (p->d_cnt) cudaFreeAsync(p->d_cnt, s);
+    if (p->d_cptr) cudaFreeAsync(p->d_cptr, s);
+    if (p->d_lists) cudaFreeAsync(p->d_lists, s);
+    if (p->d_counters) cudaFreeAsync(p->d_counters, s);
     delete p;
     return SPRS_B200_OK;
 }

@@ -99,6 +99,18 @@ static inline cudaError_t cudaMalloc(T** p, size_t bytes) {
     return cudaMalloc((void**)p, bytes);
 }
 cudaError_t cudaFree(void* p);
+// stream-ordered allocator: plain allocations here (launches are synchronous)
+static inline cudaError_t cudaMallocAsync(void** p, size_t bytes, cudaStream_t) { return cudaMalloc(p, bytes); }
+template <class T>
+static inline cudaError_t cudaMallocAsync(T** p, size_t bytes, cudaStream_t s) {
+    return cudaMallocAsync((void**)p, bytes, s);
+}
+static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { return cudaFree(p); }
+typedef void* cudaMemPool_t;
+enum cudaMemPoolAttr { cudaMemPoolAttrReleaseThreshold = 4 };
+static inline cudaError_t cudaDeviceGetDefaultMemPool(cudaMemPool_t* p, int) { *p = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaMemPoolSetAttribute(cudaMemPool_t, cudaMemPoolAttr, void*) { return cudaSuccess; }
+static inline cudaError_t cudaMemPoolTrimTo(cudaMemPool_t, size_t) { return cudaSuccess; }
 cudaError_t cudaMallocHost(void** p, size_t bytes);
 template <class T>
 static inline cudaError_t cudaMallocHost(T** p, size_t bytes) {
@@ -119,6 +131,7 @@ cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s);
 cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned flags);
 cudaError_t cudaStreamDestroy(cudaStream_t s);
 cudaError_t cudaStreamSynchronize(cudaStream_t s);
+static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }  // launches are synchronous here
 cudaError_t cudaSetDevice(int d);
 cudaError_t cudaGetDeviceCount(int* n);
 cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int d);

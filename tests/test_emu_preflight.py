@@ -60,17 +60,18 @@ def test_emu_gpu_suite(emu):
     multi-GPU ones and the natively linked C++ drivers) passes on the emulator -- under the
     default thread schedule and under a shuffled one (any order is a legal CUDA schedule, so a
     result that depends on it means a missing barrier) -- and so do the opt-in L2-blocked /
-    unrolled SpMM kernels and the uint64-indptr kernel instantiations (each of those in child
+    chunked host path and the uint64-indptr kernel instantiations (each of those in child
     processes with its environment switch).  The three runs are independent processes and run
-    side by side to keep the CPU suite short."""
+    side by side to keep the CPU suite short."""  # noqa
     suite = [os.path.join(ROOT, "tests"), "-k",
-             "not full_size and not test_cpp and not l2_blocked and not indptr64 and not unrolled_variant",
-             "--deselect", os.path.join(ROOT, "tests", "test_gpu_multi.py")]
+             "not full_size and not test_cpp and not indptr64 and not child_process",
+             "--deselect", os.path.join(ROOT, "tests", "test_gpu_comm.py")]
     runs = {
         "forward": _pytest_child({"CUEMU_SCHEDULE": "forward"}, suite, 1500),
         "random:7": _pytest_child({"CUEMU_SCHEDULE": "random:7"}, suite, 1500),
-        "variants": _pytest_child({}, [os.path.join(ROOT, "tests", "test_gpu_zz_late.py"), "-k",
-                                       "l2_blocked or indptr64 or unrolled_variant"], 900),
+        "variants": _pytest_child({}, [os.path.join(ROOT, "tests", "test_gpu_zz_late.py"),
+                                       os.path.join(ROOT, "tests", "test_gpu_zzz_e2e_chunked.py"), "-k",
+                                       "indptr64 or child_process"], 900),
     }
     failures = []
     for name, (proc, timeout) in runs.items():
@@ -92,9 +93,9 @@ def test_emu_structure_fuzz(emu):
     (tile sizes, register-path row counts, lane groups, SpGEMM bins) through every product of
     the C ABI against the oracle; a fixed slice of the campaign that found nothing else in ~15000
     cases across the default and opt-in kernel variants."""
-    runs = [({}, "1"), ({"SPRS_B200_SPGEMM_V2": "1", "SPRS_B200_SPMV_VARIANT": "256,0,8,3"}, "50001"),
-            ({"SPRS_B200_FORCE_INDPTR64": "1", "SPRS_B200_SPMM_UNROLL": "4",
-              "SPRS_B200_E2E_PIPELINE": "2"}, "90001")]
+    runs = [({}, "1"), ({"SPRS_B200_SPMV_VARIANT": "512,6"}, "50001"),
+            ({"SPRS_B200_FORCE_INDPTR64": "1", "SPRS_B200_E2E_CHUNKS": "3",
+              "SPRS_B200_E2E_MIN_TILES": "1"}, "90001")]
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "fuzz_emu.py"), "--cases", "40",
                                "--seed", seed], env=dict(os.environ, **env), cwd=ROOT,
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -155,46 +155,6 @@ def test_matrix_market_to_device(sp):
     assert csr.data.tolist() == [1., 6., 10.5, 1.5e-2, 2.505e2, -2.8e2, 3.332e1, 1.2e1]
 
 
-@pytest.mark.parametrize("panel", [8, 32])
-def test_spmm_l2_blocked_variant(panel):
-    """The opt-in column-panel SpMM (SPRS_B200_SPMM_PANEL, read once per process) gives the
-    same bits as the oracle: the dense-product tests again in a child process with it on."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, SPRS_B200_SPMM_PANEL=str(panel))
-    r = subprocess.run(
-        [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
-         os.path.join(root, "tests", "test_gpu_spmv_spmm.py"),
-         os.path.join(root, "tests", "test_gpu_zz_late.py"),
-         "-k", "dense or wide_operator or spmm_small"],
-        capture_output=True, text=True, timeout=900, env=env, cwd=root)
-    tail = "\n".join(r.stdout.splitlines()[-15:])
-    assert r.returncode == 0, tail + r.stderr[-1500:]
-    assert " passed" in tail
-
-
-def test_spmm_unrolled_variant():
-    """The opt-in SpMM variant with the B-row loads of four non-zeros in flight
-    (SPRS_B200_SPMM_UNROLL=4, read once per process): same bits as the oracle -- the
-    dense-product tests again in a child process with it on."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, SPRS_B200_SPMM_UNROLL="4")
-    r = subprocess.run(
-        [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
-         os.path.join(root, "tests", "test_gpu_spmv_spmm.py"),
-         os.path.join(root, "tests", "test_gpu_zz_late.py"),
-         "-k", "dense or wide_operator or spmm_small"],
-        capture_output=True, text=True, timeout=900, env=env, cwd=root)
-    tail = "\n".join(r.stdout.splitlines()[-15:])
-    assert r.returncode == 0, tail + r.stderr[-1500:]
-    assert " passed" in tail
-
-
 def test_indptr64_kernels():
     """The uint64-indptr instantiations (taken for nnz >= 2^32, far beyond test sizes) through
     the SPRS_B200_FORCE_INDPTR64 test hook: every SpMV / SpMM / conversion / solver test again
@@ -211,7 +171,7 @@ def test_indptr64_kernels():
         [os.path.join(root, "tests", f) for f in files] +
         ["-k", "not spgemm and not csc_csc and not csc_csr and not issue_99 and not "
                "structural_zeros and not csvec and not full_size and not test_cpp and not "
-               "l2_blocked and not indptr64 and not unrolled_variant"],
+               "indptr64"],
         capture_output=True, text=True, timeout=1500, env=env, cwd=root)
     tail = "\n".join(r.stdout.splitlines()[-15:])
     assert r.returncode == 0, tail + r.stderr[-1500:]

@@ -1,10 +1,9 @@
-"""Chunked host path (SPRS_B200_E2E_PIPELINE=2, api.cu spmv_host_chunked): the tile stream in a
+"""Chunked host path (SPRS_B200_E2E_CHUNKS=n, api.cu spmv_host_chunked): the tile stream in a
 few chunks, each chunk's finished rows copied to the host while the next chunk computes.  The
 result must be bit-identical to the one-shot device SpMV (same kernel, same carry sums).
 
-The switch is read once per process: the cases run in a child process with it set.  Written
-after the round's last GPU session: opt-in on hardware (SPRS_B200_TEST_E2E_CHUNKED=1, run by
-tools/r2_first_call.sh), always part of the CPU emulator pre-flight."""
+The switch is read once per process: the cases run in a child process with it set (and with
+the test hook SPRS_B200_E2E_MIN_TILES=1, so that small matrices take the chunked path)."""
 import ctypes as C
 import os
 import subprocess
@@ -16,12 +15,9 @@ import pytest
 from conftest import rand_csr
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-IN_CHILD = os.environ.get("SPRS_B200_E2E_PIPELINE") == "2"
+IN_CHILD = os.environ.get("SPRS_B200_E2E_MIN_TILES") == "1"
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not IN_CHILD and os.environ.get("SPRS_B200_TEST_E2E_CHUNKED") != "1"
-                                 and os.environ.get("SPRS_B200_EMU") != "1",
-                                 reason="opt-in until first hardware run: SPRS_B200_TEST_E2E_CHUNKED=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")
@@ -60,7 +56,7 @@ def _check(sp, csr, rows, cols, accumulate):
         assert np.array_equal(y, want)
 
 
-@pytest.mark.skipif(not IN_CHILD, reason="runs in the child process with SPRS_B200_E2E_PIPELINE=2")
+@pytest.mark.skipif(not IN_CHILD, reason="runs in the child process with SPRS_B200_E2E_CHUNKS set")
 @pytest.mark.parametrize("accumulate", [False, True])
 def test_chunked_host_path_matches_device_spmv(sp, accumulate):
     rng = np.random.default_rng(31)
@@ -68,7 +64,7 @@ def test_chunked_host_path_matches_device_spmv(sp, accumulate):
     _check(sp, rand_csr(rng, rows, cols, 30, empty_frac=0.15), rows, cols, accumulate)
 
 
-@pytest.mark.skipif(not IN_CHILD, reason="runs in the child process with SPRS_B200_E2E_PIPELINE=2")
+@pytest.mark.skipif(not IN_CHILD, reason="runs in the child process with SPRS_B200_E2E_CHUNKS set")
 def test_chunked_host_path_hub_rows_across_chunks(sp):
     """Rows much longer than a chunk: their carries cross chunk boundaries; trailing and
     leading empty rows belong to the first / last chunk."""
@@ -78,7 +74,7 @@ def test_chunked_host_path_hub_rows_across_chunks(sp):
     lens = np.diff(ip.astype(np.int64))
     lens[:40] = 0
     lens[-55:] = 0
-    lens[100] = 20000           # ~52 tiles of 384: spans several of the 5 chunks
+    lens[100] = 20000           # ~20 tiles of 1024: spans several of the 5 chunks
     lens[2500] = 9000
     ip2 = np.zeros(rows + 1, dtype=np.int64)
     np.cumsum(lens, out=ip2[1:])
@@ -91,7 +87,7 @@ def test_chunked_host_path_hub_rows_across_chunks(sp):
 @pytest.mark.skipif(IN_CHILD, reason="parent side")
 @pytest.mark.parametrize("chunks", ["5", "8", "1"])
 def test_e2e_chunked_child_process(chunks):
-    env = dict(os.environ, SPRS_B200_E2E_PIPELINE="2", SPRS_B200_E2E_CHUNKS=chunks)
+    env = dict(os.environ, SPRS_B200_E2E_MIN_TILES="1", SPRS_B200_E2E_CHUNKS=chunks)
     r = subprocess.run(
         [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
          os.path.join(ROOT, "tests", "test_gpu_zzz_e2e_chunked.py"),
