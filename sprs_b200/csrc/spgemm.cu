@@ -545,6 +545,9 @@ __global__ void __launch_bounds__(PANEL_NT)
             uint32_t grp_taken = 0;  // G > 1: entries of the group's B row this warp consumed
             bool landed = false;
             // two A non-zeros (kk, kk + ngrp) per pass, their chunks interleaved
+            // two A non-zeros (kk, kk + ngrp) per pass, their chunks interleaved.  (Handing the
+            // pairs out dynamically inside a panel measured 21 % SLOWER than this static deal,
+            // profiles/r2_spgemm_notes.md.)
             for (uint32_t kk = grp; kk < na; kk += 2 * ngrp) {
                 const uint32_t kb = kk + ngrp;
                 const bool has_b = kb < na;
@@ -745,10 +748,12 @@ int run_numeric(sprs_b200_ctx* ctx, sprs_b200_spgemm* p, uint32_t* d_cidx, doubl
     SPRS_CUDA(ctx, cudaMemsetAsync(p->d_counters, 0, 8 * sizeof(uint32_t), s));
     // rows with more than 16 entries per column panel are cheaper in the panel kernel (no
     // probing, no sort; fixed cost ~ n_panels) than in the CTA hash map
-    // (measured: a row costs the panel kernel ~900 instructions per warp and panel whatever it
-    // holds -- 71 G instructions for config 4 when rows from 500 entries up went there; the CTA
-    // hash map is an order of magnitude cheaper up to its 4096 entries)
-    const uint32_t num_m_max = NUM_M_MAX;
+    // Hash map or panels?  A row costs the panel kernel ~900 instructions per warp and panel
+    // whatever it holds (ncu: 71 G instructions on config 4, half of the stall samples at the
+    // panel barriers), the CTA hash map pays per product plus a bitonic sort of its table.
+    // Measured on config 4 with the cut at 496 / 1024 / 2048 / 4096 entries: 290 / 249 / 318 /
+    // 307 ms for the whole product (profiles/r2_spgemm_notes.md) -> 1024.
+    const uint32_t num_m_max = std::min<uint32_t>(NUM_M_MAX, 1024);
     bin_rows_kernel<uint32_t><<<grid_for(rows), 256, 0, s>>>(p->d_cnt, rows, NUM_S_MAX, num_m_max,
                                                             p->d_lists, p->d_counters, nullptr);
     ctx->launches += 1;

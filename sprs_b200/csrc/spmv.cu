@@ -101,42 +101,13 @@ __device__ __forceinline__ void sink_row(const RowSink& k, uint64_t r, double su
 // Rows [r0, r_last] of one warp tile [k0, k1), G lanes per row (32/G rows at a time): every
 // group walks ITS row's part of the tile with stride G, straight from global memory -- index,
 // value (coalesced inside the group, L1::no_allocate, L2 evict_first) and the x gather (L2
-// evict_last), U of each in flight per lane -- adds its products in storage order, and one
+// evict_last), U of each in flight per lane (template parameter) -- adds its products in storage order, and one
 // G-lane butterfly finishes the row.  Nothing is staged and nothing but the row sum crosses
 // lanes: ~0.5 instructions per non-zero, against ~1.5 for reducing products staged in shared
 // memory or registers (profiles/r2_spmv_notes.md).  G = 1: one lane sums a whole row in
 // storage order, i.e. the reference's bits.  Row boundaries come 31 rows at a time: lane L
 // holds indptr[rbase + L].
-// A hub row met inside a tile of short rows (much longer than its G-lane group could walk): the
-// whole warp takes it, U x 32 elements per step.  Rare; kept out of line.
-template <typename P, bool MULTI>
-__device__ __forceinline__ void long_row(const RowSink& k, const uint32_t* __restrict__ indices,
-                                      const double* __restrict__ data, const double* __restrict__ x,
-                                      P qs, P qe, uint32_t row, uint64_t pol_stream, uint64_t polx,
-                                      int lane) {
-    constexpr int U = 4;
-    double a2 = 0.0;
-    for (P w = qs + lane; w < qe; w += (P)(32 * U)) {
-        uint32_t c2[U];
-        double v2[U], x2[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            c2[u] = w + (P)(u * 32) < qe ? ldg_stream_u32(indices + w + (P)(u * 32), pol_stream) : 0u;
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            v2[u] = w + (P)(u * 32) < qe ? ldg_stream_f64(data + w + (P)(u * 32), pol_stream) : 0.0;
-#pragma unroll
-        for (int u = 0; u < U; ++u) x2[u] = w + (P)(u * 32) < qe ? ldg_f64_hint(x + c2[u], polx) : 0.0;
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (w + (P)(u * 32) < qe) a2 = __dadd_rn(a2, __dmul_rn(v2[u], x2[u]));
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a2 = __dadd_rn(a2, __shfl_xor_sync(0xffffffffu, a2, o));
-    if (lane == 0) sink_row<MULTI>(k, (uint64_t)row, a2);
-}
-
-template <typename P, int G, bool MULTI>
+template <typename P, int G, int U, bool MULTI>
 __device__ __forceinline__ void rows_direct(const RowSink& k, const P* __restrict__ indptr,
                                             const uint32_t* __restrict__ indices,
                                             const double* __restrict__ data,
@@ -144,103 +115,83 @@ __device__ __forceinline__ void rows_direct(const RowSink& k, const P* __restric
                                             uint32_t r0, uint32_t r_last, P b_first,
                                             uint64_t pol_stream, uint64_t polx, int lane) {
     constexpr int NG = 32 / G;
-    constexpr int U = 4;  // loads in flight per lane and kind
     constexpr unsigned FULL = 0xffffffffu;
     const int gid = lane / G, gl = lane % G;
     // (offsets are as wide as the indptr: 32 bits unless nnz >= 2^32; row indices are 32-bit)
-    // A "step" is U*G consecutive elements of each group's current row.  The INDICES of the next
-    // step are loaded while the gathers and values of the current one are in flight, so a step
-    // exposes one memory round trip (gather / value) instead of two (index, then gather).
-    P b = b_first;           // lane L: indptr[rbase + L]
-    uint32_t rbase = r0;     // first row of the current block of 31 boundaries
-    int nrows = (r_last - rbase) < 31u ? (int)(r_last - rbase) + 1 : 31;
-    int j0 = 0;              // first row (within the block) of the current pass
-    P q = 0, e = 0;          // this group's cursor / end in its current row
-    bool emit = false;       // this group's row gets its sum from the steps below
-    auto open_pass = [&]() {  // boundaries of rows rbase + j0 + gid -> q, e (clamped to the tile)
-        const int j = j0 + gid;
-        const bool valid = j < nrows;
-        const int js = valid ? j : 0;
-        P s = __shfl_sync(FULL, b, js);
-        P en = __shfl_sync(FULL, b, js + 1);
-        s = s > k0 ? s : k0;
-        en = en < k1 ? en : k1;
-        if (!valid || en < s) en = s;
-        bool is_long = false;
-        if (G < 32) {  // rows much longer than their group: the whole warp takes them, now
-            is_long = (en - s) > (P)(16 * G * U);
-            unsigned pending = __ballot_sync(FULL, gl == 0 && is_long);
-            while (pending) {
-                const int src = __ffs(pending) - 1;
-                pending &= pending - 1;
-                long_row<P, MULTI>(k, indices, data, x, __shfl_sync(FULL, s, src),
-                                   __shfl_sync(FULL, en, src), rbase + (uint32_t)(j0 + src / G),
-                                   pol_stream, polx, lane);
+    P b = b_first;  // boundaries of the first chunk were prefetched by the caller
+    for (uint32_t rbase = r0;; rbase += 31) {
+        if (rbase != r0) {
+            const uint32_t rr = rbase + lane;  // r_last + 1 <= rows < 2^32: no wrap for rr <= r_last + 1
+            b = (rr >= rbase && rr <= r_last + 1) ? indptr[rr] : (P)0;
+        }
+        const int nrows = (r_last - rbase + 1) < 31 ? (int)(r_last - rbase + 1) : 31;
+        for (int j0 = 0; j0 < nrows; j0 += NG) {
+            const int j = j0 + gid;
+            const bool valid = j < nrows;
+            const int js = valid ? j : 0;
+            P s = __shfl_sync(FULL, b, js);
+            P e = __shfl_sync(FULL, b, js + 1);
+            s = s > k0 ? s : k0;
+            e = e < k1 ? e : k1;
+            if (!valid || e < s) e = s;
+            // a row much longer than its group would serialise the warp behind G lanes: such
+            // rows (a hub row inside a tile of short rows) are taken by the whole warp below
+            const bool is_long = (G < 32) && (e - s) > (P)(16 * G * U);
+            double acc = 0.0;
+            for (P q = s + gl; q < (is_long ? s : e); q += (P)(G * U)) {
+                uint32_t c[U];
+                double v[U], xv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    c[u] = q + (P)(u * G) < e ? ldg_stream_u32(indices + q + (P)(u * G), pol_stream) : 0u;
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    v[u] = q + (P)(u * G) < e ? ldg_stream_f64(data + q + (P)(u * G), pol_stream) : 0.0;
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    xv[u] = q + (P)(u * G) < e ? ldg_f64_hint(x + c[u], polx) : 0.0;
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (q + (P)(u * G) < e) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
             }
-        }
-        q = s + gl;
-        e = is_long ? s : en;
-        emit = valid && !is_long;
-    };
-    open_pass();
-    uint32_t c[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-        c[u] = q + (P)(u * G) < e ? ldg_stream_u32(indices + q + (P)(u * G), pol_stream) : 0u;
-    double acc = 0.0;
-    for (;;) {
-        // operands of the current step
-        double v[U], xv[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) xv[u] = q + (P)(u * G) < e ? ldg_f64_hint(x + c[u], polx) : 0.0;
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            v[u] = q + (P)(u * G) < e ? ldg_stream_f64(data + q + (P)(u * G), pol_stream) : 0.0;
-        unsigned live = 0;  // which of the U slots of this step are real
-#pragma unroll
-        for (int u = 0; u < U; ++u) live |= (q + (P)(u * G) < e ? 1u : 0u) << u;
-        // where the next step is: further along the same rows, the next rows, the next block
-        const bool more = __any_sync(FULL, q + (P)(G * U) < e);
-        const bool emit_cur = emit;
-        const uint32_t row_cur = rbase + (uint32_t)(j0 + gid);
-        bool finished = false;
-        if (more) {
-            q += (P)(G * U);
-        } else {
-            j0 += NG;
-            if (j0 >= nrows) {
-                if (r_last - rbase < 31u) {
-                    finished = true;
-                } else {
-                    rbase += 31;
-                    const uint32_t rr = rbase + lane;  // r_last + 1 <= rows: no wrap below it
-                    b = (rr >= rbase && rr <= r_last + 1) ? indptr[rr] : (P)0;
-                    nrows = (r_last - rbase) < 31u ? (int)(r_last - rbase) + 1 : 31;
-                    j0 = 0;
-                }
-            }
-            if (!finished) open_pass();
-        }
-        if (!finished) {  // indices of the next step, in flight under this step's gathers
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                c[u] = q + (P)(u * G) < e ? ldg_stream_u32(indices + q + (P)(u * G), pol_stream) : 0u;
-        }
-        // consume the current step (storage order inside a lane)
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if ((live >> u) & 1u) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
-        if (!more) {
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(FULL, acc, o));
-            if (gl == 0 && emit_cur) sink_row<MULTI>(k, (uint64_t)row_cur, acc);
-            acc = 0.0;
+            if (G < 32) {
+                unsigned pending = __ballot_sync(FULL, gl == 0 && is_long);
+                while (pending) {
+                    const int src = __ffs(pending) - 1;
+                    pending &= pending - 1;
+                    const P qs = __shfl_sync(FULL, s, src), qe = __shfl_sync(FULL, e, src);
+                    const int jj = __shfl_sync(FULL, j, src);
+                    double a2 = 0.0;
+                    for (P q = qs + lane; q < qe; q += (P)(32 * U)) {
+                        uint32_t c[U];
+                        double v[U], xv[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            c[u] = q + (P)(u * 32) < qe ? ldg_stream_u32(indices + q + (P)(u * 32), pol_stream) : 0u;
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            v[u] = q + (P)(u * 32) < qe ? ldg_stream_f64(data + q + (P)(u * 32), pol_stream) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            xv[u] = q + (P)(u * 32) < qe ? ldg_f64_hint(x + c[u], polx) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            if (q + (P)(u * 32) < qe) a2 = __dadd_rn(a2, __dmul_rn(v[u], xv[u]));
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) a2 = __dadd_rn(a2, __shfl_xor_sync(FULL, a2, o));
+                    if (lane == 0) sink_row<MULTI>(k, (uint64_t)rbase + jj, a2);
+                }
+            }
+            if (gl == 0 && valid && !is_long) sink_row<MULTI>(k, (uint64_t)rbase + j, acc);
         }
-        if (finished) break;
+        if (r_last - rbase < 31) break;  // (also ends the loop when rbase + 31 would wrap)
     }
 }
 
-template <typename P, int WT, int NWARPS, int MINB, bool MULTI>
+template <typename P, int WT, int NWARPS, int MINB, int U, bool MULTI>
 __global__ void __launch_bounds__(NWARPS * 32, MINB)
     spmv_rows_kernel(const P* __restrict__ indptr, const uint32_t* __restrict__ indices,
                      const double* __restrict__ data, const uint32_t* __restrict__ tile_row,
@@ -278,7 +229,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
         const uint32_t r_last = r1 < rows ? r1 : r1 - 1;
         const uint64_t cnt = k1 - k0, nr = (uint64_t)(r_last - r0) + 1;  // mean row length = cnt / nr
 #define SPMV_ROWS(G)                                                                            \
-    rows_direct<P, G, MULTI>(sink, indptr, indices, data, x, k0, k1, r0, r_last, b_first,       \
+    rows_direct<P, G, U, MULTI>(sink, indptr, indices, data, x, k0, k1, r0, r_last, b_first,       \
                              pol_stream, polx, lane)
         if (cnt <= 6 * nr)
             SPMV_ROWS(1);
@@ -376,17 +327,18 @@ __global__ void spmv_fixup_range_kernel(const uint32_t* __restrict__ tile_row, c
 
 // ---- launch configuration ---------------------------------------------------------
 struct SpmvVariant {
-    int wt, ctas_per_sm;
+    int wt, ctas_per_sm, u;
 };
 // default picked from the round-2 sweeps (profiles/r2_spmv_notes.md);
-// SPRS_B200_SPMV_VARIANT="wt,ctas" overrides it for tuning runs (read once per process: the
-// tile size is baked into every mirror's tile_row).
+// SPRS_B200_SPMV_VARIANT="wt,ctas,u" (tile nnz, CTAs of 8 warps per SM, loads in flight per lane
+// and kind) overrides it for tuning runs (read once per process: the tile size is baked into
+// every mirror's tile_row).
 SpmvVariant spmv_variant() {
     static SpmvVariant v = [] {
-        SpmvVariant d{1024, 4};
+        SpmvVariant d{1024, 5, 4};
         if (const char* e = getenv("SPRS_B200_SPMV_VARIANT")) {
-            int a, b;
-            if (sscanf(e, "%d,%d", &a, &b) == 2) d = SpmvVariant{a, b};
+            int a, b, c;
+            if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3) d = SpmvVariant{a, b, c};
         }
         return d;
     }();
@@ -395,7 +347,7 @@ SpmvVariant spmv_variant() {
 
 constexpr int SPMV_NWARPS = 8;
 
-template <typename P, int WT, int CTAS>
+template <typename P, int WT, int CTAS, int U>
 int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
                    const SpmvTargets& yt, int accumulate, uint64_t t0, uint64_t t1,
                    cudaStream_t s) {
@@ -404,8 +356,8 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
     // CTAS resident CTAs per SM is also the kernel's __launch_bounds__ minBlocks: it sets the
     // register budget (the kernel hides latency with warps, not with registers).
     const bool multi = yt.n > 1;
-    auto kern = multi ? spmv_rows_kernel<P, WT, SPMV_NWARPS, CTAS, true>
-                      : spmv_rows_kernel<P, WT, SPMV_NWARPS, CTAS, false>;
+    auto kern = multi ? spmv_rows_kernel<P, WT, SPMV_NWARPS, CTAS, U, true>
+                      : spmv_rows_kernel<P, WT, SPMV_NWARPS, CTAS, U, false>;
     static bool configured_flags[64][2] = {};  // function attributes are per device
     bool& configured = configured_flags[ctx->device & 63][multi ? 1 : 0];
     if (!configured) {
@@ -433,15 +385,14 @@ int launch_dispatch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* 
                     const SpmvTargets& yt, int accumulate, uint64_t t0, uint64_t t1,
                     cudaStream_t s) {
     const SpmvVariant v = spmv_variant();
-#define SPMV_CASE(W, CT)                                                          \
-    if (v.wt == W && v.ctas_per_sm == CT)                                         \
-        return launch_variant<P, W, CT>(ctx, m, d_x, yt, accumulate, t0, t1, s);
-    SPMV_CASE(1024, 4)
-    SPMV_CASE(1024, 5)
-    SPMV_CASE(1024, 3)
-    SPMV_CASE(2048, 4)
+#define SPMV_CASE(W, CT, UU)                                                      \
+    if (v.wt == W && v.ctas_per_sm == CT && v.u == UU)                            \
+        return launch_variant<P, W, CT, UU>(ctx, m, d_x, yt, accumulate, t0, t1, s);
+    SPMV_CASE(1024, 5, 4)
+    SPMV_CASE(1024, 4, 6)
+    SPMV_CASE(1024, 4, 8)
 #undef SPMV_CASE
-    SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "unknown SPRS_B200_SPMV_VARIANT (wt,ctas)");
+    SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "unknown SPRS_B200_SPMV_VARIANT (wt,ctas,u)");
 }
 
 int check_spmv_args(sprs_b200_ctx* ctx, const sprs_b200_csmat* m) {
