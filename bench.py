@@ -406,8 +406,9 @@ def main():
             cpu_base = {"error": repr(e)}
     t_gen = time.time() - t_gen
     if args.exchange == "auto":
-        # measured at 2/4/8 GPUs (profiles/r2_scale_probe.md): see DESIGN.md section 5
-        args.exchange = "push"
+        # measured at 2 and 8 GPUs (profiles/r2_scale_modes_*.txt): the
+        # SpMV kernel storing every finished row itself beats the put kernel and NCCL
+        args.exchange = "fused"
     use_comm = world > 1 and args.exchange in ("fused", "push")
 
     def make_op(a_blk, bnds):

@@ -74,7 +74,13 @@ int sprs_b200_csmat_upload(sprs_b200_ctx* ctx, int storage, uint64_t rows, uint6
                            const void* indptr, int indptr_bytes, const void* indices,
                            int index_bytes, const double* data, sprs_b200_csmat** out);
 /* Adopt device-resident arrays (u32, zero-based, 16-byte aligned) without copying; the
- * caller keeps ownership and must keep them alive.  Used by generators / benchmarks. */
+ * caller keeps ownership and must keep them alive.  Used by generators / benchmarks.
+ * The arrays must be COMPLETE when the call is made (it reads them on the ctx's own stream:
+ * synchronise the stream that produced them first).  upload / from_device adopt the structure
+ * as given, like CsMatBase::new_unchecked: out-of-range indices are the caller's contract
+ * (the host mirrors check it, sparse.rs:300-369; sprs_b200_csmat_check_structure does so on the
+ * device).  One product at a time per mirror: a mirror carries the SpMV's per-tile carry
+ * scratch, so two SpMVs of the SAME mirror must not be in flight on different streams.     */
 int sprs_b200_csmat_from_device(sprs_b200_ctx* ctx, int storage, uint64_t rows, uint64_t cols,
                                 uint64_t nnz, const uint32_t* d_indptr,
                                 const uint32_t* d_indices, const double* d_data,
@@ -93,7 +99,8 @@ int sprs_b200_csmat_device_arrays(const sprs_b200_csmat* m, const void** d_indpt
                                   const double** d_data);
 /* TriMatBase::to_csr (sprs/src/sparse/triplet_iter.rs:127-224): COO triplets in any order,
  * duplicates allowed -> CSR mirror with ascending unique columns per row, duplicate entries
- * SUMMED (in insertion order).  Host arrays (index width 4 or 8) or device u32 arrays.   */
+ * SUMMED (in insertion order).  Host arrays (index width 4 or 8) or device u32 arrays.
+ * A triplet outside rows x cols returns ERR_STRUCTURE (the reference asserts in add_triplet). */
 int sprs_b200_csmat_from_triplets(sprs_b200_ctx* ctx, uint64_t rows, uint64_t cols, uint64_t n,
                                   const void* row_inds, const void* col_inds, int index_bytes,
                                   const double* data, sprs_b200_csmat** out);

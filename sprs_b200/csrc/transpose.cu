@@ -306,11 +306,37 @@ int transpose_launch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, sprs_b200_csm
 // column indices per row and duplicates summed: TriMatBase::to_csr
 // (sprs/src/sparse/triplet_iter.rs:127-224).  Two stable radix sorts (by column, then by
 // row) give the (row, col) order; duplicates are summed in insertion order.
+namespace {
+__global__ void triplet_bounds_kernel(const uint32_t* __restrict__ row, const uint32_t* __restrict__ col,
+                                      uint64_t n, uint32_t rows, uint32_t cols,
+                                      unsigned long long* __restrict__ bad) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i < n && (row[i] >= rows || col[i] >= cols)) atomicAdd(bad, 1ull);
+}
+}  // namespace
+
 int triplets_to_csr_launch(sprs_b200_ctx* ctx, uint64_t rows, uint64_t cols, uint64_t n,
                            const uint32_t* d_row, const uint32_t* d_col, const double* d_val,
                            sprs_b200_csmat* t, cudaStream_t s) {
     if (n >= 0xffffffffull || rows > 0xffffffffull || cols > 0xffffffffull)
         SPRS_FAIL(ctx, SPRS_B200_ERR_INDEX_RANGE, "from_triplets: needs nnz, rows, cols < 2^32");
+    if (n) {  // the reference panics on an out-of-range triplet (TriMatBase::add_triplet asserts);
+              // here it would be an out-of-bounds device write in the counting pass
+        unsigned long long* d_bad = nullptr;
+        unsigned long long h_bad = 0;
+        SPRS_CUDA(ctx, cudaMalloc((void**)&d_bad, 8));
+        cudaMemsetAsync(d_bad, 0, 8, s);
+        triplet_bounds_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_row, d_col, n, (uint32_t)rows,
+                                                                          (uint32_t)cols, d_bad);
+        ctx->launches += 1;
+        cudaMemcpyAsync(&h_bad, d_bad, 8, cudaMemcpyDeviceToHost, s);
+        const cudaError_t e = cudaStreamSynchronize(s);
+        cudaFree(d_bad);
+        if (e != cudaSuccess) SPRS_FAIL(ctx, SPRS_B200_ERR_CUDA, "from_triplets: %s", cudaGetErrorString(e));
+        if (h_bad)
+            SPRS_FAIL(ctx, SPRS_B200_ERR_STRUCTURE, "from_triplets: %llu triplet(s) outside %llu x %llu",
+                      h_bad, (unsigned long long)rows, (unsigned long long)cols);
+    }
     t->ctx = ctx;
     t->storage = SPRS_B200_CSR;
     t->rows = rows;

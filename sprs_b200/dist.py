@@ -27,6 +27,8 @@ def nnz_balanced_bounds(indptr, nparts, row_cost=0.0):
     if is_torch:
         import torch
         ip = indptr.to(torch.int64)
+        if indptr.dtype == torch.int32:
+            ip = ip & 0xFFFFFFFF  # int32 storage of u32 values (nnz < 2^32)
         base = int(ip[0].item())
         nnz = int(ip[-1].item()) - base
         if nparts > 1 and row_cost > 0:
@@ -66,6 +68,8 @@ def rebalance_bounds(indptr, bounds, times, row_cost=0.0):
     import torch
     ip = indptr.to(torch.int64) if isinstance(indptr, torch.Tensor) else torch.from_numpy(
         np.asarray(indptr).astype(np.int64))
+    if isinstance(indptr, torch.Tensor) and indptr.dtype == torch.int32:
+        ip = ip & 0xFFFFFFFF  # int32 storage of u32 values
     rows = ip.shape[0] - 1
     cost = (ip - ip[0]).to(torch.float64) + row_cost * torch.arange(rows + 1, device=ip.device,
                                                                     dtype=torch.float64)
@@ -248,7 +252,7 @@ class RowPartitionedSpGEMM:
         data = torch.empty(total, dtype=dat_l.dtype, device=dat_l.device)
         ip_views = [indptr[self.bounds[g]:self.bounds[g + 1]] for g in range(self.world)]
         ip_views[self.rank].copy_(mine[:-1])
-        indptr[n] = total
+        indptr[n:n + 1] = torch.tensor([total], dtype=torch.int64).to(ptr_dtype)  # wraps like u32
         ends = offsets[1:] + [total]
         ind_views = [indices[offsets[g]:ends[g]] for g in range(self.world)]
         dat_views = [data[offsets[g]:ends[g]] for g in range(self.world)]

@@ -48,6 +48,11 @@ class DeviceCsr:
         self.ctx, self.rows, self.cols = ctx, rows, cols
         self.indptr, self.indices, self.data = indptr, indices, data
         self.nnz = int(indices.numel())
+        # the arrays were produced on torch's current stream; the library builds the mirror's
+        # SpMV partition on ITS stream: make them ready first (sprs_b200.h: from_device adopts
+        # arrays that must be complete when the call is made)
+        if indptr.is_cuda:
+            _sync()
         h = C.c_void_p()
         ctx.check(ctx.lib.sprs_b200_csmat_from_device(
             ctx.h, _lib.CSR, rows, cols, self.nnz, _dptr(indptr), _dptr(indices), _dptr(data),
@@ -56,14 +61,20 @@ class DeviceCsr:
 
     def slice_rows(self, r0, r1):
         """slice_outer(r0..r1) + proper_indptr (slicing.rs:65-89, csmat.rs:919-921)."""
-        s, e = int(self.indptr[r0].item()), int(self.indptr[r1].item())
-        ip = (self.indptr[r0:r1 + 1] - s).contiguous()
+        s, e = u32(self.indptr[r0]), u32(self.indptr[r1])  # int32 storage of u32 values
+        ip = (self.indptr[r0:r1 + 1] - self.indptr[r0]).contiguous()  # wraps to the right u32
         return DeviceCsr(self.ctx, r1 - r0, self.cols, ip, self.indices[s:e].clone(),
                          self.data[s:e].clone())
 
     def to_host(self):
         return (self.indptr.cpu().numpy().view(np.uint32), self.indices.cpu().numpy().view(np.uint32),
                 self.data.cpu().numpy())
+
+
+def u32(t):
+    """Python int of one element of an int32 tensor that stores a u32 value (nnz < 2^32)."""
+    v = int(t.item())
+    return v & 0xFFFFFFFF if t.dtype == torch.int32 else v
 
 
 def _keys_to_csr(ctx, keys, rows, cols, seed):
@@ -201,6 +212,8 @@ def spgemm(ctx, a, b):
     ma = a.mirror if isinstance(a, DeviceCsr) else a
     mb = b.mirror if isinstance(b, DeviceCsr) else b
     lib = ctx.lib
+    if _device(ctx).type == "cuda":
+        _sync()  # operands produced on torch's stream; symbolic / numeric run on the ctx stream
     plan, nnz_c, cm = C.c_void_p(), C.c_uint64(), C.c_void_p()
     ctx.check(lib.sprs_b200_spgemm_symbolic(ctx.h, ma.h, mb.h, C.byref(plan), C.byref(nnz_c)))
     try:

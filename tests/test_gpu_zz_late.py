@@ -258,3 +258,99 @@ def test_csvec_dot(sp, fixtures):
         vec["vec1"].dot(sp.CsVec(k["panic_dims"]["sparse"], k["vec2"]["indices"], k["vec2"]["data"]))
     with pytest.raises(sp.SprsPanic):
         vec["vec1"].dot(np.arange(float(k["panic_dims"]["dense"])))
+
+
+def test_from_triplets_rejects_out_of_range_through_the_c_abi(sp):
+    """A raw C caller (no host mirror in front) handing an out-of-range triplet gets
+    ERR_STRUCTURE instead of an out-of-bounds device write (the reference asserts in
+    TriMatBase::add_triplet, triplet.rs)."""
+    import ctypes as C
+    from sprs_b200 import _lib
+    ctx = sp.Context.default()
+    r = np.array([0, 1, 7], dtype=np.uint64)      # row 7 in a 4 x 4 matrix
+    c = np.array([0, 2, 1], dtype=np.uint64)
+    d = np.array([1.0, 2.0, 3.0])
+    h = C.c_void_p()
+    st = ctx.lib.sprs_b200_csmat_from_triplets(ctx.h, 4, 4, 3, r.ctypes.data_as(C.c_void_p),
+                                               c.ctypes.data_as(C.c_void_p), 8,
+                                               d.ctypes.data_as(C.c_void_p), C.byref(h))
+    assert st == _lib.ERR_STRUCTURE and not h.value
+    assert b"outside" in ctx.lib.sprs_b200_last_error(ctx.h)
+
+
+def _whole_vector_vs_oracle(sp, O, a, x):
+    """y = A x on the device against the CPU oracle for EVERY row (gate 1e-6 * sum|terms|)."""
+    import torch
+    from sprs_b200 import generate as G
+    ctx = sp.Context.default()
+    y = torch.empty(a.rows, device=x.device, dtype=torch.float64)
+    G.spmv(ctx, a, x, y)
+    G._sync()
+    hip, hind, hdat = a.to_host()
+    hx = x.cpu().numpy()
+    ref, bound = np.zeros(a.rows), np.zeros(a.rows)
+    O.mul_acc_mat_vec_csr(hip, hind, hdat, hx, ref)
+    np.abs(hdat, out=hdat)
+    O.mul_acc_mat_vec_csr(hip, hind, hdat, np.abs(hx), bound)
+    got = y.cpu().numpy()
+    assert np.all(np.isfinite(got))
+    excess = np.abs(got - ref) - (RTOL * bound + 1e-300)
+    assert excess.max() <= 0.0, (int(np.argmax(excess)), float(excess.max()))
+
+
+def test_spmv_rand_1m_whole_vector_full_size(sp, O):
+    """BASELINE config 2 (1M x 1M sprs-rand, 32 nnz/row): every one of the 1e6 outputs against
+    the oracle (prod.rs:274-298 restated)."""
+    from sprs_b200 import generate as G
+    ctx = sp.Context.default()
+    a = G.rand_csr(ctx, 1_000_000, 1_000_000, 32, seed=0x5EED0002)
+    _whole_vector_vs_oracle(sp, O, a, G.normal_vector(ctx, 1_000_000))
+
+
+def test_spmv_rmat_10m_whole_vector_full_size(sp, O):
+    """BASELINE config 5 (10M x 10M R-MAT, ~1e9 nnz): every one of the 1e7 outputs against the
+    oracle -- the CPU port walks the whole matrix in a few seconds."""
+    from sprs_b200 import generate as G
+    ctx = sp.Context.default()
+    a = G.rmat_csr(ctx, 10_000_000, 100, seed=0x5EED0005)
+    _whole_vector_vs_oracle(sp, O, a, G.normal_vector(ctx, 10_000_000))
+
+
+def test_spgemm_rmat_500k_row_block_bit_exact_full_size(sp, O):
+    """BASELINE config 4 at full size: the rows of C = A B for a block of A holding >= 1e8
+    products -- indptr and indices BIT-EXACT against the oracle (smmp.rs:81-131, 409-415),
+    values within the gate (smmp.rs:151-189)."""
+    import ctypes as C_
+    import torch
+    from sprs_b200 import generate as G
+    ctx = sp.Context.default()
+    n = 500_000
+    A = G.rmat_csr(ctx, n, 16, seed=0x5EED0004)
+    B = G.rmat_csr(ctx, n, 16, seed=0x5EED1004)
+    cmir, cip, cind, cdat = G.spgemm(ctx, A, B)
+    # a row block of A with >= 1e8 products: n_prod_i = sum_k nnz(B_k) over A_i
+    aip = (A.indptr.to(torch.int64) & 0xFFFFFFFF)
+    blen = ((B.indptr[1:].to(torch.int64) & 0xFFFFFFFF) - (B.indptr[:-1].to(torch.int64) & 0xFFFFFFFF))
+    per_nnz = blen[A.indices.to(torch.int64) & 0xFFFFFFFF]
+    csum = torch.cumsum(per_nnz, 0)
+    r0 = 2000
+    base = int(csum[int(aip[r0]) - 1].item()) if int(aip[r0]) > 0 else 0
+    k_end = int(torch.searchsorted(csum, torch.tensor([base + 100_000_000], device=csum.device))[0])
+    r1 = min(n, int(torch.searchsorted(aip, torch.tensor([k_end], device=aip.device))[0]) + 1)
+    nprod_blk = int(csum[int(aip[r1]) - 1].item()) - base
+    assert nprod_blk >= 100_000_000
+    blk = A.slice_rows(r0, r1)
+    oip, oind, odat = O.mul_csr_csr((r1 - r0, n), blk.to_host(), (n, n), B.to_host(), threads=0)
+    cip64 = cip.to(torch.int64)
+    if cip.dtype == torch.int32:
+        cip64 &= 0xFFFFFFFF
+    s, e = int(cip64[r0]), int(cip64[r1])
+    assert np.array_equal((cip64[r0:r1 + 1] - s).cpu().numpy(), np.asarray(oip, dtype=np.int64))
+    assert np.array_equal(cind[s:e].cpu().numpy().view(np.uint32), np.asarray(oind, dtype=np.uint32))
+    got = cdat[s:e].cpu().numpy()
+    # gate per entry: 1e-6 * sum |a_ik b_kj|, from the same product on absolute values
+    absA = (blk.to_host()[0], blk.to_host()[1], np.abs(blk.to_host()[2]))
+    bh = B.to_host()
+    _, _, obound = O.mul_csr_csr((r1 - r0, n), absA, (n, n), (bh[0], bh[1], np.abs(bh[2])), threads=0)
+    assert np.all(np.abs(got - np.asarray(odat)) <= RTOL * np.asarray(obound) + 1e-300)
+    del cmir
