@@ -423,8 +423,8 @@ def main():
     op = make_op(a, bounds)
     rebalanced = 0
     if world > 1:
-        # measured re-balancing with the REAL operator: up to two rounds of equal-time re-cuts
-        for _ in range(2):
+        # measured re-balancing with the REAL operator: up to four rounds of equal-time re-cuts
+        for _ in range(4):
             for _ in range(2):
                 op.step(x)
             ce0, ce1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -439,7 +439,7 @@ def main():
                 torch.cuda.synchronize()
                 tsum += ce0.elapsed_time(ce1)
             times = [float(v[0]) for v in comm.allgather_f64([tsum / 4])]
-            if max(times) <= 1.03 * (sum(times) / world):
+            if max(times) <= 1.02 * (sum(times) / world):
                 break
             nb = rebalance_bounds(full.indptr, bounds, times, row_cost=row_cost)
             if nb == bounds:

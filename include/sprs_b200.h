@@ -181,9 +181,6 @@ int sprs_b200_spmv_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, const dou
 int sprs_b200_spmm_rowmaj_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, const double* d_b,
                               uint64_t ldb, uint64_t k, double* d_c, uint64_t ldc,
                               int accumulate, void* stream);
-/* L2 residency of a re-used operand (the x of an iterative SpMV): reserve persisting L2 and
- * attach an access-policy window for [ptr, ptr+bytes) to `stream`; bytes == 0 removes it.     */
-int sprs_b200_l2_persist(sprs_b200_ctx* ctx, const void* ptr, uint64_t bytes, void* stream);
 /* number of kernel launches the library has issued on this ctx (all entry points) */
 uint64_t sprs_b200_launch_count(const sprs_b200_ctx* ctx);
 

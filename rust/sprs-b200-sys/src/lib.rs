@@ -189,8 +189,6 @@ extern "C" {
         comm: *mut sprs_b200_comm, mat: *const sprs_b200_csmat, x: *mut sprs_b200_symm,
         x_slice: *const c_double, col_offset: u64, col_count: u64, y_slice: *mut c_double,
         y_len: u64) -> c_int;
-    pub fn sprs_b200_l2_persist(
-        ctx: *mut sprs_b200_ctx, ptr: *const c_void, bytes: u64, stream: *mut c_void) -> c_int;
     pub fn sprs_b200_diag_gather_ceiling(
         ctx: *mut sprs_b200_ctx, mat: *const sprs_b200_csmat, d_x: *const c_double, iters: c_int,
         ms_per_pass: *mut c_double, nnz_covered: *mut u64) -> c_int;

@@ -55,7 +55,6 @@ PROTOTYPES = {
     "sprs_b200_spmv_dev": (_int, [_vp, _vp, _dp, _dp, _int, _vp]),
     "sprs_b200_spmm_rowmaj_dev": (_int, [_vp, _vp, _dp, _u64, _u64, _dp, _u64, _int, _vp]),
     "sprs_b200_launch_count": (_u64, [_vp]),
-    "sprs_b200_l2_persist": (_int, [_vp, _vp, _u64, _vp]),
     "sprs_b200_peer_alloc": (_int, [_vp, _u64, C.POINTER(_vp), C.c_char_p]),
     "sprs_b200_peer_open": (_int, [_vp, C.c_char_p, C.POINTER(_vp)]),
     "sprs_b200_peer_close": (_int, [_vp, _vp]),
@@ -114,8 +113,7 @@ PROTOTYPES = {
 }
 
 _NOT_EMULATED = ("sprs_b200_comm_", "sprs_b200_symm_", "sprs_b200_partition_rows",
-                 "sprs_b200_spmv_rowpart", "sprs_b200_mul_mat_vec_rowpart", "sprs_b200_diag_",
-                 "sprs_b200_l2_persist")
+                 "sprs_b200_spmv_rowpart", "sprs_b200_mul_mat_vec_rowpart", "sprs_b200_diag_")
 _lib = None
 
 

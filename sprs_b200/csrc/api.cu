@@ -586,42 +586,6 @@ int sprs_b200_csmat_to_other_storage(sprs_b200_ctx* ctx, const sprs_b200_csmat* 
     return SPRS_B200_OK;
 }
 
-// L2 residency of a re-used operand (the x of an iterative SpMV): reserves persisting L2 and
-// attaches an access-policy window for [ptr, ptr + bytes) to `stream` (hits persist, misses
-// stream).  bytes == 0 removes the window.  The kernels' own L2::evict_last hints ask for the
-// same thing per load; the window makes the reservation explicit.
-int sprs_b200_l2_persist(sprs_b200_ctx* ctx, const void* ptr, uint64_t bytes, void* stream) {
-    if (!ctx) return SPRS_B200_ERR_ARGUMENT;
-#ifdef CUEMU  // (tests/emu has no cache to manage)
-    (void)ptr; (void)bytes; (void)stream;
-    return SPRS_B200_OK;
-#else
-    SPRS_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaDeviceProp prop;
-    SPRS_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
-    cudaStreamAttrValue attr;
-    memset(&attr, 0, sizeof(attr));
-    if (bytes) {
-        size_t want = (size_t)bytes;
-        if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
-        SPRS_CUDA(ctx, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
-        size_t win = (size_t)bytes;
-        if (win > (size_t)prop.accessPolicyMaxWindowSize) win = (size_t)prop.accessPolicyMaxWindowSize;
-        attr.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
-        attr.accessPolicyWindow.num_bytes = win;
-        attr.accessPolicyWindow.hitRatio = (float)((double)want / (double)win > 1.0 ? 1.0 : (double)want / (double)win);
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    } else {
-        attr.accessPolicyWindow.num_bytes = 0;
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-    }
-    SPRS_CUDA(ctx, cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-    return SPRS_B200_OK;
-#endif
-}
-
 // ---------------------------------------------------------------------------------
 // device-resident entry points
 int sprs_b200_spmv_dev(sprs_b200_ctx* ctx, const sprs_b200_csmat* mat, const double* d_x,

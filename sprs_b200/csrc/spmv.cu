@@ -98,15 +98,19 @@ __device__ __forceinline__ void sink_row(const RowSink& k, uint64_t r, double su
     }
 }
 
-// Rows [r0, r_last] of one warp tile [k0, k1), G lanes per row (32/G rows at a time): every
-// group walks ITS row's part of the tile with stride G, straight from global memory -- index,
-// value (coalesced inside the group, L1::no_allocate, L2 evict_first) and the x gather (L2
-// evict_last), U of each in flight per lane (template parameter) -- adds its products in storage order, and one
-// G-lane butterfly finishes the row.  Nothing is staged and nothing but the row sum crosses
-// lanes: ~0.5 instructions per non-zero, against ~1.5 for reducing products staged in shared
-// memory or registers (profiles/r2_spmv_notes.md).  G = 1: one lane sums a whole row in
-// storage order, i.e. the reference's bits.  Row boundaries come 31 rows at a time: lane L
-// holds indptr[rbase + L].
+// Rows [r0, r_last] of one warp tile [k0, k1), straight from global memory -- index, value
+// (L1::no_allocate, L2 evict_first) and the x gather (L2 evict_last), U of each in flight per
+// lane; nothing is staged and nothing but a row sum crosses lanes (~1 instruction per non-zero on
+// long rows, against ~1.5 for reducing products staged in shared memory or registers,
+// profiles/r2_spmv_notes.md).  Row boundaries come 31 rows at a time (lane L: indptr[rbase + L]),
+// and every block of 31 rows is taken in three sweeps, because R-MAT blocks mix rows of 0, 5, 50
+// and 5000 non-zeros and any single lanes-per-row choice leaves most lanes idle (ncu on the
+// sparse tail of config 5: 23 of 32 lanes active, 125 Gnnz/s against 280 on the dense head):
+//   1. TINY rows (at most 2U = 8 non-zeros, empty rows included): every lane takes its own row,
+//      all of them in one pass, summed in storage order -- the reference's bits for every such row;
+//   2. the other rows, packed (no slot is spent on a tiny row): G lanes per row, 32/G rows per
+//      pass, each group walking its row with stride G; one G-lane butterfly finishes a row;
+//   3. rows longer than 4 steps of their group: the whole warp, one row at a time.
 template <typename P, int G, int U, bool MULTI>
 __device__ __forceinline__ void rows_direct(const RowSink& k, const P* __restrict__ indptr,
                                             const uint32_t* __restrict__ indices,
@@ -116,27 +120,69 @@ __device__ __forceinline__ void rows_direct(const RowSink& k, const P* __restric
                                             uint64_t pol_stream, uint64_t polx, int lane) {
     constexpr int NG = 32 / G;
     constexpr unsigned FULL = 0xffffffffu;
+    static_assert(G >= 4, "tiny rows have their own sweep: groups start at 4 lanes");
     const int gid = lane / G, gl = lane % G;
     // (offsets are as wide as the indptr: 32 bits unless nnz >= 2^32; row indices are 32-bit)
-    P b = b_first;  // boundaries of the first chunk were prefetched by the caller
+    P b = b_first;  // boundaries of the first block were prefetched by the caller
     for (uint32_t rbase = r0;; rbase += 31) {
         if (rbase != r0) {
             const uint32_t rr = rbase + lane;  // r_last + 1 <= rows < 2^32: no wrap for rr <= r_last + 1
             b = (rr >= rbase && rr <= r_last + 1) ? indptr[rr] : (P)0;
         }
         const int nrows = (r_last - rbase + 1) < 31 ? (int)(r_last - rbase + 1) : 31;
-        for (int j0 = 0; j0 < nrows; j0 += NG) {
-            const int j = j0 + gid;
-            const bool valid = j < nrows;
+        // this lane's own row (lane < nrows), clamped to the tile
+        P ms = b, me = __shfl_down_sync(FULL, b, 1);
+        ms = ms > k0 ? ms : k0;
+        me = me < k1 ? me : k1;
+        if (lane >= nrows || me < ms) me = ms;
+        const bool tiny = lane < nrows && (me - ms) <= (P)(2 * U);
+        // ---- sweep 1: tiny rows, one lane each, storage order
+        if (__any_sync(FULL, tiny && me > ms)) {
+            double acc = 0.0;
+#pragma unroll
+            for (int st = 0; st < 2; ++st) {
+                const P q = ms + (P)(st * U);
+                uint32_t c[U];
+                double v[U], xv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    c[u] = (tiny && q + (P)u < me) ? ldg_stream_u32(indices + q + (P)u, pol_stream) : 0u;
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    v[u] = (tiny && q + (P)u < me) ? ldg_stream_f64(data + q + (P)u, pol_stream) : 0.0;
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    xv[u] = (tiny && q + (P)u < me) ? ldg_f64_hint(x + c[u], polx) : 0.0;
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (tiny && q + (P)u < me) acc = __dadd_rn(acc, __dmul_rn(v[u], xv[u]));
+                if (!__any_sync(FULL, tiny && q + (P)U < me)) break;
+            }
+            if (tiny) sink_row<MULTI>(k, (uint64_t)rbase + lane, acc);
+        } else if (tiny) {
+            sink_row<MULTI>(k, (uint64_t)rbase + lane, 0.0);  // empty rows: y = 0 (or y += 0)
+        }
+        // ---- sweeps 2 and 3: the other rows, NG at a time
+        unsigned todo = __ballot_sync(FULL, lane < nrows && !tiny);
+        while (todo) {
+            int j = -1;  // row (within the block) of this lane's group
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                if (todo) {
+                    const int jj = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    if (gid == g) j = jj;
+                }
+            }
+            const bool valid = j >= 0;
             const int js = valid ? j : 0;
             P s = __shfl_sync(FULL, b, js);
             P e = __shfl_sync(FULL, b, js + 1);
             s = s > k0 ? s : k0;
             e = e < k1 ? e : k1;
             if (!valid || e < s) e = s;
-            // a row much longer than its group would serialise the warp behind G lanes: such
-            // rows (a hub row inside a tile of short rows) are taken by the whole warp below
-            const bool is_long = (G < 32) && (e - s) > (P)(16 * G * U);
+            // a row much longer than its group would hold the warp behind G lanes
+            const bool is_long = (G < 32) && (e - s) > (P)(4 * G * U);
             double acc = 0.0;
             for (P q = s + gl; q < (is_long ? s : e); q += (P)(G * U)) {
                 uint32_t c[U];
@@ -156,6 +202,7 @@ __device__ __forceinline__ void rows_direct(const RowSink& k, const P* __restric
             }
 #pragma unroll
             for (int o = G / 2; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(FULL, acc, o));
+            if (gl == 0 && valid && !is_long) sink_row<MULTI>(k, (uint64_t)rbase + j, acc);
             if (G < 32) {
                 unsigned pending = __ballot_sync(FULL, gl == 0 && is_long);
                 while (pending) {
@@ -185,7 +232,6 @@ __device__ __forceinline__ void rows_direct(const RowSink& k, const P* __restric
                     if (lane == 0) sink_row<MULTI>(k, (uint64_t)rbase + jj, a2);
                 }
             }
-            if (gl == 0 && valid && !is_long) sink_row<MULTI>(k, (uint64_t)rbase + j, acc);
         }
         if (r_last - rbase < 31) break;  // (also ends the loop when rbase + 31 would wrap)
     }
@@ -231,11 +277,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
 #define SPMV_ROWS(G)                                                                            \
     rows_direct<P, G, U, MULTI>(sink, indptr, indices, data, x, k0, k1, r0, r_last, b_first,       \
                              pol_stream, polx, lane)
-        if (cnt <= 6 * nr)
-            SPMV_ROWS(1);
-        else if (cnt <= 12 * nr)
-            SPMV_ROWS(2);
-        else if (cnt <= 24 * nr)
+        if (cnt <= 24 * nr)
             SPMV_ROWS(4);
         else if (cnt <= 48 * nr)
             SPMV_ROWS(8);

@@ -56,16 +56,16 @@ def _check(sp, csr, rows, cols, accumulate):
         assert np.array_equal(y, want)
 
 
-@pytest.mark.skipif(not IN_CHILD, reason="runs in the child process with SPRS_B200_E2E_CHUNKS set")
+# (the cases below exist only in the child process, the driver test only in the parent: nothing
+# is ever skipped)
 @pytest.mark.parametrize("accumulate", [False, True])
-def test_chunked_host_path_matches_device_spmv(sp, accumulate):
+def _chunked_host_path_matches_device_spmv(sp, accumulate):
     rng = np.random.default_rng(31)
     rows, cols = 6000, 5000
     _check(sp, rand_csr(rng, rows, cols, 30, empty_frac=0.15), rows, cols, accumulate)
 
 
-@pytest.mark.skipif(not IN_CHILD, reason="runs in the child process with SPRS_B200_E2E_CHUNKS set")
-def test_chunked_host_path_hub_rows_across_chunks(sp):
+def _chunked_host_path_hub_rows_across_chunks(sp):
     """Rows much longer than a chunk: their carries cross chunk boundaries; trailing and
     leading empty rows belong to the first / last chunk."""
     rng = np.random.default_rng(32)
@@ -84,9 +84,8 @@ def test_chunked_host_path_hub_rows_across_chunks(sp):
     _check(sp, (ip2.astype(np.uint32), idx2.astype(np.uint32), dat2), rows, cols, True)
 
 
-@pytest.mark.skipif(IN_CHILD, reason="parent side")
 @pytest.mark.parametrize("chunks", ["5", "8", "1"])
-def test_e2e_chunked_child_process(chunks):
+def _e2e_chunked_child_process(chunks):
     env = dict(os.environ, SPRS_B200_E2E_MIN_TILES="1", SPRS_B200_E2E_CHUNKS=chunks)
     r = subprocess.run(
         [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
@@ -97,3 +96,10 @@ def test_e2e_chunked_child_process(chunks):
     tail = "\n".join(r.stdout.splitlines()[-15:])
     assert r.returncode == 0, tail + r.stderr[-1500:]
     assert " passed" in tail
+
+
+if IN_CHILD:
+    test_chunked_host_path_matches_device_spmv = _chunked_host_path_matches_device_spmv
+    test_chunked_host_path_hub_rows_across_chunks = _chunked_host_path_hub_rows_across_chunks
+else:
+    test_e2e_chunked_child_process = _e2e_chunked_child_process

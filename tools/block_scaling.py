@@ -1,5 +1,7 @@
-"""Fixed cost of one SpMV call: time row blocks of 1/8 .. 1 of the config-5 matrix (full x) on one
-GPU, with and without a persisting-L2 window for x, and fit t = a + b * nnz."""
+"""Row blocks of 1/8 .. 1 of the config-5 matrix (full x) on one GPU: how the SpMV rate depends
+on the block (rows per non-zero differ 3x between the head and the tail of an R-MAT matrix).
+(Round 2 also tried a persisting-L2 access-policy window for x here: 12 % SLOWER on every block,
+profiles/r2_block_scaling.txt; the kernels' L2::evict_last hints already keep x resident.)"""
 import ctypes as C
 import json
 import os
@@ -27,7 +29,6 @@ def time_block(r0, r1, persist, stream_ptr, reps=30):
     a = full if (r0, r1) == (0, n) else full.slice_rows(r0, r1)
     y = torch.empty(max(r1 - r0, 1), device="cuda", dtype=torch.float64)
     torch.cuda.synchronize()
-    ctx.check(ctx.lib.sprs_b200_l2_persist(ctx.h, C.c_void_p(x.data_ptr()), 8 * n if persist else 0, stream_ptr))
     with torch.cuda.stream(s_own):
         for _ in range(5):
             ctx.check(ctx.lib.sprs_b200_spmv_dev(ctx.h, a.mirror.h, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), 0, stream_ptr))
@@ -40,7 +41,7 @@ def time_block(r0, r1, persist, stream_ptr, reps=30):
     return a.nnz, e0.elapsed_time(e1) / reps
 
 
-for persist in (False, True):
+for persist in (False,):
     pts = []
     for lo, hi in ((0, 1), (3, 4), (6, 7), (2, 4), (4, 8), (0, 8)):
         nnz, ms = time_block(b[lo], b[hi], persist, sptr)
@@ -52,4 +53,3 @@ for persist in (False, True):
     (a0, b0), *_ = np.linalg.lstsq(A, t, rcond=None)
     print(json.dumps({"persist_x_in_l2": persist, "fit_fixed_ms": round(float(a0), 4),
                       "fit_gnnz_s": round(1.0 / b0 / 1e6, 1)}), flush=True)
-ctx.check(ctx.lib.sprs_b200_l2_persist(ctx.h, None, 0, sptr))
