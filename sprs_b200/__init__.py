@@ -12,4 +12,25 @@ from .sparse import (CSC, CSR, Context, CsMat, CsVec, DeviceCsMat, SprsPanic, Th
 __all__ = ["CSC", "CSR", "Context", "CsMat", "CsVec", "DeviceCsMat", "SprsPanic",
            "ThirdPartyError", "csmat_mul_csmat", "prod", "smmp", "_lib", "io", "linalg"]
 __version__ = "0.1.0"
-SPMV_TILE = 1024  # nnz per SpMV warp tile (default variant in csrc/spmv.cu); tests use it to find rows cut by a tile
+SPMV_TILE = 1024     # cost units per SpMV warp tile (default variant in csrc/spmv.cu)
+SPMV_ROW_COST = 16   # cost of one row end, in non-zeros (csrc/spmv.cu SPMV_ROW_COST)
+
+
+def spmv_rows_cut_by_tiles(indptr):
+    """Boolean mask of the rows a merge-path tile boundary of the SpMV cuts (csrc/spmv.cu
+    tile_cut_kernel restated in numpy): the cut of tile t is where nnz + SPMV_ROW_COST * rows
+    reaches t * SPMV_TILE.  Tests use it: a cut row adds two partial sums, so only the rows it
+    spares carry the storage-order (bit-exact) promise for rows of at most 8 non-zeros."""
+    import numpy as np
+    ip = np.asarray(indptr).astype(np.int64)
+    ip = ip - ip[0]
+    rows = len(ip) - 1
+    f = ip + SPMV_ROW_COST * np.arange(rows + 1)
+    total = int(f[-1])
+    d = np.arange(0, total, SPMV_TILE, dtype=np.int64)[1:]       # cuts 1 .. n_tiles-1
+    r = np.searchsorted(f, d, side="right") - 1                     # largest r with f[r] <= d
+    k = np.minimum(d - SPMV_ROW_COST * r, ip[np.minimum(r + 1, rows)])
+    inside = (k > ip[r]) & (k < ip[np.minimum(r + 1, rows)])        # strictly inside row r
+    cut = np.zeros(rows, dtype=bool)
+    cut[r[inside & (r < rows)]] = True
+    return cut

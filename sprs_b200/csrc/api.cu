@@ -418,6 +418,7 @@ int sprs_b200_csmat_free(sprs_b200_csmat* m) {
         if (m->d_data) cudaFree(m->d_data);
     }
     if (m->d_tile_row) cudaFree(m->d_tile_row);
+    if (m->d_tile_k) cudaFree(m->d_tile_k);
     if (m->d_carry) cudaFree(m->d_carry);
     if (m->csr_cache) sprs_b200_csmat_free(m->csr_cache);
     delete m;

@@ -51,9 +51,10 @@ struct sprs_b200_csmat {
     double* d_data = nullptr;      // nnz entries
     bool owns = true;              // false for from_device adoption
     bool pooled = false;           // arrays came from cudaMallocAsync (SpGEMM results)
-    // SpMV partition (built lazily, see spmv.cu): tile_row[t] = first outer index whose
-    // end lies beyond nnz position t*TILE; n_tiles+1 entries.  carry: n_tiles doubles.
+    // SpMV partition (spmv.cu): merge-path cuts (tile_row[t], tile_k[t]) = rows passed / nnz
+    // consumed at cost t*W; n_tiles+1 entries each.  carry: n_tiles doubles.
     uint32_t* d_tile_row = nullptr;
+    void* d_tile_k = nullptr;      // nnz position of every cut (as wide as the indptr)
     double* d_carry = nullptr;
     uint64_t n_tiles = 0;
     // CSC mirrors only: the CSR conversion the product kernels run on, built on first use

@@ -45,30 +45,42 @@
 
 namespace {
 
-// ---- partition: tile_row[t] = first row whose end lies beyond nnz position t*wt
+// ---- partition: merge-path cuts.  A tile is W units of COST along the path that consumes the
+// non-zeros and the row ends of the CSR stream, a row end counting ROW_COST non-zeros: the cut of
+// tile t is the point (tile_row[t], tile_k[t]) with  k + ROW_COST * r = t * W,  r = the rows
+// whose end has been passed, indptr[r] <= k <= indptr[r+1].  Equal-nnz tiles are not enough on an
+// R-MAT matrix: its sparse tail has stretches of thousands of (nearly) empty rows, a 1024-nnz
+// tile there held ~1700 rows -- 55 dependent boundary fetches for one warp while the others
+// waited (ncu on that region: 125 Gnnz/s against 280 on the dense head, half the warps idle).
+// With the row cost in the cut a tile has at most W / ROW_COST row ends.
+constexpr uint32_t SPMV_ROW_COST = 16;
+
 template <typename P>
-__global__ void tile_row_kernel(const P* __restrict__ indptr, uint32_t rows, uint64_t n_tiles,
-                                uint32_t wt, uint32_t* __restrict__ tile_row) {
+__global__ void tile_cut_kernel(const P* __restrict__ indptr, uint32_t rows, uint64_t nnz,
+                                uint64_t n_tiles, uint32_t w, uint32_t* __restrict__ tile_row,
+                                P* __restrict__ tile_k) {
     const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (t > n_tiles) return;
-    if (t == 0) {
-        tile_row[0] = 0;  // leading empty rows belong to tile 0
+    if (t == n_tiles) {  // the end of the path
+        tile_row[t] = rows;
+        tile_k[t] = (P)nnz;
         return;
     }
-    if (t == n_tiles) {
-        tile_row[t] = rows;  // trailing empty rows belong to the last tile
-        return;
-    }
-    const uint64_t k0 = t * (uint64_t)wt;
-    uint32_t lo = 0, hi = rows;  // first r with indptr[r+1] > k0
+    const uint64_t d = t * (uint64_t)w;
+    uint32_t lo = 0, hi = rows;  // largest r in [0, rows] with indptr[r] + ROW_COST * r <= d
     while (lo < hi) {
-        const uint32_t mid = lo + (hi - lo) / 2;
-        if ((uint64_t)indptr[(size_t)mid + 1] > k0)
-            hi = mid;
+        const uint32_t mid = lo + (hi - lo + 1) / 2;
+        if ((uint64_t)indptr[mid] + (uint64_t)SPMV_ROW_COST * mid <= d)
+            lo = mid;
         else
-            lo = mid + 1;
+            hi = mid - 1;
     }
+    uint64_t k = d - (uint64_t)SPMV_ROW_COST * lo;
+    // the cut may fall inside the "row end" step of row lo: all its non-zeros are then consumed
+    const uint64_t row_end = lo < rows ? (uint64_t)indptr[(size_t)lo + 1] : nnz;
+    if (k > row_end) k = row_end;
     tile_row[t] = lo;
+    tile_k[t] = (P)k;
 }
 
 // What the row emitters need.
@@ -241,7 +253,8 @@ template <typename P, int WT, int NWARPS, int MINB, int U, bool MULTI>
 __global__ void __launch_bounds__(NWARPS * 32, MINB)
     spmv_rows_kernel(const P* __restrict__ indptr, const uint32_t* __restrict__ indices,
                      const double* __restrict__ data, const uint32_t* __restrict__ tile_row,
-                     const double* __restrict__ x, const __grid_constant__ SpmvTargets yt,
+                     const P* __restrict__ tile_k, const double* __restrict__ x,
+                     const __grid_constant__ SpmvTargets yt,
                      double* __restrict__ carry, uint64_t nnz, uint32_t rows, uint32_t t_begin,
                      uint32_t t_end /* this launch covers tiles [t_begin, t_end) */, int accumulate,
                      uint64_t pol_stream /* L2 evict_first */, uint64_t polx /* L2 evict_last */) {
@@ -258,18 +271,20 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
     if (t >= t_end) return;
     // row range and the first 32 row boundaries of a tile are fetched ONE TILE AHEAD
     uint32_t r0 = tile_row[t], r1 = tile_row[t + 1];
+    P k0 = tile_k[t], k1 = tile_k[t + 1];
     // lane L: indptr[r0 + L] while r0 + L <= r_last + 1 (r_last + 1 <= rows: always in range)
     P b_first = (uint64_t)r0 + lane <= (r1 < rows ? (uint64_t)r1 + 1 : (uint64_t)r1)
                     ? indptr[(size_t)r0 + lane] : (P)0;
     for (;;) {
         const uint32_t tn = t + GW;
         uint32_t r0n = 0, r1n = 0;
+        P k0n = 0, k1n = 0;
         if (tn < t_end) {
             r0n = tile_row[tn];
             r1n = tile_row[tn + 1];
+            k0n = tile_k[tn];
+            k1n = tile_k[tn + 1];
         }
-        const uint64_t k0w = (uint64_t)t * WT;
-        const P k0 = (P)k0w, k1 = (P)(k0w + WT < nnz ? k0w + WT : nnz);
         sink.carry_slot = carry + t;
         sink.r1 = r1;
         const uint32_t r_last = r1 < rows ? r1 : r1 - 1;
@@ -292,6 +307,8 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
         t = tn;
         r0 = r0n;
         r1 = r1n;
+        k0 = k0n;
+        k1 = k1n;
         b_first = b_next;
     }
 }
@@ -415,7 +432,8 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
     const uint64_t need = (t1 - t0 + SPMV_NWARPS - 1) / SPMV_NWARPS;
     if (grid > need) grid = need;
     kern<<<(unsigned)grid, SPMV_NWARPS * 32, 0, s>>>((const P*)m->d_indptr, m->d_indices,
-                                                     m->d_data, m->d_tile_row, d_x, yt, m->d_carry,
+                                                     m->d_data, m->d_tile_row, (const P*)m->d_tile_k, d_x, yt,
+                                                     m->d_carry,
                                                      m->nnz, (uint32_t)m->rows, (uint32_t)t0,
                                                      (uint32_t)t1, accumulate, ctx->pol_evict_first,
                                                      ctx->pol_evict_last);
@@ -450,20 +468,22 @@ int spmv_tile_nnz() { return spmv_variant().wt; }
 
 int spmv_prepare(sprs_b200_ctx* ctx, sprs_b200_csmat* m, cudaStream_t s) {
     if (m->storage != SPRS_B200_CSR) return SPRS_B200_OK;  // CSC mirrors are converted first
-    const uint32_t wt = (uint32_t)spmv_tile_nnz();
-    m->n_tiles = m->nnz == 0 ? 1 : (m->nnz + wt - 1) / wt;
+    const uint32_t w = (uint32_t)spmv_tile_nnz();  // cost units per tile
+    const uint64_t total = m->nnz + (uint64_t)SPMV_ROW_COST * m->rows;
+    m->n_tiles = total == 0 ? 1 : (total + w - 1) / w;
     SPRS_CUDA(ctx, cudaMalloc((void**)&m->d_tile_row, (m->n_tiles + 1) * sizeof(uint32_t)));
+    SPRS_CUDA(ctx, cudaMalloc((void**)&m->d_tile_k, (m->n_tiles + 1) * (size_t)m->indptr_bytes));
     SPRS_CUDA(ctx, cudaMalloc((void**)&m->d_carry, m->n_tiles * sizeof(double)));
     const uint64_t n = m->n_tiles + 1;
     const unsigned grid = (unsigned)((n + 255) / 256);
     if (m->indptr_bytes == 4)
-        tile_row_kernel<uint32_t><<<grid, 256, 0, s>>>((const uint32_t*)m->d_indptr,
-                                                       (uint32_t)m->rows, m->n_tiles, wt,
-                                                       m->d_tile_row);
+        tile_cut_kernel<uint32_t><<<grid, 256, 0, s>>>((const uint32_t*)m->d_indptr, (uint32_t)m->rows,
+                                                       m->nnz, m->n_tiles, w, m->d_tile_row,
+                                                       (uint32_t*)m->d_tile_k);
     else
-        tile_row_kernel<uint64_t><<<grid, 256, 0, s>>>((const uint64_t*)m->d_indptr,
-                                                       (uint32_t)m->rows, m->n_tiles, wt,
-                                                       m->d_tile_row);
+        tile_cut_kernel<uint64_t><<<grid, 256, 0, s>>>((const uint64_t*)m->d_indptr, (uint32_t)m->rows,
+                                                       m->nnz, m->n_tiles, w, m->d_tile_row,
+                                                       (uint64_t*)m->d_tile_k);
     ctx->launches += 1;
     SPRS_CUDA(ctx, cudaGetLastError());
     return SPRS_B200_OK;

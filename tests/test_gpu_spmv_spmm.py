@@ -197,7 +197,7 @@ def test_spmv_vs_oracle(sp, O, case):
 def test_spmv_short_rows_bit_exact(sp, O):
     """Every row of at most 8 non-zeros is summed by ONE lane in storage order with unfused
     mul/add -> identical bits to the reference's sequential sum (mul_acc.rs:28-30), provided the
-    row lies inside one SPMV_TILE-nnz tile; rows cut by a tile boundary add their two partial
+    row is not cut by a (merge-path) tile boundary; rows cut by one add their two partial
     sums, longer rows use lane groups: both are held to the tolerance gate instead."""
     rng = np.random.default_rng(11)
     ip, ind, d = rand_csr(rng, 20000, 5000, 3, empty_frac=0.2)
@@ -207,7 +207,7 @@ def test_spmv_short_rows_bit_exact(sp, O):
     O.mul_acc_mat_vec_csr(ip, ind, d, x, ref)
     got = a * x
     s, e = ip[:-1].astype(np.int64), ip[1:].astype(np.int64)
-    inside = ((e == s) | (s // sp.SPMV_TILE == (np.maximum(e, 1) - 1) // sp.SPMV_TILE)) & (e - s <= 8)
+    inside = ~sp.spmv_rows_cut_by_tiles(ip) & (e - s <= 8)
     assert inside.sum() > 19500
     assert np.array_equal(got[inside], ref[inside])
     bound = np.zeros(20000)
