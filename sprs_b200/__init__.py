@@ -12,8 +12,11 @@ from .sparse import (CSC, CSR, Context, CsMat, CsVec, DeviceCsMat, SprsPanic, Th
 __all__ = ["CSC", "CSR", "Context", "CsMat", "CsVec", "DeviceCsMat", "SprsPanic",
            "ThirdPartyError", "csmat_mul_csmat", "prod", "smmp", "_lib", "io", "linalg"]
 __version__ = "0.1.0"
-SPMV_TILE = 1024     # cost units per SpMV warp tile (default variant in csrc/spmv.cu)
-SPMV_ROW_COST = 16   # cost of one row end, in non-zeros (csrc/spmv.cu SPMV_ROW_COST)
+import os as _os
+
+_v = (_os.environ.get("SPRS_B200_SPMV_VARIANT", "") + ",,,").split(",")
+SPMV_TILE = int(_v[0]) if _v[0] else 1024      # cost units per SpMV warp tile (csrc/spmv.cu)
+SPMV_ROW_COST = int(_v[3]) if _v[3] else 16    # cost of one row end, in non-zeros
 
 
 def spmv_rows_cut_by_tiles(indptr):

@@ -4,39 +4,35 @@
 // one-column case of prod::csr_mulacc_dense_colmaj (prod.rs:274-298), which is what
 // `&A * &x` runs (sprs/src/sparse/csmat.rs:2142-2148).
 //
-// Design (evidence in profiles/r2_spmv_notes.md).  The kernel is bound by the
-// L1TEX pipe that serves the x gathers (one 128-byte line per clock per SM) and by the L1 lines
-// those gathers hold while their sectors are in flight, not by HBM: the "ceiling" kernels of
-// tools/spmv_lab.cu (same streams and gathers, no row logic) top out at 0.55-0.57 of the HBM
-// roofline on the 10M R-MAT and 0.45 on uniform columns.  So the kernel is organised to keep
-// gathers in flight ALL the time and to spend as few other L1TEX/MIO operations as possible:
-//   * the nnz stream is cut into tiles of WT = 32*EPL non-zeros (not rows); a tile belongs to
-//     ONE WARP, warps are persistent and autonomous (no CTA-wide barrier anywhere);
-//   * no shared-memory staging: indices and values stream through registers with coalesced
-//     ld.global.nc.L1::no_allocate (L2 evict_first: the matrix is read exactly once), which
-//     leaves the whole L1 to the gathers (a max-shared carve-out costs 3x, lab carve sweep);
-//   * software pipeline, one tile deep: the gathers and value loads of tile t+1 (indices
-//     prefetched during tile t-1) are issued BEFORE tile t is reduced, so the reduction of a
-//     tile -- the part that used to serialise behind the gathers -- runs under the next
-//     tile's memory latency; row ranges (tile_row) are fetched two tiles ahead, the row
-//     boundaries (indptr) one tile ahead;
-//   * register reduction for tiles touching <= 24 rows: lane L holds elements L + 32*i, i.e.
-//     32 consecutive non-zeros per register "slab"; slabs are walked in order, a slab without
-//     a row end costs one add, a row end inside a slab splits the lanes (warp-uniform control
-//     flow), finished per-lane row partials are parked in 4 slots and reduced four rows at a
-//     time by one multi-value butterfly (12 shuffles for 4 rows).  Products never touch shared
-//     memory; y is written once;
-//   * tiles with more rows (short rows, runs of empty rows) store their products to a small
-//     per-warp shared buffer and reduce rows with lane groups of G = 1..32 lanes; rows of tiles
-//     with mean length <= 6 are summed by one lane in storage order, i.e. bit-identical to the
-//     reference's sequential sum; longer rows use trees and agree to rounding (parity gate:
-//     |d| <= 1e-6 * sum|terms|);
-//   * the row cut by the tile end leaves its partial in carry[t]; a second tiny kernel adds the
+// Design (evidence in profiles/r2_spmv_notes.md).  The kernel is bound by the x
+// gathers -- the L1TEX pipe, the L1 lines in-flight gathers hold, and the 42 GB they pull through
+// L2 for 12 GB of matrix -- not by HBM: "ceiling" kernels (the same streams and gathers with the
+// row logic removed; tools/spmv_lab.cu, csrc/diag.cu) plateau at 0.55-0.57 of the HBM roofline on
+// the 10M R-MAT and 0.45 on uniform columns whatever the staging.  So:
+//   * MERGE-PATH TILES: the CSR stream is cut where  nnz + 16 * (row ends)  reaches multiples of
+//     1024 (tile_cut_kernel): a tile is ~900 non-zeros of long rows or at most 64 row ends of
+//     empty ones, never a thousand rows for one warp.  A tile belongs to ONE WARP; warps are
+//     persistent and autonomous (no CTA-wide barrier, no shared memory: the whole unified array
+//     is L1 for the gathers -- a max-shared carve-out costs 3x);
+//   * ROWS STRAIGHT FROM GLOBAL MEMORY, lanes matched to the rows (rows_direct): per block of 31
+//     rows, tiny rows (<= 8 non-zeros) one lane each in storage order -- the reference's bits
+//     --, the others packed G = 4..32 lanes per row with 4 index / value / gather loads in
+//     flight per lane and one G-lane butterfly per row, very long rows by the whole warp.
+//     Nothing is staged, nothing but a row sum crosses lanes;
+//   * loads: ld.global.nc.L1::no_allocate + L2 evict_first for the matrix (read exactly once),
+//     ld.global.nc + L2 evict_last for x; 40 warps per SM hide the latency;
+//   * the row cut by a tile end leaves its partial in carry[t]; a second tiny kernel adds the
 //     carries in tile order (deterministic, no atomics).
-// Arithmetic is MulAcc::mul_acc's (mul_acc.rs:28-30): unfused multiply, then add.
+// Rows longer than 8 non-zeros use trees and agree with the reference to rounding (parity gate:
+// |d| <= 1e-6 * sum|terms|).  Arithmetic is MulAcc::mul_acc's (mul_acc.rs:28-30):
+// unfused multiply, then add.
+// What round 2 measured and dropped on the way here (all parity-green): the round-1 TMA ring with
+// register / shared-memory reductions (0.443), two software-pipelined register-stream kernels
+// with in-register segmented reductions (4.85 and 6.31 ms), index prefetch across steps, 6-8
+// loads per lane, equal-nnz tiles (the sparse tail of the matrix ran at 125 Gnnz/s).
 //
 // Algorithmic bytes per nnz: 12 (8 data + 4 index) + 8 per row (y) -- the BASELINE roofline
-// 12*nnz + 8*n; indptr (4 B/row), tile_row/carry (12 B per tile) and x gathers are overhead.
+// 12*nnz + 8*n; indptr (4 B/row), the tile cuts (16 B per tile) and x gathers are overhead.
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -53,12 +49,12 @@ namespace {
 // tile there held ~1700 rows -- 55 dependent boundary fetches for one warp while the others
 // waited (ncu on that region: 125 Gnnz/s against 280 on the dense head, half the warps idle).
 // With the row cost in the cut a tile has at most W / ROW_COST row ends.
-constexpr uint32_t SPMV_ROW_COST = 16;
+constexpr uint32_t SPMV_ROW_COST = 16;  // default; 4th field of SPRS_B200_SPMV_VARIANT for tuning runs
 
 template <typename P>
 __global__ void tile_cut_kernel(const P* __restrict__ indptr, uint32_t rows, uint64_t nnz,
-                                uint64_t n_tiles, uint32_t w, uint32_t* __restrict__ tile_row,
-                                P* __restrict__ tile_k) {
+                                uint64_t n_tiles, uint32_t w, uint32_t row_cost,
+                                uint32_t* __restrict__ tile_row, P* __restrict__ tile_k) {
     const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (t > n_tiles) return;
     if (t == n_tiles) {  // the end of the path
@@ -70,12 +66,12 @@ __global__ void tile_cut_kernel(const P* __restrict__ indptr, uint32_t rows, uin
     uint32_t lo = 0, hi = rows;  // largest r in [0, rows] with indptr[r] + ROW_COST * r <= d
     while (lo < hi) {
         const uint32_t mid = lo + (hi - lo + 1) / 2;
-        if ((uint64_t)indptr[mid] + (uint64_t)SPMV_ROW_COST * mid <= d)
+        if ((uint64_t)indptr[mid] + (uint64_t)row_cost * mid <= d)
             lo = mid;
         else
             hi = mid - 1;
     }
-    uint64_t k = d - (uint64_t)SPMV_ROW_COST * lo;
+    uint64_t k = d - (uint64_t)row_cost * lo;
     // the cut may fall inside the "row end" step of row lo: all its non-zeros are then consumed
     const uint64_t row_end = lo < rows ? (uint64_t)indptr[(size_t)lo + 1] : nnz;
     if (k > row_end) k = row_end;
@@ -249,7 +245,7 @@ __device__ __forceinline__ void rows_direct(const RowSink& k, const P* __restric
     }
 }
 
-template <typename P, int WT, int NWARPS, int MINB, int U, bool MULTI>
+template <typename P, int NWARPS, int MINB, int U, bool MULTI>
 __global__ void __launch_bounds__(NWARPS * 32, MINB)
     spmv_rows_kernel(const P* __restrict__ indptr, const uint32_t* __restrict__ indices,
                      const double* __restrict__ data, const uint32_t* __restrict__ tile_row,
@@ -386,7 +382,7 @@ __global__ void spmv_fixup_range_kernel(const uint32_t* __restrict__ tile_row, c
 
 // ---- launch configuration ---------------------------------------------------------
 struct SpmvVariant {
-    int wt, ctas_per_sm, u;
+    int wt, ctas_per_sm, u, row_cost;
 };
 // default picked from the round-2 sweeps (profiles/r2_spmv_notes.md);
 // SPRS_B200_SPMV_VARIANT="wt,ctas,u" (tile nnz, CTAs of 8 warps per SM, loads in flight per lane
@@ -394,10 +390,11 @@ struct SpmvVariant {
 // every mirror's tile_row).
 SpmvVariant spmv_variant() {
     static SpmvVariant v = [] {
-        SpmvVariant d{1024, 5, 4};
+        SpmvVariant d{1024, 5, 4, (int)SPMV_ROW_COST};
         if (const char* e = getenv("SPRS_B200_SPMV_VARIANT")) {
-            int a, b, c;
-            if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3) d = SpmvVariant{a, b, c};
+            int a, b, c, rc = (int)SPMV_ROW_COST;
+            const int got = sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &rc);
+            if (got >= 3 && rc >= 0) d = SpmvVariant{a, b, c, rc};
         }
         return d;
     }();
@@ -406,7 +403,7 @@ SpmvVariant spmv_variant() {
 
 constexpr int SPMV_NWARPS = 8;
 
-template <typename P, int WT, int CTAS, int U>
+template <typename P, int CTAS, int U>
 int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
                    const SpmvTargets& yt, int accumulate, uint64_t t0, uint64_t t1,
                    cudaStream_t s) {
@@ -415,8 +412,8 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
     // CTAS resident CTAs per SM is also the kernel's __launch_bounds__ minBlocks: it sets the
     // register budget (the kernel hides latency with warps, not with registers).
     const bool multi = yt.n > 1;
-    auto kern = multi ? spmv_rows_kernel<P, WT, SPMV_NWARPS, CTAS, U, true>
-                      : spmv_rows_kernel<P, WT, SPMV_NWARPS, CTAS, U, false>;
+    auto kern = multi ? spmv_rows_kernel<P, SPMV_NWARPS, CTAS, U, true>
+                      : spmv_rows_kernel<P, SPMV_NWARPS, CTAS, U, false>;
     static bool configured_flags[64][2] = {};  // function attributes are per device
     bool& configured = configured_flags[ctx->device & 63][multi ? 1 : 0];
     if (!configured) {
@@ -445,12 +442,12 @@ int launch_dispatch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* 
                     const SpmvTargets& yt, int accumulate, uint64_t t0, uint64_t t1,
                     cudaStream_t s) {
     const SpmvVariant v = spmv_variant();
-#define SPMV_CASE(W, CT, UU)                                                      \
-    if (v.wt == W && v.ctas_per_sm == CT && v.u == UU)                            \
-        return launch_variant<P, W, CT, UU>(ctx, m, d_x, yt, accumulate, t0, t1, s);
-    SPMV_CASE(1024, 5, 4)
-    SPMV_CASE(1024, 4, 6)
-    SPMV_CASE(1024, 4, 8)
+#define SPMV_CASE(CT, UU)                                                          \
+    if (v.ctas_per_sm == CT && v.u == UU) /* the tile size only enters the cuts */  \
+        return launch_variant<P, CT, UU>(ctx, m, d_x, yt, accumulate, t0, t1, s);
+    SPMV_CASE(5, 4)
+    SPMV_CASE(4, 6)
+    SPMV_CASE(4, 8)
 #undef SPMV_CASE
     SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "unknown SPRS_B200_SPMV_VARIANT (wt,ctas,u)");
 }
@@ -469,7 +466,8 @@ int spmv_tile_nnz() { return spmv_variant().wt; }
 int spmv_prepare(sprs_b200_ctx* ctx, sprs_b200_csmat* m, cudaStream_t s) {
     if (m->storage != SPRS_B200_CSR) return SPRS_B200_OK;  // CSC mirrors are converted first
     const uint32_t w = (uint32_t)spmv_tile_nnz();  // cost units per tile
-    const uint64_t total = m->nnz + (uint64_t)SPMV_ROW_COST * m->rows;
+    const uint32_t row_cost = (uint32_t)spmv_variant().row_cost;
+    const uint64_t total = m->nnz + (uint64_t)row_cost * m->rows;
     m->n_tiles = total == 0 ? 1 : (total + w - 1) / w;
     SPRS_CUDA(ctx, cudaMalloc((void**)&m->d_tile_row, (m->n_tiles + 1) * sizeof(uint32_t)));
     SPRS_CUDA(ctx, cudaMalloc((void**)&m->d_tile_k, (m->n_tiles + 1) * (size_t)m->indptr_bytes));
@@ -478,11 +476,11 @@ int spmv_prepare(sprs_b200_ctx* ctx, sprs_b200_csmat* m, cudaStream_t s) {
     const unsigned grid = (unsigned)((n + 255) / 256);
     if (m->indptr_bytes == 4)
         tile_cut_kernel<uint32_t><<<grid, 256, 0, s>>>((const uint32_t*)m->d_indptr, (uint32_t)m->rows,
-                                                       m->nnz, m->n_tiles, w, m->d_tile_row,
+                                                       m->nnz, m->n_tiles, w, row_cost, m->d_tile_row,
                                                        (uint32_t*)m->d_tile_k);
     else
         tile_cut_kernel<uint64_t><<<grid, 256, 0, s>>>((const uint64_t*)m->d_indptr, (uint32_t)m->rows,
-                                                       m->nnz, m->n_tiles, w, m->d_tile_row,
+                                                       m->nnz, m->n_tiles, w, row_cost, m->d_tile_row,
                                                        (uint64_t*)m->d_tile_k);
     ctx->launches += 1;
     SPRS_CUDA(ctx, cudaGetLastError());

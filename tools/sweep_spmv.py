@@ -33,7 +33,7 @@ def main():
     workloads = [("rand_1m_32", "rand", 1_000_000, 32), ("rmat_10m_100", "rmat", 10_000_000, 100)]
     if len(sys.argv) > 1 and sys.argv[1] == "small":
         workloads = [("rand_1m_32", "rand", 1_000_000, 32), ("rmat_1m_100", "rmat", 1_000_000, 100)]
-    variants = ["1024,5,4", "1024,4,6", "1024,4,8"]  # tile nnz, CTAs/SM (csrc/spmv.cu launch_dispatch)
+    variants = ["1024,5,4,16", "2048,5,4,16", "1024,5,4,8", "1024,5,4,32", "2048,5,4,32", "512,5,4,16"]  # tile nnz, CTAs/SM (csrc/spmv.cu launch_dispatch)
     if len(sys.argv) > 2:
         variants = sys.argv[2:]
     for v in variants:
