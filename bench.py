@@ -491,9 +491,6 @@ def main():
                                  "stream and x gathers as the SpMV, one sum per lane, no rows"}
         except Exception as e:
             ceiling = {"error": repr(e)}
-    if world > 1:
-        del full
-        torch.cuda.empty_cache()
     y = op.y
     local_nnz = a.nnz
 
@@ -545,7 +542,7 @@ def main():
     # memory and y D2H inside the timed region.  N=1: `&A * &x` through sprs_b200_mul_mat_vec.
     # N>1: sprs_b200_mul_mat_vec_rowpart -- every rank moves only ITS slices of x and y.
     import ctypes as C
-    rows_local = r1 - r0
+    rows_local = rows_e2e = r1 - r0
     e2e_steps = max(3, min(args.steps, 10))
     if world == 1:
         hx = torch.empty(n, dtype=torch.float64).pin_memory()
@@ -558,15 +555,44 @@ def main():
         e2e_api = "sprs_b200_mul_mat_vec (host x, y; A resident as a device mirror)"
         hop = None
     else:
-        hx = torch.empty(max(rows_local, 1), dtype=torch.float64).pin_memory()
-        hx[:rows_local].copy_(x[r0:r1])
-        hy = torch.empty(max(rows_local, 1), dtype=torch.float64).pin_memory()
-        hop = CommHostSpMV(comm, a.mirror, bounds, n, multicast=not args.no_multicast)
+        # The host-vector form has its own cut.  Every y row costs 8 bytes over PCIe on top of
+        # its share of the SpMV, so its row blocks are balanced on nnz + (row_cost + c_pcie)*rows,
+        # c_pcie = 8 B / (measured D2H rate) in non-zero equivalents of the measured SpMV rate;
+        # x (needed by every rank, whatever its rows) is uploaded in EQUAL column slices.
+        probe_n = 4 << 20
+        hprobe = torch.empty(probe_n, dtype=torch.float64).pin_memory()
+        dprobe = torch.empty(probe_n, dtype=torch.float64, device=dev)
+        hprobe.copy_(dprobe)
+        torch.cuda.synchronize()
+        tp = time.perf_counter()
+        hprobe.copy_(dprobe)
+        torch.cuda.synchronize()
+        d2h_bps = 8.0 * probe_n / (time.perf_counter() - tp)
+        nnz_per_s = local_nnz / (my_kern * 1e-3)
+        vals = comm.allgather_f64([d2h_bps, nnz_per_s])
+        d2h_bps = float(np.mean([v[0] for v in vals]))
+        nnz_per_s = float(np.mean([v[1] for v in vals]))
+        c_pcie = 8.0 / d2h_bps * nnz_per_s
+        del hprobe, dprobe
+        e2e_bounds = nnz_balanced_bounds(full.indptr, world, row_cost=row_cost + c_pcie)
+        x_bounds = [n * g // world for g in range(world + 1)]
+        er0, er1 = e2e_bounds[rank], e2e_bounds[rank + 1]
+        xc0, xc1 = x_bounds[rank], x_bounds[rank + 1]
+        a_e2e = full.slice_rows(er0, er1)
+        ref_y_e2e = y[er0:er1].clone()
+        rows_e2e = er1 - er0
+        hx = torch.empty(max(xc1 - xc0, 1), dtype=torch.float64).pin_memory()
+        hx[:xc1 - xc0].copy_(x[xc0:xc1])
+        hy = torch.empty(max(rows_e2e, 1), dtype=torch.float64).pin_memory()
+        hop = CommHostSpMV(comm, a_e2e.mirror, e2e_bounds, n, multicast=not args.no_multicast,
+                           x_bounds=x_bounds)
 
         def e2e_step():
             hop.step(hx.data_ptr(), hy.data_ptr())
-        e2e_api = ("sprs_b200_mul_mat_vec_rowpart (each rank uploads its own slice of x, x is "
-                   "all-gathered over NVLink, each rank downloads its own slice of y)")
+        e2e_api = ("sprs_b200_mul_mat_vec_rowpart (each rank uploads an equal slice of x, x is "
+                   "all-gathered over NVLink, each rank downloads the y rows of its block; blocks "
+                   "balanced on nnz + %.1f*rows: SpMV row cost + 8 B of PCIe per row)"
+                   % (row_cost + c_pcie))
     for _ in range(2):
         e2e_step()
     torch.cuda.synchronize()
@@ -578,8 +604,8 @@ def main():
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     (e2e_ms,) = allmax([e2e_ms])
-    ref_y = y[r0:r1]
-    got_y = hy[:rows_local].to(dev)
+    ref_y = y[r0:r1] if world == 1 else ref_y_e2e
+    got_y = hy[:rows_e2e].to(dev)
     ok = bool(((got_y - ref_y).abs() <= 1e-9 * (ref_y.abs().max() + 1e-300)).all())
     (e2e_bad,) = allmax([0.0 if ok else 1.0])
     if hop is not None:
@@ -601,7 +627,7 @@ def main():
         flops = 2.0 * nnz
         alg_bytes = 12.0 * nnz + 8.0 * n
         gflops = flops / (ms_per_step * 1e-3) / 1e9
-        # roofline of the dominant kernel (spmv_pipe_kernel; the carry fix-up kernel -- and at
+        # roofline of the dominant kernel (spmv_rows_kernel; the carry fix-up kernel -- and at
         # N > 1 the put kernel of the 'push' exchange -- ride in the same event pair):
         # algorithmic bytes this rank's launch moves / its mean duration.
         local_bytes = 12.0 * local_nnz + 8.0 * rows_local
@@ -612,11 +638,11 @@ def main():
                 "frac": achieved / hbm_peak,
                 "traffic": bench_other.ncu_traffic(args.workload, world),
                 "traffic_source": bench_other.ncu_traffic(args.workload, world, source=True),
-                "kernel": "spmv_pipe_kernel (+ spmv_fixup_kernel)",
+                "kernel": "spmv_rows_kernel (+ spmv_fixup_kernel)",
                 "kernel_ms": per_rank_kern[0], "kernel_ms_per_rank": per_rank_kern,
                 "peak_source": peak_src,
                 "algorithmic_bytes": "12*nnz + 8*rows of this rank's block per launch",
-                "variant": os.environ.get("SPRS_B200_SPMV_VARIANT", "default 8,2 (nnz per lane per tile, CTAs/SM)")}
+                "variant": os.environ.get("SPRS_B200_SPMV_VARIANT", "default 1024,5,4,16 (tile cost units, CTAs/SM, loads in flight, row cost)")}
         if ceiling is not None:
             roof["gather_ceiling"] = ceiling
             if "frac_of_hbm" in ceiling:

@@ -473,21 +473,25 @@ class CommSpMV:
 
 class CommHostSpMV:
     """`&A * &x` on a row-partitioned matrix with HOST vectors (sprs_b200_mul_mat_vec_rowpart):
-    every rank uploads only its own slice of x (rows bounds[rank] .. bounds[rank+1] of a square
-    system: the same cut as y), the slices are all-gathered over NVLink, the block is multiplied
-    and only the rank's y slice comes back -- h2d + d2h bytes per step = 8 n + 8 n in TOTAL over
-    all ranks."""
+    every rank uploads only its own slice of x (columns x_bounds[rank] .. x_bounds[rank+1];
+    default: the same cut as the rows of a square system), the slices are all-gathered over
+    NVLink, the block is multiplied and only the rank's y slice (rows bounds[rank] ..
+    bounds[rank+1]) comes back -- h2d + d2h bytes per step = 8 n + 8 n in TOTAL over all ranks."""
 
-    def __init__(self, comm, mirror, bounds, n, multicast=True):
+    def __init__(self, comm, mirror, bounds, n, multicast=True, x_bounds=None):
         self.comm, self.mirror, self.bounds, self.n = comm, mirror, bounds, n
+        self.x_bounds = list(x_bounds) if x_bounds is not None else list(bounds)
+        if self.x_bounds[0] != 0 or self.x_bounds[-1] != n or len(self.x_bounds) != comm.world + 1:
+            raise ValueError("x_bounds must cut [0, n) into one slice per rank")
         self.x = comm.symm(8 * max(n, 2), multicast)
 
     def step(self, x_slice_ptr, y_slice_ptr):
         import ctypes as C
         ctx = self.comm.ctx
         r0, r1 = self.bounds[self.comm.rank], self.bounds[self.comm.rank + 1]
+        c0, c1 = self.x_bounds[self.comm.rank], self.x_bounds[self.comm.rank + 1]
         ctx.check(ctx.lib.sprs_b200_mul_mat_vec_rowpart(
-            self.comm.h, self.mirror.h, self.x.h, C.c_void_p(x_slice_ptr), r0, r1 - r0,
+            self.comm.h, self.mirror.h, self.x.h, C.c_void_p(x_slice_ptr), c0, c1 - c0,
             C.c_void_p(y_slice_ptr), r1 - r0))
 
     def close(self):

@@ -241,12 +241,15 @@ def _install_fakes(rank, world, port):
         multicast_ptr = 0
 
     class FakeCommHostSpMV:
-        def __init__(self, comm, mirror, bounds, n, multicast=True):
+        def __init__(self, comm, mirror, bounds, n, multicast=True, x_bounds=None):
             self.comm, self.blk, self.bounds, self.n, self.x = comm, mirror.owner, bounds, n, _FakeX()
+            self.x_bounds = x_bounds if x_bounds is not None else bounds
+            assert self.x_bounds[0] == 0 and self.x_bounds[-1] == n
 
         def step(self, x_ptr, y_ptr):
             r0, r1 = self.bounds[self.comm.rank], self.bounds[self.comm.rank + 1]
-            xs = D.tensor_view(x_ptr, max(r1 - r0, 1), "cpu")[:r1 - r0]
+            c0, c1 = self.x_bounds[self.comm.rank], self.x_bounds[self.comm.rank + 1]
+            xs = D.tensor_view(x_ptr, max(c1 - c0, 1), "cpu")[:c1 - c0]
             parts = [None] * self.comm.world
             dist.all_gather_object(parts, xs.numpy().copy())
             xf = np.concatenate(parts)

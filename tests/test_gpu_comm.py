@@ -84,6 +84,17 @@ def _rank_main(rank, world, q_id, q_out, ndev):
         err = np.abs(hy[:r1 - r0].numpy() - ref[r0:r1]) / (1e-6 * bound[r0:r1] + 1e-300)
         report["host_slices"] = float(err.max()) if err.size else 0.0
         hop.close()
+        # x uploaded in EQUAL column slices, whatever the row cut (bench.py's e2e form)
+        xb = [n * g // world for g in range(world + 1)]
+        hop = CommHostSpMV(comm, a.mirror, bounds, n, multicast=True, x_bounds=xb)
+        hx_slice = torch.from_numpy(hx[xb[rank]:xb[rank + 1]].copy()).pin_memory()
+        hy.fill_(float("nan"))
+        for _ in range(2):
+            hop.step(hx_slice.data_ptr(), hy.data_ptr())
+        err = np.abs(hy[:r1 - r0].numpy() - ref[r0:r1]) / (1e-6 * bound[r0:r1] + 1e-300)
+        report["host_equal_x_slices"] = (float(np.nanmax(err)) if np.all(np.isfinite(hy[:r1 - r0].numpy()))
+                                         else float("inf")) if err.size else 0.0
+        hop.close()
         comm.close()
         q_out.put((rank, report))
     except Exception as e:  # report instead of leaving the parent to time out
@@ -112,6 +123,7 @@ def test_comm_two_ranks_python_vs_oracle():
         for mode, worst in res[r]["modes"].items():
             assert worst <= 1.0, (r, mode, worst)
         assert res[r]["host_slices"] <= 1.0, (r, res[r])
+        assert res[r]["host_equal_x_slices"] <= 1.0, (r, res[r])
     if ndev >= 2 and res[0]["multicast_supported"]:
         assert any(m.endswith("+mc") for m in res[0]["modes"]), res[0]
     assert sp is not None

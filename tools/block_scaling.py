@@ -25,10 +25,34 @@ s_own = torch.cuda.Stream()
 sptr = C.c_void_p(s_own.cuda_stream)
 
 
+FLUSH_LIST = [int(v) for v in os.environ.get("BLOCK_SCALING_FLUSH_MB", "0").split(",")]  # > 0: write that many MB between products
+FLUSH_MB = 0
+flush = torch.empty(max(max(FLUSH_LIST), 1) << 17, device="cuda", dtype=torch.float64)
+
+
+def time_block_cold(a, y, stream_ptr, reps=20):
+    """each product timed on its own, after FLUSH_MB of plain writes went through L2 (what a
+    rank's L2 sees between two steps when its peers deposit their slices of y)"""
+    tot = 0.0
+    with torch.cuda.stream(s_own):
+        for i in range(reps + 3):
+            flush[:FLUSH_MB << 17].fill_(float(i))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s_own)
+            ctx.check(ctx.lib.sprs_b200_spmv_dev(ctx.h, a.mirror.h, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), 0, stream_ptr))
+            e1.record(s_own)
+            s_own.synchronize()
+            if i >= 3:
+                tot += e0.elapsed_time(e1)
+    return tot / reps
+
+
 def time_block(r0, r1, persist, stream_ptr, reps=30):
     a = full if (r0, r1) == (0, n) else full.slice_rows(r0, r1)
     y = torch.empty(max(r1 - r0, 1), device="cuda", dtype=torch.float64)
     torch.cuda.synchronize()
+    if FLUSH_MB:
+        return a.nnz, time_block_cold(a, y, stream_ptr)
     with torch.cuda.stream(s_own):
         for _ in range(5):
             ctx.check(ctx.lib.sprs_b200_spmv_dev(ctx.h, a.mirror.h, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), 0, stream_ptr))
@@ -41,12 +65,13 @@ def time_block(r0, r1, persist, stream_ptr, reps=30):
     return a.nnz, e0.elapsed_time(e1) / reps
 
 
-for persist in (False,):
+for FLUSH_MB in FLUSH_LIST:
+    persist = False
     pts = []
     for lo, hi in ((0, 1), (3, 4), (6, 7), (2, 4), (4, 8), (0, 8)):
         nnz, ms = time_block(b[lo], b[hi], persist, sptr)
         pts.append((nnz, ms))
-        print(json.dumps({"persist_x_in_l2": persist, "blocks": [lo, hi], "nnz": nnz, "ms": round(ms, 4),
+        print(json.dumps({"flush_mb": FLUSH_MB, "prefetch_x": os.environ.get("SPRS_B200_SPMV_PREFETCH_X", "1"), "blocks": [lo, hi], "nnz": nnz, "ms": round(ms, 4),
                           "gnnz_s": round(nnz / ms / 1e6, 1)}), flush=True)
     A = np.array([[1.0, p[0]] for p in pts])
     t = np.array([p[1] for p in pts])
