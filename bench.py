@@ -642,7 +642,7 @@ def main():
                 "kernel_ms": per_rank_kern[0], "kernel_ms_per_rank": per_rank_kern,
                 "peak_source": peak_src,
                 "algorithmic_bytes": "12*nnz + 8*rows of this rank's block per launch",
-                "variant": os.environ.get("SPRS_B200_SPMV_VARIANT", "default 1024,5,4,16 (tile cost units, CTAs/SM, loads in flight, row cost)")}
+                "variant": os.environ.get("SPRS_B200_SPMV_VARIANT", "default 1024,16 (cost units per tile, row cost); 8-warp CTAs, 5 per SM, 4 loads in flight")}
         if ceiling is not None:
             roof["gather_ceiling"] = ceiling
             if "frac_of_hbm" in ceiling:

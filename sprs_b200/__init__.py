@@ -14,9 +14,9 @@ __all__ = ["CSC", "CSR", "Context", "CsMat", "CsVec", "DeviceCsMat", "SprsPanic"
 __version__ = "0.1.0"
 import os as _os
 
-_v = (_os.environ.get("SPRS_B200_SPMV_VARIANT", "") + ",,,").split(",")
-SPMV_TILE = int(_v[0]) if _v[0] else 1024      # cost units per SpMV warp tile (csrc/spmv.cu)
-SPMV_ROW_COST = int(_v[3]) if _v[3] else 16    # cost of one row end, in non-zeros
+_v = (_os.environ.get("SPRS_B200_SPMV_VARIANT", "") + ",").split(",")   # "w,row_cost" (csrc/spmv.cu)
+SPMV_TILE = int(_v[0]) if _v[0] else 1024      # cost units per SpMV warp tile
+SPMV_ROW_COST = int(_v[1]) if _v[1] else 16    # cost of one row end, in non-zeros
 
 
 def spmv_rows_cut_by_tiles(indptr):

@@ -49,7 +49,7 @@ namespace {
 // tile there held ~1700 rows -- 55 dependent boundary fetches for one warp while the others
 // waited (ncu on that region: 125 Gnnz/s against 280 on the dense head, half the warps idle).
 // With the row cost in the cut a tile has at most W / ROW_COST row ends.
-constexpr uint32_t SPMV_ROW_COST = 16;  // default; 4th field of SPRS_B200_SPMV_VARIANT for tuning runs
+constexpr uint32_t SPMV_ROW_COST = 16;  // default; 2nd field of SPRS_B200_SPMV_VARIANT for tuning runs
 
 template <typename P>
 __global__ void tile_cut_kernel(const P* __restrict__ indptr, uint32_t rows, uint64_t nnz,
@@ -381,36 +381,37 @@ __global__ void spmv_fixup_range_kernel(const uint32_t* __restrict__ tile_row, c
 }
 
 // ---- launch configuration ---------------------------------------------------------
+// One kernel configuration ships: 8-warp CTAs, 5 per SM (= __launch_bounds__ minBlocks: the
+// register budget; the kernel hides latency with warps, not registers), 4 loads of each kind in
+// flight per lane.  Round 2 swept 4-6 CTAs/SM and 4 / 6 / 8 loads (profiles/r2_spmv_notes.md):
+// the others lost and were deleted.  The two numbers of the CUT stay tunable for experiments:
+// SPRS_B200_SPMV_VARIANT="w,row_cost" (cost units per tile, cost of a row end in non-zeros;
+// read once per process -- they are baked into every mirror's tile arrays).
 struct SpmvVariant {
-    int wt, ctas_per_sm, u, row_cost;
+    int wt, row_cost;
 };
-// default picked from the round-2 sweeps (profiles/r2_spmv_notes.md);
-// SPRS_B200_SPMV_VARIANT="wt,ctas,u" (tile nnz, CTAs of 8 warps per SM, loads in flight per lane
-// and kind) overrides it for tuning runs (read once per process: the tile size is baked into
-// every mirror's tile_row).
 SpmvVariant spmv_variant() {
     static SpmvVariant v = [] {
-        SpmvVariant d{1024, 5, 4, (int)SPMV_ROW_COST};
+        SpmvVariant d{1024, (int)SPMV_ROW_COST};
         if (const char* e = getenv("SPRS_B200_SPMV_VARIANT")) {
-            int a, b, c, rc = (int)SPMV_ROW_COST;
-            const int got = sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &rc);
-            if (got >= 3 && rc >= 0) d = SpmvVariant{a, b, c, rc};
+            int a, rc = (int)SPMV_ROW_COST;
+            const int got = sscanf(e, "%d,%d", &a, &rc);
+            if (got >= 1 && a >= 64 && rc >= 0) d = SpmvVariant{a, rc};
         }
         return d;
     }();
     return v;
 }
 
-constexpr int SPMV_NWARPS = 8;
+constexpr int SPMV_NWARPS = 8, SPMV_CTAS_PER_SM = 5, SPMV_LOADS_IN_FLIGHT = 4;
 
-template <typename P, int CTAS, int U>
+template <typename P>
 int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
                    const SpmvTargets& yt, int accumulate, uint64_t t0, uint64_t t1,
                    cudaStream_t s) {
     if (m->n_tiles >= 0xffffffffull)
         SPRS_FAIL(ctx, SPRS_B200_ERR_UNSUPPORTED, "spmv: more than 2^32 tiles");
-    // CTAS resident CTAs per SM is also the kernel's __launch_bounds__ minBlocks: it sets the
-    // register budget (the kernel hides latency with warps, not with registers).
+    constexpr int CTAS = SPMV_CTAS_PER_SM, U = SPMV_LOADS_IN_FLIGHT;
     const bool multi = yt.n > 1;
     auto kern = multi ? spmv_rows_kernel<P, SPMV_NWARPS, CTAS, U, true>
                       : spmv_rows_kernel<P, SPMV_NWARPS, CTAS, U, false>;
@@ -435,21 +436,6 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
                                                      (uint32_t)t1, accumulate, ctx->pol_evict_first,
                                                      ctx->pol_evict_last);
     return SPRS_B200_OK;
-}
-
-template <typename P>
-int launch_dispatch(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d_x,
-                    const SpmvTargets& yt, int accumulate, uint64_t t0, uint64_t t1,
-                    cudaStream_t s) {
-    const SpmvVariant v = spmv_variant();
-#define SPMV_CASE(CT, UU)                                                          \
-    if (v.ctas_per_sm == CT && v.u == UU) /* the tile size only enters the cuts */  \
-        return launch_variant<P, CT, UU>(ctx, m, d_x, yt, accumulate, t0, t1, s);
-    SPMV_CASE(5, 4)
-    SPMV_CASE(4, 6)
-    SPMV_CASE(4, 8)
-#undef SPMV_CASE
-    SPRS_FAIL(ctx, SPRS_B200_ERR_ARGUMENT, "unknown SPRS_B200_SPMV_VARIANT (wt,ctas,u)");
 }
 
 int check_spmv_args(sprs_b200_ctx* ctx, const sprs_b200_csmat* m) {
@@ -492,9 +478,9 @@ int spmv_launch_targets(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const doub
     SPRS_TRY(check_spmv_args(ctx, m));
     if (m->rows == 0) return SPRS_B200_OK;
     if (m->indptr_bytes == 4)
-        SPRS_TRY(launch_dispatch<uint32_t>(ctx, m, d_x, yt, accumulate, 0, m->n_tiles, s));
+        SPRS_TRY(launch_variant<uint32_t>(ctx, m, d_x, yt, accumulate, 0, m->n_tiles, s));
     else
-        SPRS_TRY(launch_dispatch<uint64_t>(ctx, m, d_x, yt, accumulate, 0, m->n_tiles, s));
+        SPRS_TRY(launch_variant<uint64_t>(ctx, m, d_x, yt, accumulate, 0, m->n_tiles, s));
     ctx->launches += 1;
     if (m->n_tiles > 1) {
         const unsigned fgrid = (unsigned)((m->n_tiles - 1 + 255) / 256);
@@ -521,9 +507,9 @@ int spmv_launch_tile_range(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const d
     yt.p[0] = d_y;
     for (int q = 1; q < SPMV_MAX_TARGETS; ++q) yt.p[q] = nullptr;
     if (m->indptr_bytes == 4)
-        SPRS_TRY(launch_dispatch<uint32_t>(ctx, m, d_x, yt, accumulate, t0, t1, s));
+        SPRS_TRY(launch_variant<uint32_t>(ctx, m, d_x, yt, accumulate, t0, t1, s));
     else
-        SPRS_TRY(launch_dispatch<uint64_t>(ctx, m, d_x, yt, accumulate, t0, t1, s));
+        SPRS_TRY(launch_variant<uint64_t>(ctx, m, d_x, yt, accumulate, t0, t1, s));
     spmv_fixup_range_kernel<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, s>>>(
         m->d_tile_row, m->d_carry, d_y, t0, t1);
     ctx->launches += 2;

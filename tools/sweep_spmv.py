@@ -1,4 +1,4 @@
-"""Times the SpMV kernel variants (SPRS_B200_SPMV_VARIANT=wt,stages,nwarps,ctas_per_sm) on the
+"""Times the SpMV tile cuts (SPRS_B200_SPMV_VARIANT=w,row_cost) on the
 bench workloads; one subprocess per variant because the variant is read once per process."""
 import json
 import os
@@ -33,7 +33,7 @@ def main():
     workloads = [("rand_1m_32", "rand", 1_000_000, 32), ("rmat_10m_100", "rmat", 10_000_000, 100)]
     if len(sys.argv) > 1 and sys.argv[1] == "small":
         workloads = [("rand_1m_32", "rand", 1_000_000, 32), ("rmat_1m_100", "rmat", 1_000_000, 100)]
-    variants = ["1024,5,4,16", "2048,5,4,16", "1024,5,4,8", "1024,5,4,32", "2048,5,4,32", "512,5,4,16"]  # tile nnz, CTAs/SM (csrc/spmv.cu launch_dispatch)
+    variants = ["1024,16", "2048,16", "1024,8", "1024,32", "2048,32", "512,16"]  # cost units per tile, row cost (csrc/spmv.cu)
     if len(sys.argv) > 2:
         variants = sys.argv[2:]
     for v in variants:
