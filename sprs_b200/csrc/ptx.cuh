@@ -70,3 +70,9 @@ static __device__ __forceinline__ double ldg_stream_f64(const double* p, uint64_
     return v;
 }
 
+// 8-byte store carrying an L2 eviction policy (peer / multicast targets: the line is the first
+// victim in the L2 it lands in)
+static __device__ __forceinline__ void stg_f64_hint(double* p, double v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy)
+                 : "memory");
+}

@@ -86,6 +86,7 @@ struct RowSink {
     double* carry_slot;
     uint32_t r1;                // first row NOT owned by the tile (== its carry row when < rows)
     int accumulate;
+    uint64_t pol_remote;        // MULTI only: L2 policy of the stores to targets 1.. (0: plain)
 };
 // y[r] is written to every target buffer: target 0 is this GPU's own y; targets 1.. are the
 // peer GPUs' y buffers (CUDA IPC / VMM mappings) or the NVSwitch multicast address of y (fused
@@ -99,7 +100,12 @@ __device__ __forceinline__ void sink_row(const RowSink& k, uint64_t r, double su
         if (MULTI) {
 #pragma unroll
             for (int q = 1; q < SPMV_MAX_TARGETS; ++q)
-                if (q < k.yt->n) k.yt->p[q][r] = v;
+                if (q < k.yt->n) {
+                    if (k.pol_remote)
+                        stg_f64_hint(k.yt->p[q] + r, v, k.pol_remote);
+                    else
+                        k.yt->p[q][r] = v;
+                }
         }
     } else {
         *k.carry_slot = sum;  // row continues in a later tile: spmv_fixup_kernel adds it
@@ -253,7 +259,8 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
                      const __grid_constant__ SpmvTargets yt,
                      double* __restrict__ carry, uint64_t nnz, uint32_t rows, uint32_t t_begin,
                      uint32_t t_end /* this launch covers tiles [t_begin, t_end) */, int accumulate,
-                     uint64_t pol_stream /* L2 evict_first */, uint64_t polx /* L2 evict_last */) {
+                     uint64_t pol_stream /* L2 evict_first */, uint64_t polx /* L2 evict_last */,
+                     uint64_t pol_remote /* MULTI: policy of the peer stores, 0 = plain */) {
     // (the two L2 policies are kernel PARAMETERS: warp-uniform by construction, so they live in
     // uniform registers; as per-thread createpolicy results every hinted load re-materialised
     // its descriptor)
@@ -263,6 +270,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
     sink.y = yt.p[0];
     sink.yt = &yt;
     sink.accumulate = accumulate;
+    sink.pol_remote = pol_remote;
     uint32_t t = t_begin + blockIdx.x * NWARPS + warp;
     if (t >= t_end) return;
     // row range and the first 32 row boundaries of a tile are fetched ONE TILE AHEAD
@@ -426,6 +434,11 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
                                             carve));
         configured = true;
     }
+    // experiment switch, read per launch: peer stores of y as L2 evict_first lines
+    uint64_t pol_remote = 0;
+    if (multi)
+        if (const char* e = getenv("SPRS_B200_SPMV_Y_EVICT_FIRST"))
+            if (e[0] == '1') pol_remote = ctx->pol_evict_first;
     uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
     const uint64_t need = (t1 - t0 + SPMV_NWARPS - 1) / SPMV_NWARPS;
     if (grid > need) grid = need;
@@ -434,7 +447,7 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
                                                      m->d_carry,
                                                      m->nnz, (uint32_t)m->rows, (uint32_t)t0,
                                                      (uint32_t)t1, accumulate, ctx->pol_evict_first,
-                                                     ctx->pol_evict_last);
+                                                     ctx->pol_evict_last, pol_remote);
     return SPRS_B200_OK;
 }
 

@@ -58,3 +58,4 @@ static inline uint64_t policy_evict_last() { return 0; }
 static inline double ldg_f64_hint(const double* p, uint64_t) { return *p; }
 static inline uint32_t ldg_stream_u32(const uint32_t* p, uint64_t) { return *p; }
 static inline double ldg_stream_f64(const double* p, uint64_t) { return *p; }
+static inline void stg_f64_hint(double* p, double v, uint64_t) { *p = v; }

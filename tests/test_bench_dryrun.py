@@ -334,4 +334,4 @@ def test_scale_modes_control_flow_gloo_world2():
     assert len(done) == 3 and all(d["correct"] and d["speedup_vs_n1"] > 0 for d in done)
     assert [d for d in lines if "skipped" in d][0]["mode"] == "push+mc"   # the stand-in has no multicast
     assert any("partition_round" in d for d in lines) and any("setup_seconds" in d for d in lines)
-    assert sum(1 for d in lines if "e2e_host_slices" in d and d.get("correct")) == 2
+    assert sum(1 for d in lines if "e2e_host_slices" in d and d.get("correct")) == 3   # same cut x2, pcie cut

@@ -7,8 +7,10 @@ events, max over ranks.  One JSON line per mode on rank 0.
       [--n 10000000 --npr 100 --steps 20 --warmup 5 --modes "nccl push fused push+mc fused+mc"]
 
 Modes: nccl = NCCL all_gather after the kernel; push / fused = the library's communicator over
-CUDA IPC peer mappings; "+mc" = the same through the NVSwitch multicast address of y.  The
-multicast modes run last (they are the ones that can fail hard on an unsupported box).
+CUDA IPC peer mappings; "+mc" = the same through the NVSwitch multicast address of y; "+yef" =
+fused with the peer stores of y carrying an L2 evict_first policy (experiment switch
+SPRS_B200_SPMV_Y_EVICT_FIRST).  The multicast modes run last (they are the ones that can fail
+hard on an unsupported box).
 """
 import argparse
 import json
@@ -26,7 +28,7 @@ def main():
     ap.add_argument("--npr", type=int, default=100)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--modes", default="nccl push fused push+mc fused+mc")
+    ap.add_argument("--modes", default="nccl push fused fused+yef push+mc fused+mc fused+mc+yef")
     args = ap.parse_args()
 
     import torch
@@ -112,7 +114,9 @@ def main():
     r0, r1 = bounds[rank], bounds[rank + 1]
 
     def run_mode(mode):
-        name, _, mc = mode.partition("+")
+        parts = mode.split("+")
+        name, mc = parts[0], ("mc" if "mc" in parts[1:] else "")
+        os.environ["SPRS_B200_SPMV_Y_EVICT_FIRST"] = "1" if "yef" in parts[1:] else "0"
         if name == "nccl":
             yb = torch.zeros(n, device=dev, dtype=torch.float64)
             op = RowPartitionedSpMV(bounds, rank, world, yb, lambda xv, ys: G.spmv(ctx, a, xv, ys), dist=dist)
@@ -163,12 +167,25 @@ def main():
             res = {"mode": mode, "error": repr(e)[:300]}
         say(res)
 
-    # ---- host-vector form (e2e): every rank moves only its own slices
-    for mc in (False, True):
+    os.environ["SPRS_B200_SPMV_Y_EVICT_FIRST"] = "0"
+    # ---- host-vector form (e2e): every rank moves only its own slices.  "same cut": x and y
+    # sliced like the SpMV's row blocks; "pcie cut": x in equal slices, row blocks re-balanced
+    # with 8 bytes of PCIe per y row on top of the SpMV cost (what bench.py's e2e does)
+    for mc, pcie_cut in ((False, False), (True, False), (True, True)):
         try:
-            hop = CommHostSpMV(comm, a.mirror, bounds, n, multicast=mc)
-            hx = torch.empty(max(r1 - r0, 1), dtype=torch.float64).pin_memory()
-            hx[:r1 - r0].copy_(x[r0:r1])
+            if pcie_cut:
+                c_pcie = 8.0 / 50e9 * (full.nnz / world / (n1_ms / world * 1e-3))
+                eb = nnz_balanced_bounds(full.indptr, world, row_cost=row_cost + c_pcie)
+                xb = [n * g // world for g in range(world + 1)]
+                del a
+                torch.cuda.empty_cache()
+                a = full.slice_rows(eb[rank], eb[rank + 1])
+                bounds, (r0, r1) = eb, (eb[rank], eb[rank + 1])
+            else:
+                xb = bounds
+            hop = CommHostSpMV(comm, a.mirror, bounds, n, multicast=mc, x_bounds=xb)
+            hx = torch.empty(max(xb[rank + 1] - xb[rank], 1), dtype=torch.float64).pin_memory()
+            hx[:xb[rank + 1] - xb[rank]].copy_(x[xb[rank]:xb[rank + 1]])
             hy = torch.empty(max(r1 - r0, 1), dtype=torch.float64).pin_memory()
             for _ in range(2):
                 hop.step(hx.data_ptr(), hy.data_ptr())
@@ -181,6 +198,8 @@ def main():
             ok = bool(((hy[:r1 - r0].to(dev) - y_ref[r0:r1]).abs() <= 1e-9 * scale).all().item())
             (bad,) = allmax([0.0 if ok else 1.0])
             say({"e2e_host_slices": "multicast" if mc and hop.x.multicast_ptr else "ipc",
+                 "cut": "pcie" if pcie_cut else "same", "rows_per_rank_max": max(
+                     bounds[g + 1] - bounds[g] for g in range(world)),
                  "ms_per_step": ms, "correct": bad == 0.0})
             hop.close()
         except Exception as e:
