@@ -70,9 +70,21 @@ static __device__ __forceinline__ double ldg_stream_f64(const double* p, uint64_
     return v;
 }
 
-// 8-byte store carrying an L2 eviction policy (peer / multicast targets: the line is the first
-// victim in the L2 it lands in)
-static __device__ __forceinline__ void stg_f64_hint(double* p, double v, uint64_t policy) {
-    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy)
+// ---- TMA bulk store shared -> global (bulk async-group completion); the destination may be a
+// peer GPU's memory or an NVSwitch multicast address
+static __device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
                  : "memory");
+}
+static __device__ __forceinline__ void bulk_commit_group() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the shared-memory SOURCE of every committed group has been read (it may be overwritten)
+static __device__ __forceinline__ void bulk_wait_group_read0() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+// every committed group has completed (its writes are performed)
+static __device__ __forceinline__ void bulk_wait_group0() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }

@@ -49,6 +49,7 @@ namespace {
 // tile there held ~1700 rows -- 55 dependent boundary fetches for one warp while the others
 // waited (ncu on that region: 125 Gnnz/s against 280 on the dense head, half the warps idle).
 // With the row cost in the cut a tile has at most W / ROW_COST row ends.
+constexpr int SPMV_STAGE_ROWS = 66;  // fused all-gather: staged rows per warp tile (64 row ends + parity pad)
 constexpr uint32_t SPMV_ROW_COST = 16;  // default; 2nd field of SPRS_B200_SPMV_VARIANT for tuning runs
 
 template <typename P>
@@ -86,7 +87,11 @@ struct RowSink {
     double* carry_slot;
     uint32_t r1;                // first row NOT owned by the tile (== its carry row when < rows)
     int accumulate;
-    uint64_t pol_remote;        // MULTI only: L2 policy of the stores to targets 1.. (0: plain)
+    // MULTI only: the tile's rows for the peers are STAGED in shared memory (row r at
+    // stage[r - stage_off]) and leave as one TMA bulk store per target when the tile is done;
+    // nullptr = every row is stored to the peers directly
+    double* stage;
+    uint32_t stage_off;
 };
 // y[r] is written to every target buffer: target 0 is this GPU's own y; targets 1.. are the
 // peer GPUs' y buffers (CUDA IPC / VMM mappings) or the NVSwitch multicast address of y (fused
@@ -99,13 +104,13 @@ __device__ __forceinline__ void sink_row(const RowSink& k, uint64_t r, double su
         k.y[r] = v;
         if (MULTI) {
 #pragma unroll
-            for (int q = 1; q < SPMV_MAX_TARGETS; ++q)
-                if (q < k.yt->n) {
-                    if (k.pol_remote)
-                        stg_f64_hint(k.yt->p[q] + r, v, k.pol_remote);
-                    else
-                        k.yt->p[q][r] = v;
-                }
+            if (k.stage) {
+                k.stage[(uint32_t)r - k.stage_off] = v;
+            } else {
+#pragma unroll
+                for (int q = 1; q < SPMV_MAX_TARGETS; ++q)
+                    if (q < k.yt->n) k.yt->p[q][r] = v;
+            }
         }
     } else {
         *k.carry_slot = sum;  // row continues in a later tile: spmv_fixup_kernel adds it
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
                      double* __restrict__ carry, uint64_t nnz, uint32_t rows, uint32_t t_begin,
                      uint32_t t_end /* this launch covers tiles [t_begin, t_end) */, int accumulate,
                      uint64_t pol_stream /* L2 evict_first */, uint64_t polx /* L2 evict_last */,
-                     uint64_t pol_remote /* MULTI: policy of the peer stores, 0 = plain */) {
+                     int stage_rows /* MULTI: peers get their rows by TMA bulk stores (0: plain stores) */) {
     // (the two L2 policies are kernel PARAMETERS: warp-uniform by construction, so they live in
     // uniform registers; as per-thread createpolicy results every hinted load re-materialised
     // its descriptor)
@@ -270,7 +275,24 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
     sink.y = yt.p[0];
     sink.yt = &yt;
     sink.accumulate = accumulate;
-    sink.pol_remote = pol_remote;
+    sink.stage = nullptr;
+    sink.stage_off = 0;
+    // The peers' copies of y (fused all-gather).  A store per finished row to a peer or to the
+    // multicast address slows the ISSUING kernel in proportion to its row count (8 GPUs,
+    // profiles/r2_scale_modes_8gpu_mergepath.txt: +0.03 ms on the dense head rank, +0.16 ms on a
+    // tail rank with 3 M rows, against 0.52 ms of compute): remote stores queue in the LSU in
+    // front of the loads.  So the rows of a tile are staged in shared memory (at most 64 row ends
+    // per tile = 512 bytes per warp) and leave through the TMA instead -- one cp.async.bulk per
+    // target and tile, nothing for the LSU to wait on.  Bulk copies need 16-byte alignment on both
+    // sides: row r sits at stage[r + par - even base] with par = the parity of the peers' y
+    // address (the launcher checked that all targets share it), an odd first / last row goes out
+    // as a plain store.
+    double* my_stage = nullptr;  // (the single-target kernel keeps all of the unified array as L1)
+    if constexpr (MULTI) {
+        __shared__ __align__(16) double stage_all[NWARPS * SPMV_STAGE_ROWS];
+        my_stage = stage_all + warp * SPMV_STAGE_ROWS;
+    }
+    const uint32_t par = MULTI ? (uint32_t)(((uintptr_t)yt.p[1] >> 3) & 1) : 0u;
     uint32_t t = t_begin + blockIdx.x * NWARPS + warp;
     if (t >= t_end) return;
     // row range and the first 32 row boundaries of a tile are fetched ONE TILE AHEAD
@@ -291,6 +313,17 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
         }
         sink.carry_slot = carry + t;
         sink.r1 = r1;
+        if (MULTI && stage_rows) {
+            // rows r0 .. r1-1 are the ones this tile delivers (r1 itself continues: carry)
+            const uint32_t base = (r0 + par) & ~1u;  // even element index of the first staged slot
+            const bool fits = r1 > r0 && (r1 + par - base) <= (uint32_t)SPMV_STAGE_ROWS;
+            sink.stage = fits ? my_stage : nullptr;
+            sink.stage_off = base - par;  // (wraps for r0 = 0, par = 1: r - stage_off is still r + 1)
+            if (fits) {  // the previous tile's bulk stores must have READ the stage
+                if (lane == 0) bulk_wait_group_read0();
+                __syncwarp();
+            }
+        }
         const uint32_t r_last = r1 < rows ? r1 : r1 - 1;
         const uint64_t cnt = k1 - k0, nr = (uint64_t)(r_last - r0) + 1;  // mean row length = cnt / nr
 #define SPMV_ROWS(G)                                                                            \
@@ -305,6 +338,29 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
         else
             SPMV_ROWS(32);
 #undef SPMV_ROWS
+        if (MULTI && sink.stage) {
+            fence_proxy_async();  // the lanes' stage writes -> visible to the async proxy
+            __syncwarp();
+            if (lane == 0) {
+                uint32_t lo = r0, hi = r1;
+                if ((lo + par) & 1u) {  // odd first row: plain store
+                    const double v = my_stage[lo - sink.stage_off];
+                    for (int q = 1; q < yt.n; ++q) yt.p[q][lo] = v;
+                    ++lo;
+                }
+                if ((hi - lo) & 1u) {  // odd count: the last row as a plain store
+                    --hi;
+                    const double v = my_stage[hi - sink.stage_off];
+                    for (int q = 1; q < yt.n; ++q) yt.p[q][hi] = v;
+                }
+                if (hi > lo) {
+                    for (int q = 1; q < yt.n; ++q)
+                        bulk_s2g(yt.p[q] + lo, my_stage + (lo - sink.stage_off), (hi - lo) * 8u);
+                    bulk_commit_group();
+                }
+            }
+            sink.stage = nullptr;
+        }
         if (tn >= t_end) break;
         const P b_next = (uint64_t)r0n + lane <= (r1n < rows ? (uint64_t)r1n + 1 : (uint64_t)r1n)
                              ? indptr[(size_t)r0n + lane] : (P)0;
@@ -315,6 +371,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
         k1 = k1n;
         b_first = b_next;
     }
+    if (MULTI && stage_rows && lane == 0) bulk_wait_group0();  // performed before the grid retires
 }
 
 // carries: tile t left the partial sum of row tile_row[t+1] in carry[t]; consecutive
@@ -428,17 +485,24 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
     if (!configured) {
         // no shared memory at all: the whole unified array is L1 for the gathers (every
         // in-flight gather holds an L1 line; lab carve sweep: 0 % 303, 50 % 275, 100 % 106 Gnnz/s)
-        int carve = 0;
+        // (the multi-target kernel stages 4.1 KB per CTA for its TMA stores: 5 CTAs need 26 KB)
+        int carve = multi ? 15 : 0;
         if (const char* e = getenv("SPRS_B200_SPMV_CARVEOUT")) carve = atoi(e);
         SPRS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                             carve));
         configured = true;
     }
-    // experiment switch, read per launch: peer stores of y as L2 evict_first lines
-    uint64_t pol_remote = 0;
-    if (multi)
-        if (const char* e = getenv("SPRS_B200_SPMV_Y_EVICT_FIRST"))
-            if (e[0] == '1') pol_remote = ctx->pol_evict_first;
+    // peers' rows through the TMA (staged per tile) unless the targets disagree on the parity of
+    // their address (a bulk copy needs 16-byte alignment) or SPRS_B200_SPMV_PEER_STORES=direct
+    // asks for a plain store per row (read per launch: tools/scale_modes.py times both)
+    int stage_rows = 0;
+    if (multi) {
+        stage_rows = SPMV_STAGE_ROWS;
+        for (int q = 2; q < yt.n; ++q)
+            if ((((uintptr_t)yt.p[q] ^ (uintptr_t)yt.p[1]) >> 3) & 1) stage_rows = 0;
+        if (const char* e = getenv("SPRS_B200_SPMV_PEER_STORES"))
+            if (e[0] == 'd') stage_rows = 0;
+    }
     uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
     const uint64_t need = (t1 - t0 + SPMV_NWARPS - 1) / SPMV_NWARPS;
     if (grid > need) grid = need;
@@ -447,7 +511,7 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
                                                      m->d_carry,
                                                      m->nnz, (uint32_t)m->rows, (uint32_t)t0,
                                                      (uint32_t)t1, accumulate, ctx->pol_evict_first,
-                                                     ctx->pol_evict_last, pol_remote);
+                                                     ctx->pol_evict_last, stage_rows);
     return SPRS_B200_OK;
 }
 

@@ -284,3 +284,31 @@ def test_spmv_linearity_and_scaling_full_size(sp):
         O.mul_acc_mat_vec_csr(np.array([0, e - s], np.uint32), ci, cv, hx, ref)
         bound = float(np.sum(np.abs(cv * hx[ci])))
         assert abs(float(y1[r]) - ref[0]) <= RTOL * bound + 1e-300
+
+
+@pytest.mark.parametrize("offsets", [(0, 0, 0), (5, 5, 5), (0, 4, 2), (1, 2, 1)])
+def test_spmv_allgather_targets_identical_bits(sp, offsets):
+    """sprs_b200_spmv_allgather_dev (the fused all-gather of the multi-GPU path with every target
+    on this device): targets 1.. receive the rows of a tile as ONE TMA bulk store from shared
+    memory (odd first / last rows as plain stores); every target must hold the plain SpMV's bits,
+    and nothing outside the row block may be touched.  Targets whose addresses differ in
+    16-byte parity (last case) take the store-per-row path."""
+    import ctypes as C
+    import torch
+    from sprs_b200 import generate as G
+    ctx = sp.Context.default()
+    n = 300_000
+    a = G.rmat_csr(ctx, n, 24, seed=21)
+    x = G.normal_vector(ctx, n, 5)
+    ref = torch.empty(n, device="cuda", dtype=torch.float64)
+    G.spmv(ctx, a, x, ref)
+    pad = 8
+    bufs = [torch.full((n + 2 * pad,), -7.0, device="cuda", dtype=torch.float64) for _ in offsets]
+    ptrs = (C.c_void_p * len(bufs))(*[b.data_ptr() + 8 * o for b, o in zip(bufs, offsets)])
+    torch.cuda.synchronize()
+    ctx.check(ctx.lib.sprs_b200_spmv_allgather_dev(ctx.h, a.mirror.h, C.c_void_p(x.data_ptr()), 0,
+                                                  len(bufs), ptrs, 0, None))
+    torch.cuda.synchronize()
+    for b, o in zip(bufs, offsets):
+        assert torch.equal(b[o:o + n].view(torch.int64), ref.view(torch.int64)), o
+        assert bool((b[:o] == -7.0).all()) and bool((b[o + n:] == -7.0).all()), o

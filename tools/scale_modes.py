@@ -7,10 +7,11 @@ events, max over ranks.  One JSON line per mode on rank 0.
       [--n 10000000 --npr 100 --steps 20 --warmup 5 --modes "nccl push fused push+mc fused+mc"]
 
 Modes: nccl = NCCL all_gather after the kernel; push / fused = the library's communicator over
-CUDA IPC peer mappings; "+mc" = the same through the NVSwitch multicast address of y; "+yef" =
-fused with the peer stores of y carrying an L2 evict_first policy (experiment switch
-SPRS_B200_SPMV_Y_EVICT_FIRST).  The multicast modes run last (they are the ones that can fail
-hard on an unsupported box).
+CUDA IPC peer mappings; "+mc" = the same through the NVSwitch multicast address of y.  fused =
+the SpMV kernel stages a tile's rows in shared memory and sends them with one TMA bulk store per
+target; "+direct" = a plain store per finished row instead (SPRS_B200_SPMV_PEER_STORES=direct,
+the round's first form).  The multicast modes run last (they are the ones that can fail hard on
+an unsupported box).
 """
 import argparse
 import json
@@ -28,7 +29,7 @@ def main():
     ap.add_argument("--npr", type=int, default=100)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--modes", default="nccl push fused fused+yef push+mc fused+mc fused+mc+yef")
+    ap.add_argument("--modes", default="nccl push fused+direct fused push+mc fused+mc+direct fused+mc")
     args = ap.parse_args()
 
     import torch
@@ -116,7 +117,7 @@ def main():
     def run_mode(mode):
         parts = mode.split("+")
         name, mc = parts[0], ("mc" if "mc" in parts[1:] else "")
-        os.environ["SPRS_B200_SPMV_Y_EVICT_FIRST"] = "1" if "yef" in parts[1:] else "0"
+        os.environ["SPRS_B200_SPMV_PEER_STORES"] = "direct" if "direct" in parts[1:] else "tma"
         if name == "nccl":
             yb = torch.zeros(n, device=dev, dtype=torch.float64)
             op = RowPartitionedSpMV(bounds, rank, world, yb, lambda xv, ys: G.spmv(ctx, a, xv, ys), dist=dist)
@@ -167,7 +168,7 @@ def main():
             res = {"mode": mode, "error": repr(e)[:300]}
         say(res)
 
-    os.environ["SPRS_B200_SPMV_Y_EVICT_FIRST"] = "0"
+    os.environ["SPRS_B200_SPMV_PEER_STORES"] = "tma"
     # ---- host-vector form (e2e): every rank moves only its own slices.  "same cut": x and y
     # sliced like the SpMV's row blocks; "pcie cut": x in equal slices, row blocks re-balanced
     # with 8 bytes of PCIe per y row on top of the SpMV cost (what bench.py's e2e does)
