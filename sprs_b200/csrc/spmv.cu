@@ -277,13 +277,13 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
     sink.accumulate = accumulate;
     sink.stage = nullptr;
     sink.stage_off = 0;
-    // The peers' copies of y (fused all-gather).  A store per finished row to a peer or to the
-    // multicast address slows the ISSUING kernel in proportion to its row count (8 GPUs,
-    // profiles/r2_scale_modes_8gpu_mergepath.txt: +0.03 ms on the dense head rank, +0.16 ms on a
-    // tail rank with 3 M rows, against 0.52 ms of compute): remote stores queue in the LSU in
-    // front of the loads.  So the rows of a tile are staged in shared memory (at most 64 row ends
-    // per tile = 512 bytes per warp) and leave through the TMA instead -- one cp.async.bulk per
-    // target and tile, nothing for the LSU to wait on.  Bulk copies need 16-byte alignment on both
+    // The peers' copies of y (fused all-gather).  A store per finished row and peer slows the
+    // ISSUING kernel in proportion to rows x peers (8 GPUs over IPC mappings,
+    // profiles/r2_scale_modes_8gpu_tma_vs_direct.txt: +0.03 ms on the dense head rank, +0.31 ms
+    // on a tail rank with 3 M rows, against 0.53 ms of compute): remote stores queue in the LSU
+    // in front of the loads.  With stage_rows set, the rows of a tile are staged in shared memory
+    // (at most 64 row ends per tile = 512 bytes per warp) and leave through the TMA instead -- one
+    // cp.async.bulk per target and tile.  Bulk copies need 16-byte alignment on both
     // sides: row r sits at stage[r + par - even base] with par = the parity of the peers' y
     // address (the launcher checked that all targets share it), an odd first / last row goes out
     // as a plain store.
@@ -492,16 +492,23 @@ int launch_variant(sprs_b200_ctx* ctx, const sprs_b200_csmat* m, const double* d
                                             carve));
         configured = true;
     }
-    // peers' rows through the TMA (staged per tile) unless the targets disagree on the parity of
-    // their address (a bulk copy needs 16-byte alignment) or SPRS_B200_SPMV_PEER_STORES=direct
-    // asks for a plain store per row (read per launch: tools/scale_modes.py times both)
+    // How the peers get their rows (8 GPUs, profiles/r2_scale_modes_8gpu_tma_vs_direct.txt):
+    //   * several peer mappings (CUDA IPC / VMM, world-1 targets): staged per tile and sent by
+    //     TMA bulk stores -- 0.718 ms per step against 0.862 with a store per row and target;
+    //   * ONE multicast target: a plain store per row -- 0.601 against 0.639 staged (one store
+    //     per row is cheap enough, and the staged form waits on the TMA between tiles).
+    // Staging also needs all targets to agree on the 16-byte parity of their address.
+    // SPRS_B200_SPMV_PEER_STORES=direct|tma forces one form (read per launch:
+    // tools/scale_modes.py times both).
     int stage_rows = 0;
     if (multi) {
-        stage_rows = SPMV_STAGE_ROWS;
+        stage_rows = yt.n > 2 ? SPMV_STAGE_ROWS : 0;
+        if (const char* e = getenv("SPRS_B200_SPMV_PEER_STORES")) {
+            if (e[0] == 'd') stage_rows = 0;
+            if (e[0] == 't') stage_rows = SPMV_STAGE_ROWS;
+        }
         for (int q = 2; q < yt.n; ++q)
             if ((((uintptr_t)yt.p[q] ^ (uintptr_t)yt.p[1]) >> 3) & 1) stage_rows = 0;
-        if (const char* e = getenv("SPRS_B200_SPMV_PEER_STORES"))
-            if (e[0] == 'd') stage_rows = 0;
     }
     uint64_t grid = (uint64_t)ctx->sm_count * CTAS;
     const uint64_t need = (t1 - t0 + SPMV_NWARPS - 1) / SPMV_NWARPS;

@@ -286,14 +286,17 @@ def test_spmv_linearity_and_scaling_full_size(sp):
         assert abs(float(y1[r]) - ref[0]) <= RTOL * bound + 1e-300
 
 
-@pytest.mark.parametrize("offsets", [(0, 0, 0), (5, 5, 5), (0, 4, 2), (1, 2, 1)])
-def test_spmv_allgather_targets_identical_bits(sp, offsets):
+@pytest.mark.parametrize("offsets", [(0, 0, 0), (5, 5, 5), (0, 4, 2), (1, 2, 1), (0, 3), (2, 2)])
+def test_spmv_allgather_targets_identical_bits(sp, offsets, monkeypatch):
     """sprs_b200_spmv_allgather_dev (the fused all-gather of the multi-GPU path with every target
     on this device): targets 1.. receive the rows of a tile as ONE TMA bulk store from shared
     memory (odd first / last rows as plain stores); every target must hold the plain SpMV's bits,
     and nothing outside the row block may be touched.  Targets whose addresses differ in
-    16-byte parity (last case) take the store-per-row path."""
+    16-byte parity (fourth case) take the store-per-row path; a single remote target (the
+    multicast form) defaults to plain stores, so the two-target cases force the staged form."""
     import ctypes as C
+    if len(offsets) == 2:
+        monkeypatch.setenv("SPRS_B200_SPMV_PEER_STORES", "tma")
     import torch
     from sprs_b200 import generate as G
     ctx = sp.Context.default()
