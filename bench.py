@@ -423,27 +423,11 @@ def main():
     op = make_op(a, bounds)
     rebalanced = 0
     if world > 1:
-        # measured re-balancing with the REAL operator: up to four rounds of equal-time re-cuts
-        for _ in range(4):
-            for _ in range(2):
-                op.step(x)
-            ce0, ce1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            tsum = 0.0
-            for _ in range(4):
-                torch.cuda.synchronize()
-                dist.barrier()
-                ce0.record()
-                op.compute(x)
-                ce1.record()
-                op.exchange()
-                torch.cuda.synchronize()
-                tsum += ce0.elapsed_time(ce1)
-            times = [float(v[0]) for v in comm.allgather_f64([tsum / 4])]
-            if max(times) <= 1.02 * (sum(times) / world):
-                break
-            nb = rebalance_bounds(full.indptr, bounds, times, row_cost=row_cost)
-            if nb == bounds:
-                break
+        # measured re-balancing with the REAL operator: up to four equal-time re-cuts; the cut
+        # with the lowest measured maximum is the one that is timed (a re-cut made from noisy
+        # timings can be worse than the one before it)
+        def rebuild(nb):
+            nonlocal op, a, bounds, r0, r1
             if hasattr(op, "close"):
                 op.close()
             del op, a
@@ -452,7 +436,37 @@ def main():
             r0, r1 = bounds[rank], bounds[rank + 1]
             a = full.slice_rows(r0, r1)
             op = make_op(a, bounds)
+
+        def measure():
+            for _ in range(2):
+                op.step(x)
+            ce0, ce1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tsum = 0.0
+            for _ in range(6):
+                torch.cuda.synchronize()
+                dist.barrier()
+                ce0.record()
+                op.compute(x)
+                ce1.record()
+                op.exchange()
+                torch.cuda.synchronize()
+                tsum += ce0.elapsed_time(ce1)
+            return [float(v[0]) for v in comm.allgather_f64([tsum / 6])]
+
+        best = None  # (max time, bounds)
+        for rnd in range(5):
+            times = measure()
+            if best is None or max(times) < best[0]:
+                best = (max(times), list(bounds))
+            if rnd == 4 or max(times) <= 1.01 * (sum(times) / world):
+                break
+            nb = rebalance_bounds(full.indptr, bounds, times, row_cost=row_cost)
+            if nb == bounds:
+                break
+            rebuild(nb)
             rebalanced += 1
+        if best[1] != list(bounds):
+            rebuild(best[1])
     multicast = bool(getattr(op, "multicast", False))
 
     # ---- parity first, untimed: this rank's WHOLE y against the CPU oracle (every rank)
@@ -656,7 +670,7 @@ def main():
                        "generator": gen, "index_bytes": 4,
                        "partition": "contiguous row blocks balanced on nnz + %.2f*rows "
                                     "(row cost fitted from per-rank timings), then %d measured "
-                                    "equal-time re-cut(s)" % (row_cost, rebalanced),
+                                    "equal-time re-cut(s), the cut with the lowest measured maximum kept" % (row_cost, rebalanced),
                        "collective": ("none" if world == 1 else
                                       (EXCHANGE_TEXT[args.exchange] % target
                                        if args.exchange != "nccl" else EXCHANGE_TEXT["nccl"])),
