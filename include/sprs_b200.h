@@ -270,11 +270,12 @@ uint64_t sprs_b200_symm_bytes(const sprs_b200_symm* buf);
  * equivalents; 0 balances non-zeros only).  Host arrays, indptr width 4 or 8.             */
 int sprs_b200_partition_rows(const void* indptr, int indptr_bytes, uint64_t rows, int nparts,
                              double row_cost, uint64_t* bounds);
-/* How the rows of y reach the other ranks in spmv_rowpart: FUSED = the SpMV kernel stores each
- * finished row into every target itself; PUSH = plain SpMV, then one put kernel copying the
- * rank's slice (coalesced 16-byte stores).  With a multicast-bound y there is ONE remote
- * target (the multicast address: the row leaves the GPU once and the switch replicates it),
- * otherwise world-1 peer mappings.  AUTO = the measured default.            */
+/* How the rows of y reach the other ranks in spmv_rowpart: FUSED = the SpMV kernel delivers the
+ * finished rows itself -- to ONE multicast address when y is multicast-bound (a store per row;
+ * the row leaves the GPU once and the switch replicates it), otherwise to world-1 peer mappings
+ * (the rows of a warp tile staged in shared memory, one TMA bulk store per peer and tile);
+ * PUSH = plain SpMV, then one put kernel copying the rank's slice (coalesced 16-byte stores).
+ * AUTO = the measured default.                                              */
 enum { SPRS_B200_EXCHANGE_AUTO = 0, SPRS_B200_EXCHANGE_FUSED = 1, SPRS_B200_EXCHANGE_PUSH = 2,
        /* OR-ed into `exchange`: leave the closing device barrier to the caller (who then calls
         * sprs_b200_comm_barrier_dev on the same stream before y is read anywhere) */

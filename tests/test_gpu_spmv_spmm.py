@@ -287,8 +287,10 @@ def test_spmv_linearity_and_scaling_full_size(sp):
 
 
 @pytest.mark.parametrize("offsets", [(0, 0, 0), (5, 5, 5), (0, 4, 2), (1, 2, 1), (0, 3), (2, 2)])
-def test_spmv_allgather_targets_identical_bits(sp, offsets, monkeypatch):
-    """sprs_b200_spmv_allgather_dev (the fused all-gather of the multi-GPU path with every target
+def test_spmv_allgather_targets_identical_bits_full_size(sp, offsets, monkeypatch):
+    """(device-generated matrix: hardware only, like the other *_full_size tests; the emulator
+    covers the same entry point through tools/fuzz_emu.py.)
+    sprs_b200_spmv_allgather_dev (the fused all-gather of the multi-GPU path with every target
     on this device): targets 1.. receive the rows of a tile as ONE TMA bulk store from shared
     memory (odd first / last rows as plain stores); every target must hold the plain SpMV's bits,
     and nothing outside the row block may be touched.  Targets whose addresses differ in
