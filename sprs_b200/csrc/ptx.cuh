@@ -1,45 +1,14 @@
-// ptx.cuh -- inline-PTX wrappers shared by the sm_100a kernels: mbarrier + 1-D TMA bulk copy
-// (cp.async.bulk -> SASS UBLKCP), L2 cache policies and hinted global loads.
+// ptx.cuh -- inline-PTX wrappers shared by the sm_100a kernels: L2 cache policies, hinted
+// global loads, and the 1-D TMA bulk store shared -> global (cp.async.bulk -> SASS UBLKCP).
 // (tests/emu/transform.py swaps this header for tests/emu/cuemu_ptx.h.)
 #pragma once
 #include "common.cuh"
 
-// ---- PTX wrappers: mbarrier + 1-D TMA bulk copy + L2 cache policies -------------
-static __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)
-                 : "memory");
-}
-static __device__ __forceinline__ void fence_mbar_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
+// ---- PTX wrappers: L2 cache policies, hinted loads, TMA bulk store -----------------
+// (round 1's mbarrier + cp.async.bulk global->shared ring is gone with the kernel that used it:
+// on this path a staged stream measured no faster than coalesced register loads and cost L1)
 static __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-static __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-static __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LAB_DONE;\n"
-        "bra LAB_WAIT;\n"
-        "LAB_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-static __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
-                                         uint64_t* bar, uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
-        "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-        : "memory");
 }
 static __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;
