@@ -22,6 +22,19 @@ class _FakeEvent:
         return 1.0
 
 
+def _skew_event(rank):
+    """Events for the N > 1 dry runs: rank-dependent, changing "timings" (0.3 or 0.05 per rank,
+    alternating every 6 readings) so that bench.py's measured re-cut loop really re-cuts,
+    rebuilds its operator and falls back to the best cut."""
+    class Ev(_FakeEvent):
+        count = 0
+
+        def elapsed_time(self, other):
+            Ev.count += 1
+            return 1.0 + rank * (0.3 if ((Ev.count - 1) // 6) % 2 == 0 else 0.05)
+    return Ev
+
+
 class _FakeMirror:
     @property
     def h(self):
@@ -174,7 +187,7 @@ def _install_fakes(rank, world, port):
     torch.cuda.set_device = lambda d: None
     torch.cuda.synchronize = lambda *a: None
     torch.cuda.empty_cache = lambda: None
-    torch.cuda.Event = _FakeEvent
+    torch.cuda.Event = _skew_event(rank)
     torch.Tensor.pin_memory = lambda self: self
     real_init = dist.init_process_group
     dist.init_process_group = lambda backend, **k: real_init("gloo")
@@ -309,6 +322,10 @@ def test_bench_n2_control_flow_gloo(exchange):
     assert e2e["matches_device_result"] and e2e["h2d_bytes_per_step"] == 8 * 3000 == e2e["d2h_bytes_per_step"]
     assert len(line["roofline"]["kernel_ms_per_rank"]) == 2
     assert ("NCCL" in line["config"]["collective"]) == (exchange == "nccl")
+    # the skewed stand-in timings must have driven the measured re-cut loop (operator rebuilt)
+    import re
+    recuts = int(re.search(r"then (\d+) measured", line["config"]["partition"]).group(1))
+    assert recuts >= 1, line["config"]["partition"]
 
 
 def _scale_modes_worker(rank, world, port, q):
