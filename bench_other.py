@@ -249,7 +249,18 @@ def extra_spgemm(ctx, G, hbm, dev):
     got_ind = torch.as_tensor(G._DevArray(d_ind.value + 4 * s, e - s, "<i4"),
                               device=dev).cpu().numpy().view(np.uint32)
     blk = A.slice_rows(r0, r1)
-    oip, oind, _ = O.mul_csr_csr((r1 - r0, n), blk.to_host(), (n, n), Bm.to_host(), threads=0)
+    a_host, b_host = blk.to_host(), Bm.to_host()
+    t_cpu = time.perf_counter()
+    oip, oind, _ = O.mul_csr_csr((r1 - r0, n), a_host, (n, n), b_host, threads=0)
+    t_cpu = time.perf_counter() - t_cpu
+    try:  # the same call, timed: the CPU port beside the GPU number (a reported baseline only)
+        b_len = np.diff(b_host[0].astype(np.int64))
+        nprod_blk = int(b_len[a_host[1].astype(np.int64)].sum())
+        cpu = {"value": 2.0 * nprod_blk / t_cpu / 1e9, "unit": "GFLOP/s", "kind": "port",
+               "threads": "the reference's Automatic rule (smmp.rs:210-227)",
+               "sample": "rows %d..%d of A times B: %d products" % (r0, r1, nprod_blk)}
+    except Exception as e:
+        cpu = {"error": repr(e)}
     parity = {"rows_checked": r1 - r0, "nnz_checked": int(e - s),
               "indptr_bit_exact": bool(np.array_equal(got_ip, np.asarray(oip, dtype=np.int64))),
               "indices_bit_exact": bool(np.array_equal(got_ind, np.asarray(oind, dtype=np.uint32)))}
@@ -264,4 +275,5 @@ def extra_spgemm(ctx, G, hbm, dev):
     alg = 12.0 * (A.nnz + nprod + nnz_c) + 8.0 * (n + 1)
     return {"n_prod": nprod, "nnzC": nnz_c, "ms": ms, "gflops": 2.0 * nprod / ms / 1e6,
             "frac_of_roofline": alg / ms / 1e6 / hbm, "parity_vs_oracle": parity,
+            "cpu_baseline": cpu,
             "timing": "host clock around symbolic + numeric (synchronous calls), C left on the device"}
