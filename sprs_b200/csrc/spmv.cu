@@ -22,7 +22,11 @@
 //   * loads: ld.global.nc.L1::no_allocate + L2 evict_first for the matrix (read exactly once),
 //     ld.global.nc + L2 evict_last for x; 40 warps per SM hide the latency;
 //   * the row cut by a tile end leaves its partial in carry[t]; a second tiny kernel adds the
-//     carries in tile order (deterministic, no atomics).
+//     carries in tile order (deterministic, no atomics);
+//   * the multi-target flavour (fused all-gather of the multi-GPU path) also
+//     delivers every finished row to the peers: a plain store into ONE multicast address, or --
+//     several peer mappings -- the tile's rows staged in 528 bytes of shared memory per warp and
+//     sent as one TMA bulk store per peer (the only shared memory in this file).
 // Rows longer than 8 non-zeros use trees and agree with the reference to rounding (parity gate:
 // |d| <= 1e-6 * sum|terms|).  Arithmetic is MulAcc::mul_acc's (mul_acc.rs:28-30):
 // unfused multiply, then add.
