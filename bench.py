@@ -329,9 +329,12 @@ def main():
     ap.add_argument("--no-multicast", action="store_true",
                     help="keep the symmetric buffers on CUDA IPC peer mappings")
     ap.add_argument("--gen-to", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--extra-only", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.gen_to:
         return generate_to_dir(args.workload, args.gen_to)
+    if args.extra_only:
+        return extra_child(args.extra_only)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -632,7 +635,14 @@ def main():
         for name, fn in (("spmv_rand_1m", bench_small_spmv), ("spmm_rand_1m_k64", bench_other.extra_spmm),
                          ("spgemm_rmat_500k", bench_other.extra_spgemm)):
             try:
-                extra[name] = fn(ctx, G, hbm_peak, dev)
+                res = None
+                if name == "spmv_rand_1m":
+                    # a 0.19 ms kernel is the one entry that is sensitive to what the process did
+                    # before it (0.217 ms behind the config-5 legs, 0.186 ms in a process of its
+                    # own, profiles/r2_l2_state_probe.txt): measured in a child process, like
+                    # tools/sweep_spmv.py does; in this process only if the child fails
+                    res = run_extra_in_child(name)
+                extra[name] = res if res is not None else fn(ctx, G, hbm_peak, dev)
             except Exception as e:
                 extra[name] = {"error": repr(e)}
             torch.cuda.empty_cache()
@@ -701,6 +711,38 @@ def main():
             op.close()
         comm.close()
         dist.destroy_process_group()
+
+
+def extra_child(name):
+    """Child-process entry (`bench.py --extra-only NAME`): one entry of `extra` measured in a
+    process of its own; prints its JSON on the last line."""
+    import torch
+    import sprs_b200 as sp
+    from sprs_b200 import generate as G
+    if name != "spmv_rand_1m":
+        raise SystemExit("unknown extra %r" % name)
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    ctx = sp.Context.default(local)
+    peaks, _ = measured_peaks()
+    out = bench_small_spmv(ctx, G, float(peaks["hbm_gbs"]), torch.device("cuda", local))
+    out["process"] = "child process of bench.py (nothing else ran in it)"
+    print(json.dumps(out))
+    return 0
+
+
+def run_extra_in_child(name, timeout=600):
+    """None when the child did not deliver (the caller then measures in-process)."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--extra-only", name],
+                           capture_output=True, text=True, timeout=timeout)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return None
+        res = json.loads(lines[-1])
+        return res if isinstance(res, dict) and "ms" in res else None
+    except Exception:
+        return None
 
 
 def bench_small_spmv(ctx, G, hbm_peak, dev):

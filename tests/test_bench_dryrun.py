@@ -352,3 +352,26 @@ def test_scale_modes_control_flow_gloo_world2():
     assert [d for d in lines if "skipped" in d][0]["mode"] == "push+mc"   # the stand-in has no multicast
     assert any("partition_round" in d for d in lines) and any("setup_seconds" in d for d in lines)
     assert sum(1 for d in lines if "e2e_host_slices" in d and d.get("correct")) == 3   # same cut x2, pcie cut
+
+
+def test_extra_child_entry_and_parent_parse(fake_gpu, monkeypatch, capsys):
+    """`bench.py --extra-only spmv_rand_1m` (the config-2 extra in a process of its own): the child
+    entry prints one JSON object with the entry's keys; the parent takes the last JSON line of a
+    successful child and returns None (-> in-process measurement) for anything else."""
+    import subprocess
+    import bench
+    assert bench.extra_child("spmv_rand_1m") == 0
+    out = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+    child = json.loads(out[-1])
+    assert child["ms"] > 0 and child["parity_vs_oracle"]["ok"] and "child process" in child["process"]
+
+    def fake_run(rc, stdout):
+        return lambda *a, **k: subprocess.CompletedProcess(a, rc, stdout=stdout, stderr="")
+    monkeypatch.setattr(subprocess, "run", fake_run(0, "noise\n" + out[-1] + "\n"))
+    assert bench.run_extra_in_child("spmv_rand_1m")["ms"] == child["ms"]
+    monkeypatch.setattr(subprocess, "run", fake_run(1, out[-1]))
+    assert bench.run_extra_in_child("spmv_rand_1m") is None
+    monkeypatch.setattr(subprocess, "run", fake_run(0, "no json here"))
+    assert bench.run_extra_in_child("spmv_rand_1m") is None
+    monkeypatch.setattr(subprocess, "run", fake_run(0, '{"error": "x"}'))
+    assert bench.run_extra_in_child("spmv_rand_1m") is None
